@@ -1,0 +1,143 @@
+/* jolt_b200.h - C ABI of the B200 (sm_100a) backend for the a16z/jolt prover hot path.
+ *
+ * The reference (a16z/jolt @ ff9f8c13) has no FFI today: its compute seam is a set of Rust
+ * traits. Each entry point below names the reference interface it replaces (file:line under
+ * /root/reference); INTEGRATION.md shows the Rust-side binding a maintainer would add.
+ *
+ * Conventions (specs/clean-slate-prover.md:565-591):
+ *  - Field elements are 4 x uint64_t little-endian Montgomery limbs (a * 2^256 mod p), exactly
+ *    `Fr::inner_limbs()` (crates/jolt-field/src/bn254/mod.rs:33-42). Every output is canonical
+ *    (fully reduced, < p).
+ *  - G1 points cross the ABI as affine (x, y) = 8 limbs over Fq (Montgomery); the identity is
+ *    x = y = 0. Jacobian inputs/outputs are 12 limbs (X, Y, Z), identity Z = 0
+ *    (`Bn254G1` = repr(transparent) G1Projective, crates/jolt-crypto/src/ec/bn254/mod.rs:17-24).
+ *  - Host buffers are borrowed for the duration of the call. Device state lives in a context
+ *    (one per ProofSession, crates/jolt-kernels/src/backend.rs:283-286) and is freed with it.
+ *  - Every function returns a jb_status; nothing unwinds or aborts across the ABI
+ *    (maps to KernelError / SumcheckError, crates/jolt-kernels/src/error.rs:80-89).
+ *  - A context serialises its calls with an internal mutex; distinct contexts are independent
+ *    (Rayon threads call msm concurrently, crates/jolt-hyperkzg/src/scheme.rs:141-145).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point returns
+ *    JB_ERR_NO_DEVICE.
+ */
+#ifndef JOLT_B200_H
+#define JOLT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum jb_status {
+    JB_OK = 0,
+    JB_ERR_NO_DEVICE = 1,    /* no CUDA device / driver */
+    JB_ERR_CUDA = 2,         /* a CUDA call failed (see jb_last_error) */
+    JB_ERR_INVALID = 3,      /* KernelError::InvariantViolation: bad handle, length, order ... */
+    JB_ERR_OOM = 4,          /* device allocation failed (recoverable at plan time) */
+    JB_ERR_ROUND_CHECK = 5,  /* SumcheckError::RoundCheckFailed: s(0)+s(1) != previous_claim */
+    JB_ERR_UNSUPPORTED = 6,  /* KernelError::Unsupported */
+    JB_ERR_LENGTH = 7        /* msm: bases/scalars length mismatch (mod.rs:200-204) */
+} jb_status;
+
+/* BindingOrder, crates/jolt-poly/src/lib.rs (HighToLow pairs (i, i+half); LowToHigh (2i, 2i+1)). */
+typedef enum jb_order { JB_HIGH_TO_LOW = 0, JB_LOW_TO_HIGH = 1 } jb_order;
+
+typedef struct jb_ctx jb_ctx;       /* ~ ProofSession: device pools + stream */
+typedef struct jb_member jb_member; /* ~ Box<dyn SumcheckKernel>: a ProveRounds member on device */
+typedef uint64_t jb_table;          /* device-resident Polynomial<Fr> / DensePolynomial<Fr> */
+typedef uint64_t jb_srs;            /* device-resident affine G1 bases (HyperKZGProverSetup::g1_powers) */
+
+/* ---- library / context ---------------------------------------------------------------- */
+const char* jb_version(void);
+const char* jb_status_str(int status);
+int jb_device_count(void);
+/* ProofSession::new - owns a stream and memory pools on `device`. */
+int jb_ctx_create(int device, jb_ctx** out);
+/* Same, but enqueues on a caller-owned cudaStream_t (e.g. torch's current stream). */
+int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out);
+void jb_ctx_destroy(jb_ctx* ctx);
+const char* jb_last_error(jb_ctx* ctx);
+int jb_ctx_synchronize(jb_ctx* ctx);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches claim). */
+uint64_t jb_ctx_launch_count(jb_ctx* ctx);
+
+/* ---- tables: Polynomial<Fr>::new (crates/jolt-poly/src/dense.rs:35-60),
+ *      DensePolynomial::new (crates/jolt-prover-legacy/src/poly/dense_mlpoly.rs:27-39) --------- */
+int jb_table_upload(jb_ctx* ctx, const uint64_t* mont_limbs, size_t len, jb_table* out);
+int jb_table_alloc(jb_ctx* ctx, size_t len, jb_table* out);
+/* Borrow caller-owned device memory (len * 32 bytes, 32-byte aligned); never freed by the context. */
+int jb_table_wrap_device(jb_ctx* ctx, void* device_ptr, size_t len, jb_table* out);
+int jb_table_len(jb_ctx* ctx, jb_table t, size_t* len);
+int jb_table_device_ptr(jb_ctx* ctx, jb_table t, void** device_ptr);
+int jb_table_download(jb_ctx* ctx, jb_table t, uint64_t* out_limbs, size_t len);
+int jb_table_clone(jb_ctx* ctx, jb_table t, jb_table* out);
+int jb_table_free(jb_ctx* ctx, jb_table t);
+
+/* Polynomial::bind_with_order (crates/jolt-poly/src/dense.rs:180-263); legacy
+ * DensePolynomial::bind / bind_parallel (dense_mlpoly.rs:71-83). Halves the table.
+ * `r` = Montgomery limbs of the challenge; limbs [0,0,lo,hi] (the 125-bit MontU128Challenge,
+ * crates/jolt-prover-legacy/src/field/challenge/mont_ark_u128.rs:28-34) take the half-cost path. */
+int jb_table_bind(jb_ctx* ctx, jb_table t, const uint64_t r[4], int order);
+
+/* EqPolynomial::evals(r, scaling_factor) (crates/jolt-poly/src/eq.rs:221-231): 2^nvars entries,
+ * r[0] <-> most-significant index bit. scale_or_null == NULL means 1. */
+int jb_eq_evals(jb_ctx* ctx, const uint64_t* r, size_t nvars, const uint64_t* scale_or_null, jb_table* out);
+/* EqPolynomial::evals_for_aligned_block (eq.rs:238-263): the per-GPU slice of a sharded eq table. */
+int jb_eq_evals_aligned_block(jb_ctx* ctx, const uint64_t* r, size_t nvars, size_t start_index,
+                              size_t block_size, jb_table* out);
+
+/* ---- sumcheck member: ProveRounds (crates/jolt-sumcheck/src/prover.rs:52-72) for the
+ *      product-of-m-tables relation, degree m (naive.rs:241-316; tests/roundtrip.rs:26-97) ------- */
+/* Takes ownership of the m tables (all the same power-of-two length). m in 1..4. */
+int jb_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, int order, jb_member** out);
+int jb_member_num_rounds(jb_member* mem, size_t* rounds);
+int jb_member_degree(jb_member* mem, size_t* degree);
+/* prove_round(bind, round, previous_claim): binds `bind_or_null` (NULL on the first active round)
+ * and returns the evaluations s(0..degree) (degree+1 elements) of the round polynomial, fused in
+ * one pass over the tables. Returns JB_ERR_ROUND_CHECK if s(0)+s(1) != previous_claim
+ * (naive.rs:301-308); pass previous_claim_or_null == NULL to skip the check. */
+int jb_member_prove_round(jb_member* mem, const uint64_t* bind_or_null, size_t round,
+                          const uint64_t* previous_claim_or_null, uint64_t* out_evals);
+/* finish_rounds(bind): the terminal bind. */
+int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]);
+/* The m fully bound table values (SumcheckKernel::output_claims, kernel.rs:72-126). */
+int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
+/* Multi-GPU: like prove_round but leaves this rank's degree+1 partial sums on the device as
+ * (degree+1) x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32
+ * ranks); the caller all-reduces that buffer and calls jb_partials_finalize. No round check. */
+int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null, size_t round,
+                                   void* device_lanes_out);
+int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
+void jb_member_destroy(jb_member* mem);
+
+/* ---- G1 MSM: JoltGroup::msm (crates/jolt-crypto/src/ec/group.rs:70; impl
+ *      ec/bn254/mod.rs:195-212) and kzg_commit (crates/jolt-hyperkzg/src/kzg.rs:15-27) ------- */
+/* Upload bases once per ProverSetup (HyperKZGProverSetup::g1_powers, scheme.rs:60-66). */
+int jb_srs_upload_affine(jb_ctx* ctx, const uint64_t* xy_limbs, size_t n, jb_srs* out);
+/* Jacobian bases as JoltGroup::msm receives them; normalised on device (batch inversion). */
+int jb_srs_upload_jacobian(jb_ctx* ctx, const uint64_t* xyz_limbs, size_t n, jb_srs* out);
+int jb_srs_len(jb_ctx* ctx, jb_srs s, size_t* n);
+int jb_srs_download_affine(jb_ctx* ctx, jb_srs s, uint64_t* out_xy, size_t n);
+int jb_srs_free(jb_ctx* ctx, jb_srs s);
+/* sum_i scalars[i] * bases[offset + i], i < n; scalars = host Montgomery limbs. Result as Jacobian
+ * X, Y, Z (Z = 1, or Z = 0 for the identity). n == 0 -> identity (group_laws.rs:143-146);
+ * offset + n > srs length -> JB_ERR_LENGTH (mod.rs:200-204). */
+int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
+/* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
+int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
+
+/* ---- raw element-wise ops (parity harness for bn254_differential.rs:75-99) -----------------
+ * field: 0 = Fr, 1 = Fq; op: 0 add, 1 sub, 2 mul, 3 mul-by-[0,0,lo,hi]. Host buffers. */
+int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* ---- diagnostics (no reference counterpart): sustained Montgomery-product rate of the integer
+ * pipes, used for the ALU ceiling quoted beside the HBM roofline in DESIGN.md.
+ * variant: 0 full product, 1 product by a [0,0,lo,hi] challenge, 2 add/sub. Giga-ops/s out. */
+int jb_diag_mul_throughput(jb_ctx* ctx, int field, int variant, int iters, int blocks, double* out_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOLT_B200_H */

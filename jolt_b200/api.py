@@ -1,0 +1,365 @@
+"""Python mirror of the reference's operator surface for the hot path, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference so that the parity tests read
+like its own (crates/jolt-poly/src/dense.rs, eq.rs, univariate.rs; crates/jolt-sumcheck/src/prover.rs).
+All table-sized data stays on the device; only O(rounds * degree) values cross back."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field as dc_field
+
+import numpy as np
+
+from . import _lib
+from . import field as F
+from ._lib import JoltB200Error, c_u64p
+
+HIGH_TO_LOW = 0  # BindingOrder::HighToLow - pairs (i, i + half)
+LOW_TO_HIGH = 1  # BindingOrder::LowToHigh - pairs (2i, 2i + 1)
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_u64p)
+
+
+def _limbs(x) -> np.ndarray:
+    """Accepts a Python int (canonical value) or 4 Montgomery limbs."""
+    if isinstance(x, (int, np.integer)):
+        return F.to_limbs(int(x))
+    a = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1)
+    assert a.size == 4, "field element = 4 x u64 Montgomery limbs"
+    return a
+
+
+class SumcheckError(RuntimeError):
+    """Mirrors jolt_sumcheck::SumcheckError (crates/jolt-sumcheck/src/error.rs)."""
+
+
+class Session:
+    """Device half of ProofSession (crates/jolt-kernels/src/backend.rs:283-286)."""
+
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        if cuda_stream is None:
+            st = self.lib.jb_ctx_create(device, ctypes.byref(h))
+        else:
+            st = self.lib.jb_ctx_create_on_stream(device, ctypes.c_void_p(cuda_stream), ctypes.byref(h))
+        if st != _lib.JB_OK:
+            raise JoltB200Error(st, self.lib.jb_status_str(st).decode())
+        self.h = h
+        self.device = device
+
+    def check(self, st: int):
+        if st != _lib.JB_OK:
+            detail = self.lib.jb_last_error(self.h).decode() or self.lib.jb_status_str(st).decode()
+            if st == _lib.JB_ERR_ROUND_CHECK:
+                raise SumcheckError(detail)
+            raise JoltB200Error(st, detail)
+
+    def synchronize(self):
+        self.check(self.lib.jb_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.jb_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.jb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # element-wise parity harness (bn254_differential.rs:75-99)
+    def vec_op(self, field: int, op: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty_like(a)
+        self.check(self.lib.jb_vec_op(self.h, field, op, _p(a), _p(b), _p(out), a.shape[0]))
+        return out
+
+
+class Polynomial:
+    """Device-resident multilinear polynomial in evaluation form
+    (jolt_poly::Polynomial<Fr>, dense.rs:35; legacy DensePolynomial, dense_mlpoly.rs:20)."""
+
+    def __init__(self, session: Session, handle: int):
+        self.s = session
+        self.handle = handle
+
+    @classmethod
+    def new(cls, session: Session, evals_limbs: np.ndarray) -> "Polynomial":
+        a = np.ascontiguousarray(evals_limbs, dtype=np.uint64).reshape(-1, 4)
+        n = a.shape[0]
+        if n == 0 or n & (n - 1):
+            raise ValueError(f"Dense multi-linear polynomials must be made from a power of 2 (not {n})")
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_table_upload(session.h, _p(a), n, ctypes.byref(h)))
+        return cls(session, h.value)
+
+    @classmethod
+    def from_ints(cls, session: Session, values) -> "Polynomial":
+        return cls.new(session, F.ints_to_limbs(values))
+
+    @classmethod
+    def wrap_device(cls, session: Session, device_ptr: int, length: int) -> "Polynomial":
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_table_wrap_device(session.h, ctypes.c_void_p(device_ptr), length, ctypes.byref(h)))
+        return cls(session, h.value)
+
+    def __len__(self) -> int:
+        n = ctypes.c_size_t()
+        self.s.check(self.s.lib.jb_table_len(self.s.h, self.handle, ctypes.byref(n)))
+        return n.value
+
+    def num_vars(self) -> int:
+        return len(self).bit_length() - 1
+
+    def device_ptr(self) -> int:
+        p = ctypes.c_void_p()
+        self.s.check(self.s.lib.jb_table_device_ptr(self.s.h, self.handle, ctypes.byref(p)))
+        return p.value
+
+    def bind_with_order(self, scalar, order: int = HIGH_TO_LOW) -> None:
+        r = _limbs(scalar)
+        self.s.check(self.s.lib.jb_table_bind(self.s.h, self.handle, _p(r), order))
+
+    def bind(self, scalar, order: int = HIGH_TO_LOW) -> None:
+        """Polynomial::bind == HighToLow (dense.rs:169-171); the legacy signature passes the order."""
+        self.bind_with_order(scalar, order)
+
+    bind_parallel = bind  # legacy DensePolynomial::bind_parallel (dense_mlpoly.rs:78)
+
+    def clone(self) -> "Polynomial":
+        h = ctypes.c_uint64()
+        self.s.check(self.s.lib.jb_table_clone(self.s.h, self.handle, ctypes.byref(h)))
+        return Polynomial(self.s, h.value)
+
+    def evals(self) -> np.ndarray:
+        n = len(self)
+        out = np.empty((n, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_table_download(self.s.h, self.handle, _p(out), n))
+        return out
+
+    def to_ints(self) -> list[int]:
+        return F.limbs_to_ints(self.evals())
+
+    def free(self):
+        if self.handle:
+            self.s.check(self.s.lib.jb_table_free(self.s.h, self.handle))
+            self.handle = 0
+
+
+class EqPolynomial:
+    """jolt_poly::EqPolynomial (eq.rs:24): tables in big-endian index order (r[0] <-> MSB)."""
+
+    @staticmethod
+    def evals(session: Session, r_limbs, scaling_factor=None) -> Polynomial:
+        r = np.ascontiguousarray(r_limbs, dtype=np.uint64).reshape(-1, 4)
+        sc = None if scaling_factor is None else _limbs(scaling_factor)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_eq_evals(session.h, _p(r) if r.shape[0] else None, r.shape[0],
+                                               _p(sc) if sc is not None else None, ctypes.byref(h)))
+        return Polynomial(session, h.value)
+
+    @staticmethod
+    def evals_for_aligned_block(session: Session, r_limbs, start_index: int, block_size: int) -> Polynomial:
+        r = np.ascontiguousarray(r_limbs, dtype=np.uint64).reshape(-1, 4)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_eq_evals_aligned_block(session.h, _p(r), r.shape[0], start_index, block_size,
+                                                             ctypes.byref(h)))
+        return Polynomial(session, h.value)
+
+
+class UnivariatePoly:
+    """jolt_poly::UnivariatePoly (univariate.rs:27): coefficients ascending, values as ints mod r.
+    Stays on the host in the reference too (O(d^2) work on <= ~10 elements)."""
+
+    def __init__(self, coefficients: list[int]):
+        self.coefficients = [c % F.R_MOD for c in coefficients]
+
+    def degree(self) -> int:
+        return max(len(self.coefficients) - 1, 0)
+
+    def evaluate(self, point: int) -> int:
+        acc = 0
+        for c in reversed(self.coefficients):
+            acc = (acc * point + c) % F.R_MOD
+        return acc
+
+    @classmethod
+    def from_evals(cls, evals: list[int]) -> "UnivariatePoly":
+        """Interpolation on nodes 0..n-1 (univariate.rs:198-202). Newton forward differences
+        (exact in the field; value-equal to the reference's Vandermonde solve)."""
+        p = F.R_MOD
+        n = len(evals)
+        diffs = [e % p for e in evals]
+        newton = []
+        for k in range(n):
+            newton.append(diffs[0])
+            diffs = [(diffs[i + 1] - diffs[i]) % p for i in range(len(diffs) - 1)]
+        # p(x) = sum_k newton[k] * C(x, k); expand the falling factorials
+        coeffs = [0] * n
+        basis = [1]  # x(x-1)...(x-k+1) coefficients
+        fact_inv = 1
+        for k in range(n):
+            if k:
+                fact_inv = fact_inv * pow(k, -1, p) % p
+            scale = newton[k] * fact_inv % p
+            for i, b in enumerate(basis):
+                coeffs[i] = (coeffs[i] + scale * b) % p
+            nxt = [0] * (len(basis) + 1)
+            for i, b in enumerate(basis):  # multiply by (x - k)
+                nxt[i + 1] = (nxt[i + 1] + b) % p
+                nxt[i] = (nxt[i] - k * b) % p
+            basis = nxt
+        return cls(coeffs)
+
+    @classmethod
+    def from_evals_and_hint(cls, hint: int, evals: list[int]) -> "UnivariatePoly":
+        full = list(evals)
+        full.insert(1, (hint - full[0]) % F.R_MOD)
+        return cls.from_evals(full)
+
+    def compress(self) -> list[int]:
+        assert len(self.coefficients) >= 2, "cannot compress a polynomial of degree < 1"
+        return self.coefficients[:1] + self.coefficients[2:]
+
+    def __eq__(self, other):
+        return isinstance(other, UnivariatePoly) and self.coefficients == other.coefficients
+
+    def __repr__(self):
+        return f"UnivariatePoly({[hex(c) for c in self.coefficients]})"
+
+
+class ProductMember:
+    """A device-backed ProveRounds member (prover.rs:52-72) for the relation
+    sum_x prod_j f_j(x) over m dense tables, degree m - the GPU twin of the reference tier's
+    NaiveSumcheckProver (naive.rs:241-316) / tests' DenseMember (tests.rs:1123-1175, m = 1)."""
+
+    def __init__(self, session: Session, polys: list[Polynomial], order: int = HIGH_TO_LOW):
+        self.s = session
+        handles = np.array([p.handle for p in polys], dtype=np.uint64)
+        h = ctypes.c_void_p()
+        session.check(session.lib.jb_member_create(session.h, _p(handles), len(polys), order, ctypes.byref(h)))
+        for p in polys:
+            p.handle = 0  # ownership moved into the member
+        self.h = h
+        self.m = len(polys)
+
+    def num_rounds(self) -> int:
+        n = ctypes.c_size_t()
+        self.s.check(self.s.lib.jb_member_num_rounds(self.h, ctypes.byref(n)))
+        return n.value
+
+    def degree(self) -> int:
+        return self.m
+
+    def prove_round_evals(self, bind, rnd: int, previous_claim=None) -> list[int]:
+        b = None if bind is None else _limbs(bind)
+        c = None if previous_claim is None else _limbs(previous_claim)
+        out = np.empty((self.m + 1, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_member_prove_round(self.h, _p(b) if b is not None else None, rnd,
+                                                      _p(c) if c is not None else None, _p(out)))
+        return F.limbs_to_ints(out)
+
+    def prove_round(self, bind, rnd: int, previous_claim) -> UnivariatePoly:
+        return UnivariatePoly.from_evals(self.prove_round_evals(bind, rnd, previous_claim))
+
+    def finish_rounds(self, bind) -> None:
+        self.s.check(self.s.lib.jb_member_finish_rounds(self.h, _p(_limbs(bind))))
+
+    def final_evals(self) -> list[int]:
+        out = np.empty((self.m, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_member_final_evals(self.h, _p(out)))
+        return F.limbs_to_ints(out)
+
+    def close(self):
+        if self.h:
+            self.s.lib.jb_member_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class BatchMember:
+    """jolt_sumcheck::BatchMember (batch.rs:24-71)."""
+    input_claim: int
+    coefficient: int
+    rounds: int
+    offset: int = 0
+
+
+@dataclass
+class ProvedBatch:
+    """prover.rs:153-157 (+ the per-round batched polynomials the recorder saw)."""
+    challenges: list[int]
+    final_claim: int
+    member_claims: list[int]
+    round_polynomials: list[UnivariatePoly] = dc_field(default_factory=list)
+
+
+def prove_batch(members_desc: list[BatchMember], members: list, max_num_vars: int, max_degree: int, claimed_sum: int,
+                absorb_round) -> ProvedBatch:
+    """Host engine, line-for-line semantics of prove_batch (prover.rs:193-362); `absorb_round(round,
+    UnivariatePoly) -> challenge` stands in for recorder.absorb_round + the transcript, which stay
+    host-side (Fiat-Shamir is the only forced device sync per round, specs/clean-slate-prover.md:579-582)."""
+    p = F.R_MOD
+    if len(members) != len(members_desc):
+        raise SumcheckError(f"BatchMemberCountMismatch {{ expected: {len(members_desc)}, got: {len(members)} }}")
+    for i, (m, d) in enumerate(zip(members, members_desc)):
+        if m.num_rounds() != d.rounds:
+            raise SumcheckError(f"BatchMemberRoundsMismatch {{ member: {i}, expected: {d.rounds}, got: {m.num_rounds()} }}")
+        if d.offset + d.rounds > max_num_vars:
+            raise SumcheckError(f"BatchMemberWindowOutOfRange {{ member: {i} }}")
+    if max_num_vars > 0 and max_degree < 1:
+        raise SumcheckError(f"ZeroBatchDegree {{ max_num_vars: {max_num_vars} }}")
+    two_inv = pow(2, -1, p)
+    claims = [d.input_claim * pow(2, max_num_vars - d.rounds, p) % p for d in members_desc]
+    running = claimed_sum % p
+    challenges: list[int] = []
+    pending: list[int | None] = [None] * len(members)
+    polys: list[UnivariatePoly] = []
+    for rnd in range(max_num_vars):
+        batched = [0] * (max_degree + 1)
+        work = []
+        for i, (m, d) in enumerate(zip(members, members_desc)):
+            active = d.offset <= rnd < d.offset + d.rounds
+            if not active:
+                claims[i] = claims[i] * two_inv % p
+                batched[0] = (batched[0] + d.coefficient * claims[i]) % p
+                continue
+            b, pending[i] = pending[i], None
+            work.append((i, m.prove_round(b, rnd - d.offset, claims[i])))
+        for i, poly in work:
+            if poly.degree() > max_degree:
+                raise SumcheckError(f"DegreeBoundExceeded {{ got: {poly.degree()}, max: {max_degree} }}")
+            for k, c in enumerate(poly.coefficients):
+                batched[k] = (batched[k] + members_desc[i].coefficient * c) % p
+        while len(batched) > 2 and batched[-1] == 0:  # trim_round_polynomial
+            batched.pop()
+        bp = UnivariatePoly(batched)
+        if (bp.evaluate(0) + bp.evaluate(1)) % p != running:
+            raise SumcheckError(f"RoundCheckFailed {{ round: {rnd} }}")
+        c = absorb_round(rnd, bp) % p
+        running = bp.evaluate(c)
+        challenges.append(c)
+        polys.append(bp)
+        for i, poly in work:
+            claims[i] = poly.evaluate(c)
+            pending[i] = c
+    for m, b in zip(members, pending):
+        if b is not None:
+            m.finish_rounds(b)
+    return ProvedBatch(challenges, running, claims, polys)

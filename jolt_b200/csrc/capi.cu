@@ -1,0 +1,702 @@
+// C ABI of the B200 backend (see include/jolt_b200.h for the per-function reference citations).
+// The context mirrors ProofSession (crates/jolt-kernels/src/backend.rs:283-286): it owns the
+// stream, the stream-ordered device pool, and the small reduction / staging buffers.
+#include "../../include/jolt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ctx.hpp"
+#include "host_fr.hpp"
+#include "poly_kernels.cuh"
+
+using namespace jb;
+
+namespace {
+
+struct Guard {
+    jb_ctx* c;
+    std::lock_guard<std::mutex> lk;
+    explicit Guard(jb_ctx* ctx) : c(ctx), lk(ctx->mu) { cudaSetDevice(ctx->device); }
+};
+
+BindScalar make_scalar(const uint64_t r[4], bool* hi4) {
+    BindScalar s;
+    for (int i = 0; i < 4; ++i) {
+        s.w[2 * i] = (uint32_t)r[i];
+        s.w[2 * i + 1] = (uint32_t)(r[i] >> 32);
+    }
+    *hi4 = (r[0] == 0 && r[1] == 0);
+    return s;
+}
+
+bool canonical_fr(const uint64_t r[4]) { return !HostFr::geq_p(r); }
+
+template <typename K>
+int blocks_per_sm(K kernel) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+int grid_for(jb_ctx* c, size_t items, int per_sm) {
+    size_t need = (items + 255) / 256;
+    size_t cap = (size_t)c->sm_count * per_sm;
+    if (cap > JB_MAX_PARTIAL_BLOCKS) cap = JB_MAX_PARTIAL_BLOCKS;
+    size_t g = need < cap ? need : cap;
+    return g < 1 ? 1 : (int)g;
+}
+
+template <int ORDER, bool HI4>
+int launch_bind(jb_ctx* c, const uint64_t* in, uint64_t* out, size_t half, const BindScalar& s) {
+    static int per_sm = blocks_per_sm(bind_kernel<ORDER, HI4>);
+    int grid = grid_for(c, half, per_sm);
+    bind_kernel<ORDER, HI4><<<grid, 256, 0, c->stream>>>(in, out, half, s);
+    c->launches++;
+    return c->check(cudaGetLastError(), "bind_kernel launch");
+}
+
+// Halves one table under `r` (Polynomial::bind_with_order).
+int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
+    if (t.len < 2 || (t.len & (t.len - 1))) return c->fail(JB_ERR_INVALID, "bind: table length must be a power of two >= 2");
+    if (!canonical_fr(r)) return c->fail(JB_ERR_INVALID, "bind: challenge limbs not canonical (>= r)");
+    bool hi4;
+    BindScalar s = make_scalar(r, &hi4);
+    size_t half = t.len / 2;
+    int st;
+    if (order == JB_HIGH_TO_LOW) {
+        st = hi4 ? launch_bind<ORDER_HIGH_TO_LOW, true>(c, t.buf, t.buf, half, s)
+                 : launch_bind<ORDER_HIGH_TO_LOW, false>(c, t.buf, t.buf, half, s);
+    } else if (order == JB_LOW_TO_HIGH) {
+        if ((st = c->ensure_alt(t, half)) != JB_OK) return st;
+        st = hi4 ? launch_bind<ORDER_LOW_TO_HIGH, true>(c, t.buf, t.alt, half, s)
+                 : launch_bind<ORDER_LOW_TO_HIGH, false>(c, t.buf, t.alt, half, s);
+        if (st == JB_OK) t.swap_buffers();
+    } else {
+        return c->fail(JB_ERR_INVALID, "bind: unknown binding order");
+    }
+    if (st == JB_OK) t.len = half;
+    return st;
+}
+
+template <int M, int ORDER, bool BIND, bool HI4>
+int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, int* grid_out) {
+    static int per_sm = blocks_per_sm(fused_round_kernel<M, ORDER, BIND, HI4>);
+    int grid = grid_for(c, pairs, per_sm);
+    fused_round_kernel<M, ORDER, BIND, HI4><<<grid, 256, 0, c->stream>>>(tp, pairs, s, c->d_partial);
+    c->launches++;
+    *grid_out = grid;
+    return c->check(cudaGetLastError(), "fused_round_kernel launch");
+}
+
+template <int M, int ORDER>
+int dispatch_fused2(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
+                    int* grid) {
+    if (!bind) return launch_fused<M, ORDER, false, false>(c, tp, pairs, s, grid);
+    return hi4 ? launch_fused<M, ORDER, true, true>(c, tp, pairs, s, grid)
+               : launch_fused<M, ORDER, true, false>(c, tp, pairs, s, grid);
+}
+
+template <int M>
+int dispatch_fused1(jb_ctx* c, int order, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
+                    const BindScalar& s, int* grid) {
+    return order == JB_HIGH_TO_LOW ? dispatch_fused2<M, ORDER_HIGH_TO_LOW>(c, tp, pairs, bind, hi4, s, grid)
+                                   : dispatch_fused2<M, ORDER_LOW_TO_HIGH>(c, tp, pairs, bind, hi4, s, grid);
+}
+
+int dispatch_fused(jb_ctx* c, int m, int order, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
+                   const BindScalar& s, int* grid) {
+    switch (m) {
+        case 1: return dispatch_fused1<1>(c, order, tp, pairs, bind, hi4, s, grid);
+        case 2: return dispatch_fused1<2>(c, order, tp, pairs, bind, hi4, s, grid);
+        case 3: return dispatch_fused1<3>(c, order, tp, pairs, bind, hi4, s, grid);
+        case 4: return dispatch_fused1<4>(c, order, tp, pairs, bind, hi4, s, grid);
+        default: return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
+    }
+}
+
+// eq table for `nvars` variables (device r), scale from device pointer or null; recursive prefix.
+int eq_build(jb_ctx* c, const uint64_t* d_r, size_t nvars, const uint64_t* d_scale, uint64_t* d_out) {
+    if (nvars <= (size_t)EQ_BLOCK_VARS) {
+        eq_expand_kernel<<<1, 256, 0, c->stream>>>(nullptr, d_scale, d_r, (int)nvars, d_out);
+        c->launches++;
+        return c->check(cudaGetLastError(), "eq_expand_kernel launch");
+    }
+    size_t hi_vars = nvars - EQ_BLOCK_VARS;
+    uint64_t* d_prefix = nullptr;
+    int st = c->dev_alloc((void**)&d_prefix, ((size_t)1 << hi_vars) * 32);
+    if (st != JB_OK) return st;
+    st = eq_build(c, d_r, hi_vars, d_scale, d_prefix);
+    if (st == JB_OK) {
+        eq_expand_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, nullptr, d_r + 4 * hi_vars,
+                                                                                EQ_BLOCK_VARS, d_out);
+        c->launches++;
+        st = c->check(cudaGetLastError(), "eq_expand_kernel launch");
+    }
+    c->dev_free(d_prefix);
+    return st;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* jb_version(void) { return "jolt_b200 0.1 (sm_100a)"; }
+
+const char* jb_status_str(int status) {
+    switch (status) {
+        case JB_OK: return "ok";
+        case JB_ERR_NO_DEVICE: return "no CUDA device (this backend has no CPU fallback)";
+        case JB_ERR_CUDA: return "CUDA error";
+        case JB_ERR_INVALID: return "invariant violation";
+        case JB_ERR_OOM: return "device out of memory";
+        case JB_ERR_ROUND_CHECK: return "sumcheck round check failed: s(0)+s(1) != previous_claim";
+        case JB_ERR_UNSUPPORTED: return "unsupported";
+        case JB_ERR_LENGTH: return "msm: bases/scalars length mismatch";
+        default: return "unknown status";
+    }
+}
+
+int jb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
+    if (!out) return JB_ERR_INVALID;
+    *out = nullptr;
+    int n = jb_device_count();
+    if (n <= 0) return JB_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return JB_ERR_INVALID;
+    jb_ctx* c = new (std::nothrow) jb_ctx();
+    if (!c) return JB_ERR_OOM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return JB_ERR_CUDA; }
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+        c->owns_stream = false;
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JB_ERR_CUDA; }
+        c->owns_stream = true;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->sm_count = prop.multiProcessorCount;
+    // keep freed blocks in the pool (ProofSession "device memory pools")
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    bool ok = cudaMalloc((void**)&c->d_partial, (size_t)JB_MAX_PARTIAL_BLOCKS * JB_MAX_EVALS * 32) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_small, JB_SMALL_BYTES) == cudaSuccess &&
+              cudaMallocHost((void**)&c->h_small, JB_SMALL_BYTES) == cudaSuccess;
+    if (!ok) {
+        jb_ctx_destroy(c);
+        return JB_ERR_OOM;
+    }
+    *out = c;
+    return JB_OK;
+}
+
+int jb_ctx_create(int device, jb_ctx** out) { return jb_ctx_create_on_stream(device, nullptr, out); }
+
+void jb_ctx_destroy(jb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->tables) c->release(kv.second);
+    c->tables.clear();
+    for (auto& kv : c->srs) {
+        if (kv.second.xy) cudaFree(kv.second.xy);
+    }
+    c->srs.clear();
+    c->msm_release();
+    if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_small) cudaFree(c->d_small);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* jb_last_error(jb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int jb_ctx_synchronize(jb_ctx* c) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    return c->check(cudaStreamSynchronize(c->stream), "stream synchronize");
+}
+
+uint64_t jb_ctx_launch_count(jb_ctx* c) { return c ? c->launches : 0; }
+
+// ---- tables ------------------------------------------------------------------------------
+int jb_table_alloc(jb_ctx* c, size_t len, jb_table* out) {
+    if (!c || !out || len == 0) return JB_ERR_INVALID;
+    Guard g(c);
+    Table t;
+    int st = c->dev_alloc((void**)&t.buf, len * 32);
+    if (st != JB_OK) return st;
+    t.cap = t.len = len;
+    t.buf_owned = true;
+    *out = c->next_id++;
+    c->tables[*out] = t;
+    return JB_OK;
+}
+
+int jb_table_upload(jb_ctx* c, const uint64_t* limbs, size_t len, jb_table* out) {
+    if (!c || !limbs) return JB_ERR_INVALID;
+    int st = jb_table_alloc(c, len, out);
+    if (st != JB_OK) return st;
+    Guard g(c);
+    Table& t = c->tables[*out];
+    return c->check(cudaMemcpyAsync(t.buf, limbs, len * 32, cudaMemcpyHostToDevice, c->stream), "table upload");
+}
+
+int jb_table_wrap_device(jb_ctx* c, void* dptr, size_t len, jb_table* out) {
+    if (!c || !dptr || !out || len == 0 || ((uintptr_t)dptr & 31)) return JB_ERR_INVALID;
+    Guard g(c);
+    Table t;
+    t.buf = (uint64_t*)dptr;
+    t.cap = t.len = len;
+    t.buf_owned = false;
+    *out = c->next_id++;
+    c->tables[*out] = t;
+    return JB_OK;
+}
+
+int jb_table_len(jb_ctx* c, jb_table h, size_t* len) {
+    if (!c || !len) return JB_ERR_INVALID;
+    Guard g(c);
+    Table* t = c->find(h);
+    if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    *len = t->len;
+    return JB_OK;
+}
+
+int jb_table_device_ptr(jb_ctx* c, jb_table h, void** p) {
+    if (!c || !p) return JB_ERR_INVALID;
+    Guard g(c);
+    Table* t = c->find(h);
+    if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    *p = t->buf;
+    return JB_OK;
+}
+
+int jb_table_download(jb_ctx* c, jb_table h, uint64_t* out, size_t len) {
+    if (!c || !out) return JB_ERR_INVALID;
+    Guard g(c);
+    Table* t = c->find(h);
+    if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    if (len > t->len) return c->fail(JB_ERR_INVALID, "download: len exceeds table length");
+    int st = c->check(cudaMemcpyAsync(out, t->buf, len * 32, cudaMemcpyDeviceToHost, c->stream), "table download");
+    if (st != JB_OK) return st;
+    return c->check(cudaStreamSynchronize(c->stream), "table download sync");
+}
+
+int jb_table_clone(jb_ctx* c, jb_table h, jb_table* out) {
+    if (!c || !out) return JB_ERR_INVALID;
+    size_t len;
+    {
+        Guard g(c);
+        Table* t = c->find(h);
+        if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+        len = t->len;
+    }
+    int st = jb_table_alloc(c, len, out);
+    if (st != JB_OK) return st;
+    Guard g(c);
+    return c->check(cudaMemcpyAsync(c->tables[*out].buf, c->tables[h].buf, len * 32, cudaMemcpyDeviceToDevice, c->stream),
+                    "table clone");
+}
+
+int jb_table_free(jb_ctx* c, jb_table h) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->tables.find(h);
+    if (it == c->tables.end()) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    c->release(it->second);
+    c->tables.erase(it);
+    return JB_OK;
+}
+
+int jb_table_bind(jb_ctx* c, jb_table h, const uint64_t r[4], int order) {
+    if (!c || !r) return JB_ERR_INVALID;
+    Guard g(c);
+    Table* t = c->find(h);
+    if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    return bind_table(c, *t, r, order);
+}
+
+// ---- eq ----------------------------------------------------------------------------------
+int jb_eq_evals(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, jb_table* out) {
+    if (!c || !out || (nvars && !r) || nvars > 40) return JB_ERR_INVALID;
+    for (size_t i = 0; i < nvars; ++i)
+        if (!canonical_fr(r + 4 * i)) return c->fail(JB_ERR_INVALID, "eq: point limbs not canonical");
+    if (scale && !canonical_fr(scale)) return c->fail(JB_ERR_INVALID, "eq: scale limbs not canonical");
+    int st = jb_table_alloc(c, (size_t)1 << nvars, out);
+    if (st != JB_OK) return st;
+    Guard g(c);
+    // stage r and the scale on the device (n + 1 elements)
+    uint64_t* d_r = nullptr;
+    st = c->dev_alloc((void**)&d_r, (nvars + 1) * 32);
+    if (st != JB_OK) return st;
+    std::vector<uint64_t> host((nvars + 1) * 4);
+    if (nvars) std::memcpy(host.data(), r, nvars * 32);
+    if (scale) std::memcpy(host.data() + 4 * nvars, scale, 32);
+    st = c->check(cudaMemcpyAsync(d_r, host.data(), (nvars + 1) * 32, cudaMemcpyHostToDevice, c->stream), "eq: H2D");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "eq: H2D sync");  // `host` is pageable
+    if (st == JB_OK) st = eq_build(c, d_r, nvars, scale ? d_r + 4 * nvars : nullptr, c->tables[*out].buf);
+    c->dev_free(d_r);
+    return st;
+}
+
+int jb_eq_evals_aligned_block(jb_ctx* c, const uint64_t* r, size_t nvars, size_t start_index, size_t block_size,
+                              jb_table* out) {
+    if (!c || !out || !r) return JB_ERR_INVALID;
+    if (block_size == 0 || (block_size & (block_size - 1)) || start_index % block_size)
+        return c->fail(JB_ERR_INVALID, "eq aligned block: block_size must be a power of two dividing start_index");
+    size_t block_vars = 0;
+    while (((size_t)1 << block_vars) < block_size) ++block_vars;
+    if (block_vars > nvars) return c->fail(JB_ERR_INVALID, "eq aligned block: block larger than the domain");
+    size_t prefix_len = nvars - block_vars;
+    size_t prefix_value = start_index >> block_vars;
+    // prefix scale = prod_i (bit ? r_i : 1 - r_i): O(log G) host multiplications (eq.rs:252-260)
+    HostFr scale = HostFr::one();
+    for (size_t i = 0; i < prefix_len; ++i) {
+        if (!canonical_fr(r + 4 * i)) return c->fail(JB_ERR_INVALID, "eq: point limbs not canonical");
+        HostFr ri = HostFr::from_limbs(r + 4 * i);
+        bool bit = (prefix_value >> (prefix_len - 1 - i)) & 1;
+        scale = scale * (bit ? ri : HostFr::one() - ri);
+    }
+    return jb_eq_evals(c, r + 4 * prefix_len, block_vars, scale.l, out);
+}
+
+// ---- sumcheck member -------------------------------------------------------------------
+struct jb_member {
+    jb_ctx* ctx;
+    std::vector<Table> tables;
+    int m;
+    int order;
+    size_t rounds;  // total
+    size_t len;     // current table length
+};
+
+int jb_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, jb_member** out) {
+    if (!c || !handles || !out) return JB_ERR_INVALID;
+    Guard g(c);
+    if (m < 1 || m > 4) return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
+    if (order != JB_HIGH_TO_LOW && order != JB_LOW_TO_HIGH) return c->fail(JB_ERR_INVALID, "member: unknown order");
+    size_t len = 0;
+    for (size_t j = 0; j < m; ++j) {
+        Table* t = c->find(handles[j]);
+        if (!t) return c->fail(JB_ERR_INVALID, "member: unknown table handle");
+        for (size_t k = 0; k < j; ++k)
+            if (handles[k] == handles[j]) return c->fail(JB_ERR_INVALID, "member: duplicate table handle");
+        if (j == 0) len = t->len;
+        if (t->len != len) return c->fail(JB_ERR_INVALID, "member: tables differ in length");
+    }
+    if (len == 0 || (len & (len - 1))) return c->fail(JB_ERR_INVALID, "member: table length must be a power of two");
+    jb_member* mem = new (std::nothrow) jb_member();
+    if (!mem) return JB_ERR_OOM;
+    mem->ctx = c;
+    mem->m = (int)m;
+    mem->order = order;
+    mem->len = len;
+    mem->rounds = 0;
+    while (((size_t)1 << mem->rounds) < len) ++mem->rounds;
+    for (size_t j = 0; j < m; ++j) {
+        auto it = c->tables.find(handles[j]);
+        mem->tables.push_back(it->second);
+        c->tables.erase(it);  // ownership moves into the member
+    }
+    *out = mem;
+    return JB_OK;
+}
+
+int jb_member_num_rounds(jb_member* mem, size_t* rounds) {
+    if (!mem || !rounds) return JB_ERR_INVALID;
+    *rounds = mem->rounds;
+    return JB_OK;
+}
+
+int jb_member_degree(jb_member* mem, size_t* degree) {
+    if (!mem || !degree) return JB_ERR_INVALID;
+    *degree = (size_t)mem->m;
+    return JB_OK;
+}
+
+// Runs the fused pass; on return d_small[0..m] holds the m+1 sums (canonical) or, if lanes_out,
+// lanes_out holds them widened to one 32-bit limb per u64.
+static int member_round(jb_member* mem, const uint64_t* bind, void* lanes_out) {
+    jb_ctx* c = mem->ctx;
+    bool do_bind = bind != nullptr;
+    bool hi4 = false;
+    BindScalar s;
+    std::memset(&s, 0, sizeof s);
+    size_t len = mem->len;
+    if (do_bind) {
+        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
+        if (len < 4) return c->fail(JB_ERR_INVALID, "prove_round: no round left after this bind (use finish_rounds)");
+        s = make_scalar(bind, &hi4);
+        len /= 2;
+    } else if (len < 2) {
+        return c->fail(JB_ERR_INVALID, "prove_round: member is fully bound");
+    }
+    size_t pairs = len / 2;
+    TablePtrs tp;
+    std::memset(&tp, 0, sizeof tp);
+    for (int j = 0; j < mem->m; ++j) {
+        Table& t = mem->tables[j];
+        tp.in[j] = t.buf;
+        tp.out[j] = t.buf;
+        if (do_bind && mem->order == JB_LOW_TO_HIGH) {
+            int st = c->ensure_alt(t, len);
+            if (st != JB_OK) return st;
+            tp.out[j] = t.alt;
+        }
+    }
+    int grid = 0;
+    int st = dispatch_fused(c, mem->m, mem->order, tp, pairs, do_bind, hi4, s, &grid);
+    if (st != JB_OK) return st;
+    if (do_bind) {
+        for (int j = 0; j < mem->m; ++j) {
+            if (mem->order == JB_LOW_TO_HIGH) mem->tables[j].swap_buffers();
+            mem->tables[j].len = len;
+        }
+        mem->len = len;
+    }
+    int K = mem->m + 1;
+    if (lanes_out) {
+        sum_partials_lanes_kernel<<<1, 256, 0, c->stream>>>(c->d_partial, grid, K, (uint64_t*)lanes_out);
+    } else {
+        sum_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partial, grid, K, c->d_small);
+    }
+    c->launches++;
+    return c->check(cudaGetLastError(), "sum_partials launch");
+}
+
+int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
+                          uint64_t* out_evals) {
+    if (!mem || !out_evals) return JB_ERR_INVALID;
+    jb_ctx* c = mem->ctx;
+    Guard g(c);
+    size_t bound = mem->rounds;
+    {
+        size_t l = mem->len;
+        while (l > 1) { l >>= 1; --bound; }  // bound = rounds already bound
+    }
+    if (round != bound + (bind ? 1 : 0)) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
+    int st = member_round(mem, bind, nullptr);
+    if (st != JB_OK) return st;
+    int K = mem->m + 1;
+    st = c->check(cudaMemcpyAsync(c->h_small, c->d_small, (size_t)K * 32, cudaMemcpyDeviceToHost, c->stream), "round D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "round sync");
+    if (st != JB_OK) return st;
+    std::memcpy(out_evals, c->h_small, (size_t)K * 32);
+    if (claim) {
+        HostFr s0 = HostFr::from_limbs(out_evals), s1 = HostFr::from_limbs(out_evals + 4);
+        if ((s0 + s1) != HostFr::from_limbs(claim)) {
+            char buf[96];
+            std::snprintf(buf, sizeof buf, "RoundCheckFailed { round: %zu }", round);
+            return c->fail(JB_ERR_ROUND_CHECK, buf);
+        }
+    }
+    return JB_OK;
+}
+
+int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind, size_t round, void* lanes_out) {
+    (void)round;
+    if (!mem || !lanes_out) return JB_ERR_INVALID;
+    Guard g(mem->ctx);
+    return member_round(mem, bind, lanes_out);
+}
+
+int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint64_t* out) {
+    if (!c || !device_lanes || !out || count == 0 || count * 64 > JB_SMALL_BYTES) return JB_ERR_INVALID;
+    Guard g(c);
+    int st = c->check(cudaMemcpyAsync(c->h_small, device_lanes, count * 64, cudaMemcpyDeviceToHost, c->stream),
+                      "partials D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "partials sync");
+    if (st != JB_OK) return st;
+    // carry-propagate the 8 x (32-bit limb sums) and reduce mod r: O(count) host work.
+    for (size_t k = 0; k < count; ++k) {
+        const uint64_t* lane = c->h_small + 8 * k;
+        uint32_t w[10];
+        unsigned __int128 carry = 0;
+        for (int i = 0; i < 8; ++i) {
+            carry += lane[i];
+            w[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        w[8] = (uint32_t)carry;
+        w[9] = (uint32_t)(carry >> 32);
+        // value < 2^32 * r < 2^286; fold by subtracting (r << k) from the top down
+        uint64_t v[5] = {(uint64_t)w[0] | ((uint64_t)w[1] << 32), (uint64_t)w[2] | ((uint64_t)w[3] << 32),
+                         (uint64_t)w[4] | ((uint64_t)w[5] << 32), (uint64_t)w[6] | ((uint64_t)w[7] << 32),
+                         (uint64_t)w[8] | ((uint64_t)w[9] << 32)};
+        for (int sh = 33; sh >= 0; --sh) {
+            uint64_t ps[5] = {0, 0, 0, 0, 0};  // r << sh
+            for (int i = 0; i < 4; ++i) {
+                ps[i] |= sh ? (HostFr::P[i] << sh) : HostFr::P[i];
+                if (sh) ps[i + 1] |= HostFr::P[i] >> (64 - sh);
+            }
+            bool ge = true;
+            for (int i = 4; i >= 0; --i)
+                if (v[i] != ps[i]) { ge = v[i] > ps[i]; break; }
+            if (ge) {
+                uint64_t borrow = 0;
+                for (int i = 0; i < 5; ++i) {
+                    unsigned __int128 t = (unsigned __int128)v[i] - ps[i] - borrow;
+                    v[i] = (uint64_t)t;
+                    borrow = (uint64_t)(t >> 64) & 1;
+                }
+            }
+        }
+        std::memcpy(out + 4 * k, v, 32);
+    }
+    return JB_OK;
+}
+
+int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
+    if (!mem || !bind) return JB_ERR_INVALID;
+    jb_ctx* c = mem->ctx;
+    Guard g(c);
+    if (mem->len < 2) return c->fail(JB_ERR_INVALID, "finish_rounds: member already fully bound");
+    for (int j = 0; j < mem->m; ++j) {
+        int st = bind_table(c, mem->tables[j], bind, mem->order);
+        if (st != JB_OK) return st;
+    }
+    mem->len /= 2;
+    return JB_OK;
+}
+
+int jb_member_final_evals(jb_member* mem, uint64_t* out) {
+    if (!mem || !out) return JB_ERR_INVALID;
+    jb_ctx* c = mem->ctx;
+    Guard g(c);
+    if (mem->len != 1) {
+        char buf[96];
+        size_t remaining = 0;
+        for (size_t l = mem->len; l > 1; l >>= 1) ++remaining;
+        std::snprintf(buf, sizeof buf, "NotFullyBound { remaining: %zu }", remaining);
+        return c->fail(JB_ERR_INVALID, buf);
+    }
+    for (int j = 0; j < mem->m; ++j) {
+        int st = c->check(cudaMemcpyAsync(c->h_small + 4 * j, mem->tables[j].buf, 32, cudaMemcpyDeviceToHost, c->stream),
+                          "final evals D2H");
+        if (st != JB_OK) return st;
+    }
+    int st = c->check(cudaStreamSynchronize(c->stream), "final evals sync");
+    if (st != JB_OK) return st;
+    std::memcpy(out, c->h_small, (size_t)mem->m * 32);
+    return JB_OK;
+}
+
+void jb_member_destroy(jb_member* mem) {
+    if (!mem) return;
+    {
+        Guard g(mem->ctx);
+        for (auto& t : mem->tables) mem->ctx->release(t);
+    }
+    delete mem;
+}
+
+// ---- element-wise parity harness ---------------------------------------------------------------
+int jb_vec_op(jb_ctx* c, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (!c || !a || !b || !out || op < 0 || op > 3 || (field != 0 && field != 1)) return JB_ERR_INVALID;
+    if (n == 0) return JB_OK;
+    Guard g(c);
+    uint64_t *da = nullptr, *db = nullptr, *dd = nullptr;
+    int st = c->dev_alloc((void**)&da, n * 32);
+    if (st == JB_OK) st = c->dev_alloc((void**)&db, n * 32);
+    if (st == JB_OK) st = c->dev_alloc((void**)&dd, n * 32);
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, c->stream), "vec H2D");
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, c->stream), "vec H2D");
+    if (st == JB_OK) {
+        unsigned grid = (unsigned)((n + 255) / 256);
+        if (field == 0) vec_op_kernel<Fr><<<grid, 256, 0, c->stream>>>(da, db, dd, n, op);
+        else vec_op_kernel<Fq><<<grid, 256, 0, c->stream>>>(da, db, dd, n, op);
+        c->launches++;
+        st = c->check(cudaGetLastError(), "vec_op launch");
+    }
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(out, dd, n * 32, cudaMemcpyDeviceToHost, c->stream), "vec D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "vec sync");
+    if (da) c->dev_free(da);
+    if (db) c->dev_free(db);
+    if (dd) c->dev_free(dd);
+    return st;
+}
+
+}  // extern "C"
+
+// ---- diagnostics: ALU ceiling of the Montgomery product (DESIGN.md roofline evidence) ------------
+namespace {
+template <class F, int VARIANT>
+__global__ void __launch_bounds__(256) mul_chain_kernel(uint64_t* io, int iters) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    F x0 = ld_elem_rw<F>(io, 4 * i), x1 = ld_elem_rw<F>(io, 4 * i + 1);
+    F b0 = ld_elem_rw<F>(io, 4 * i + 2), b1 = ld_elem_rw<F>(io, 4 * i + 3);
+    for (int k = 0; k < iters; ++k) {
+        if (VARIANT == 0) {  // full 8x8 product + reduction
+            x0 = fp_mul(x0, b0);
+            x1 = fp_mul(x1, b1);
+        } else if (VARIANT == 1) {  // 125-bit challenge multiplier (4 rows)
+            x0 = fp_mul_hi4(x0, b0.v + 4);
+            x1 = fp_mul_hi4(x1, b1.v + 4);
+        } else {  // add/sub only
+            x0 = fp_add(x0, b0);
+            x1 = fp_sub(x1, b1);
+        }
+    }
+    st_elem(io, 4 * i, x0);
+    st_elem(io, 4 * i + 1, x1);
+}
+}  // namespace
+
+extern "C" int jb_diag_mul_throughput(jb_ctx* c, int field, int variant, int iters, int blocks, double* out_gops) {
+    if (!c || !out_gops || iters < 1 || blocks < 1 || variant < 0 || variant > 2) return JB_ERR_INVALID;
+    Guard g(c);
+    size_t threads = (size_t)blocks * 256;
+    uint64_t* d = nullptr;
+    int st = c->dev_alloc((void**)&d, threads * 4 * 32);
+    if (st != JB_OK) return st;
+    std::vector<uint64_t> h(threads * 16);
+    uint64_t sm = 0x1234;
+    for (auto& v : h) { sm += 0x9E3779B97F4A7C15ULL; uint64_t z = sm; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; v = z ^ (z >> 31); }
+    for (size_t i = 0; i < threads * 4; ++i) h[4 * i + 3] &= 0x0fffffffffffffffULL;  // < p
+    st = c->check(cudaMemcpyAsync(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream), "diag H2D");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5 && st == JB_OK; ++rep) {
+        cudaEventRecord(e0, c->stream);
+#define JB_DIAG_LAUNCH(F, V) mul_chain_kernel<F, V><<<blocks, 256, 0, c->stream>>>(d, iters)
+        if (field == 0) { if (variant == 0) JB_DIAG_LAUNCH(Fr, 0); else if (variant == 1) JB_DIAG_LAUNCH(Fr, 1); else JB_DIAG_LAUNCH(Fr, 2); }
+        else { if (variant == 0) JB_DIAG_LAUNCH(Fq, 0); else if (variant == 1) JB_DIAG_LAUNCH(Fq, 1); else JB_DIAG_LAUNCH(Fq, 2); }
+#undef JB_DIAG_LAUNCH
+        c->launches++;
+        cudaEventRecord(e1, c->stream);
+        st = c->check(cudaEventSynchronize(e1), "diag sync");
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->dev_free(d);
+    if (st == JB_OK) *out_gops = (double)threads * 2.0 * iters / (best * 1e-3) / 1e9;
+    return st;
+}

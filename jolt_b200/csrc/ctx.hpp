@@ -1,0 +1,98 @@
+// Context internals shared by capi.cu and msm.cu. A jb_ctx is the device half of the
+// reference's ProofSession (crates/jolt-kernels/src/backend.rs:283-286).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "../../include/jolt_b200.h"
+
+constexpr int JB_MAX_PARTIAL_BLOCKS = 148 * 8;  // per-block partial-sum slots (grid cap for fused passes)
+constexpr int JB_MAX_EVALS = 8;                 // degree + 1 <= 8
+constexpr size_t JB_SMALL_BYTES = 4096;         // staging for round evaluations / points
+
+struct Table {
+    uint64_t* buf = nullptr;  // current data (len elements)
+    size_t cap = 0;           // capacity of buf in elements
+    size_t len = 0;
+    uint64_t* alt = nullptr;  // ping-pong scratch for LowToHigh binds
+    size_t alt_cap = 0;
+    bool buf_owned = true;    // false: caller's device memory (jb_table_wrap_device)
+    bool alt_owned = true;
+    void swap_buffers() {
+        uint64_t* b = buf; buf = alt; alt = b;
+        size_t c = cap; cap = alt_cap; alt_cap = c;
+        bool o = buf_owned; buf_owned = alt_owned; alt_owned = o;
+    }
+};
+
+struct Srs {
+    uint64_t* xy = nullptr;  // n affine points, 8 limbs each (x, y), identity = all zero
+    size_t n = 0;
+};
+
+struct MsmWorkspace;  // msm.cu
+
+struct jb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    std::mutex mu;
+    std::unordered_map<uint64_t, Table> tables;
+    std::unordered_map<uint64_t, Srs> srs;
+    uint64_t next_id = 1;
+    std::string err;
+    uint64_t launches = 0;
+    uint64_t* d_partial = nullptr;  // JB_MAX_PARTIAL_BLOCKS * JB_MAX_EVALS elements
+    uint64_t* d_small = nullptr;    // device staging
+    uint64_t* h_small = nullptr;    // pinned host staging
+    MsmWorkspace* msm = nullptr;
+
+    int fail(int status, const char* what) {
+        err = what;
+        return status;
+    }
+    int check(cudaError_t e, const char* what) {
+        if (e == cudaSuccess) return JB_OK;
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? JB_ERR_OOM : JB_ERR_CUDA;
+    }
+    int dev_alloc(void** p, size_t bytes) {
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 32, stream);
+        if (e != cudaSuccess) {
+            *p = nullptr;
+            err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return JB_ERR_OOM;
+        }
+        return JB_OK;
+    }
+    void dev_free(void* p) {
+        if (p) cudaFreeAsync(p, stream);
+    }
+    Table* find(uint64_t h) {
+        auto it = tables.find(h);
+        return it == tables.end() ? nullptr : &it->second;
+    }
+    int ensure_alt(Table& t, size_t elems) {
+        if (t.alt && t.alt_cap >= elems) return JB_OK;
+        if (t.alt && t.alt_owned) dev_free(t.alt);
+        t.alt = nullptr;
+        t.alt_cap = 0;
+        t.alt_owned = true;
+        int st = dev_alloc((void**)&t.alt, elems * 32);
+        if (st == JB_OK) t.alt_cap = elems;
+        return st;
+    }
+    void release(Table& t) {
+        if (t.buf && t.buf_owned) dev_free(t.buf);
+        if (t.alt && t.alt_owned) dev_free(t.alt);
+        t.buf = t.alt = nullptr;
+    }
+    void msm_release();
+};

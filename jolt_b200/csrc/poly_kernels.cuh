@@ -1,0 +1,288 @@
+// Device kernels for the sumcheck hot path over BN254 Fr (sm_100a):
+//   * bind            - Polynomial::bind_with_order, crates/jolt-poly/src/dense.rs:180-263
+//                       (legacy DensePolynomial::bind, jolt-prover-legacy/src/poly/dense_mlpoly.rs:71-221)
+//   * fused bind+eval - the fused ProveRounds contract, crates/jolt-sumcheck/src/prover.rs:45-72,
+//                       restating NaiveSumcheckProver::prove_round (jolt-kernels/src/reference/naive.rs:241-310)
+//                       for Expr = product of m dense tables, degree m
+//   * eq expansion    - EqPolynomial::evals, crates/jolt-poly/src/eq.rs:221-231, 299-315 (r[0] <-> MSB)
+// All are HBM-streaming integer kernels: one field element (32 B) per 256-bit request, one
+// output index per thread per iteration, grid-stride over a grid sized in multiples of the SM
+// count. No tensor cores (there is no dense contraction on this path).
+#pragma once
+#include "field.cuh"
+
+namespace jb {
+
+enum : int { ORDER_HIGH_TO_LOW = 0, ORDER_LOW_TO_HIGH = 1 };
+
+// The bind multiplier: either a generic 254-bit element or a 125-bit challenge [0,0,lo,hi].
+struct BindScalar {
+    uint32_t w[8];
+};
+
+template <bool HI4>
+__device__ __forceinline__ Fr bind_pair(const Fr& lo, const Fr& hi, const BindScalar& s) {
+    Fr d = fp_sub_lazy(hi, lo);  // in (0, 2p)
+    Fr m;
+    if (HI4) {
+        m = fp_mul_hi4(d, s.w + 4);
+    } else {
+        Fr sv;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sv.v[i] = s.w[i];
+        m = fp_mul(d, sv);
+    }
+    return fp_add(lo, m);  // canonical
+}
+
+// out[i] = lo + s*(hi - lo).  HighToLow: (in[i], in[i+half]) - may run in place (out == in);
+// LowToHigh: (in[2i], in[2i+1]) - out must not alias in.
+template <int ORDER, bool HI4>
+__global__ void __launch_bounds__(256) bind_kernel(const uint64_t* in, uint64_t* out, size_t half, BindScalar s) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+        Fr lo, hi;
+        if (ORDER == ORDER_HIGH_TO_LOW) {
+            lo = ld_elem_rw<Fr>(in, i);
+            hi = ld_elem_rw<Fr>(in, i + half);
+        } else {
+            lo = ld_elem<Fr>(in, 2 * i);
+            hi = ld_elem<Fr>(in, 2 * i + 1);
+        }
+        st_elem(out, i, bind_pair<HI4>(lo, hi, s));
+    }
+}
+
+// ---- block reduction of field elements (warp shuffle, then one smem stage) ---------------------
+__device__ __forceinline__ Fr warp_sum(Fr x) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fr y;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) y.v[k] = __shfl_down_sync(0xffffffffu, x.v[k], off);
+        x = fp_add(x, y);
+    }
+    return x;
+}
+
+// Sums K accumulators over the block; thread 0 ends up with the totals. smem: (blockDim/32)*K*8 words.
+template <int K>
+__device__ __forceinline__ void block_sum(Fr (&acc)[K], uint32_t* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) smem[(warp * K + k) * 8 + w] = acc[k].v[w];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            Fr x = Fr::zero();
+            if (lane < nwarps) {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) x.v[w] = smem[(lane * K + k) * 8 + w];
+            }
+            acc[k] = warp_sum(x);
+        }
+    }
+}
+
+struct TablePtrs {
+    const uint64_t* in[4];
+    uint64_t* out[4];
+};
+
+// Fused pass for a product-of-M member:
+//   BIND: first fold every table under `s` (writing the bound table), then
+//   evaluate s(t) = sum_y prod_j (lo_j(y) + t (hi_j(y) - lo_j(y))), t = 0..M, over the BOUND tables.
+// `pairs` = number of y indices = (bound length)/2. Layout:
+//   HighToLow, BIND : reads e[y], e[y+P], e[y+2P], e[y+3P] (P = pairs); writes e'[y], e'[y+P] in place
+//   LowToHigh, BIND : reads e[4y..4y+3]; writes out[2y], out[2y+1]   (out-of-place)
+//   no BIND         : reads the pair only, writes nothing
+// Each block writes its M+1 partial sums to partial[blockIdx.x*(M+1) + t] (canonical limbs);
+// sum_partials_kernel folds them. No atomics, deterministic values.
+template <int M, int ORDER, bool BIND, bool HI4>
+__global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s,
+                                                          uint64_t* partial) {
+    __shared__ uint32_t smem[8 * (M + 1) * 8];
+    Fr acc[M + 1];
+#pragma unroll
+    for (int t = 0; t <= M; ++t) acc[t] = Fr::zero();
+
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
+        Fr cur[M], dlt[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            Fr lo, hi;
+            if (BIND) {
+                Fr a, b, c, d;
+                if (ORDER == ORDER_HIGH_TO_LOW) {
+                    a = ld_elem_rw<Fr>(tp.in[j], y);
+                    c = ld_elem_rw<Fr>(tp.in[j], y + 2 * pairs);
+                    b = ld_elem_rw<Fr>(tp.in[j], y + pairs);
+                    d = ld_elem_rw<Fr>(tp.in[j], y + 3 * pairs);
+                    lo = bind_pair<HI4>(a, c, s);
+                    hi = bind_pair<HI4>(b, d, s);
+                    st_elem(tp.out[j], y, lo);
+                    st_elem(tp.out[j], y + pairs, hi);
+                } else {
+                    a = ld_elem<Fr>(tp.in[j], 4 * y);
+                    b = ld_elem<Fr>(tp.in[j], 4 * y + 1);
+                    c = ld_elem<Fr>(tp.in[j], 4 * y + 2);
+                    d = ld_elem<Fr>(tp.in[j], 4 * y + 3);
+                    lo = bind_pair<HI4>(a, b, s);
+                    hi = bind_pair<HI4>(c, d, s);
+                    st_elem(tp.out[j], 2 * y, lo);
+                    st_elem(tp.out[j], 2 * y + 1, hi);
+                }
+            } else {
+                if (ORDER == ORDER_HIGH_TO_LOW) {
+                    lo = ld_elem_rw<Fr>(tp.in[j], y);
+                    hi = ld_elem_rw<Fr>(tp.in[j], y + pairs);
+                } else {
+                    lo = ld_elem<Fr>(tp.in[j], 2 * y);
+                    hi = ld_elem<Fr>(tp.in[j], 2 * y + 1);
+                }
+            }
+            cur[j] = lo;
+            dlt[j] = fp_sub(hi, lo);
+        }
+#pragma unroll
+        for (int t = 0; t <= M; ++t) {
+            Fr prod = cur[0];
+#pragma unroll
+            for (int j = 1; j < M; ++j) prod = fp_mul(prod, cur[j]);
+            acc[t] = fp_add(acc[t], prod);
+            if (t < M) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) cur[j] = fp_add(cur[j], dlt[j]);
+            }
+        }
+    }
+    block_sum<M + 1>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t <= M; ++t) st_elem(partial, (size_t)blockIdx.x * (M + 1) + t, acc[t]);
+    }
+}
+
+// out[t] = sum_b partial[b*K + t], one block. K <= 8.
+__global__ void __launch_bounds__(256) sum_partials_kernel(const uint64_t* partial, int nblocks, int K,
+                                                           uint64_t* out) {
+    __shared__ uint32_t smem[8 * 8];
+    for (int t = 0; t < K; ++t) {
+        Fr acc[1] = {Fr::zero()};
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+            acc[0] = fp_add(acc[0], ld_elem_rw<Fr>(partial, (size_t)b * K + t));
+        block_sum<1>(acc, smem);
+        if (threadIdx.x == 0) st_elem(out, t, acc[0]);
+        __syncthreads();
+    }
+}
+
+// Multi-GPU variant: the K block-reduced sums leave as 8 u64 lanes each holding one 32-bit limb,
+// so an integer ncclSum over ranks is exact; the carry + mod-r fold happens after the all-reduce.
+__global__ void __launch_bounds__(256) sum_partials_lanes_kernel(const uint64_t* partial, int nblocks, int K,
+                                                                 uint64_t* lanes) {
+    __shared__ uint32_t smem[8 * 8];
+    for (int t = 0; t < K; ++t) {
+        Fr acc[1] = {Fr::zero()};
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
+            acc[0] = fp_add(acc[0], ld_elem_rw<Fr>(partial, (size_t)b * K + t));
+        block_sum<1>(acc, smem);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) lanes[t * 8 + w] = acc[0].v[w];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- eq-table expansion --------------------------------------------------------------------
+// table[x] = scale * prod_i (r_i if bit_i(x) else 1 - r_i), bit_i(x) = bit (n-1-i) of x.
+// One block expands EQ_BLOCK_VARS trailing variables from one prefix value:
+//   stage 1: the block builds the 2^(nv-3) table of the first nv-3 block variables in shared
+//            memory, level by level (1 mul + 1 sub per pair, eq.rs:308-312);
+//   stage 2: each thread expands the last 3 variables in registers and writes 8 consecutive
+//            outputs (256 B). Total work ~ 1 mul + 1 sub per output, written once: 32 B/output.
+constexpr int EQ_BLOCK_VARS = 11;  // 2^11 outputs per block, 256 threads x 8
+
+__global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix,  // gridDim.x prefix values (or null: scale)
+                                                        const uint64_t* scale,   // used when prefix == null (may be null: one)
+                                                        const uint64_t* r,       // nv block variables, r[0] = most significant
+                                                        int nv, uint64_t* out) {
+    __shared__ uint32_t tab[8 * 256];  // word-major: tab[w*256 + idx] (conflict-free)
+    const int tid = threadIdx.x;
+    const int reg_vars = nv < 3 ? nv : 3;
+    const int smem_vars = nv - reg_vars;  // <= 8
+    if (tid == 0) {
+        Fr base = Fr::one();
+        if (prefix) base = ld_elem_rw<Fr>(prefix, blockIdx.x);
+        else if (scale) base = ld_elem_rw<Fr>(scale, 0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tab[w * 256] = base.v[w];
+    }
+    __syncthreads();
+    // level j doubles the table: new[2i+1] = old[i]*r_j, new[2i] = old[i] - new[2i+1].
+    for (int j = 0; j < smem_vars; ++j) {
+        const int cur = 1 << j;
+        Fr v, hi;
+        if (tid < cur) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v.v[w] = tab[w * 256 + tid];
+            hi = fp_mul(v, ld_elem_rw<Fr>(r, j));
+        }
+        __syncthreads();
+        if (tid < cur) {
+            Fr lo = fp_sub(v, hi);
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                tab[w * 256 + 2 * tid] = lo.v[w];
+                tab[w * 256 + 2 * tid + 1] = hi.v[w];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid >= (1 << smem_vars)) return;
+    Fr e[8];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) e[0].v[w] = tab[w * 256 + tid];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        if (j < reg_vars) {  // block-uniform
+            Fr rj = ld_elem_rw<Fr>(r, smem_vars + j);
+#pragma unroll
+            for (int i = (1 << j) - 1; i >= 0; --i) {
+                Fr hi = fp_mul(e[i], rj);
+                e[2 * i] = fp_sub(e[i], hi);
+                e[2 * i + 1] = hi;
+            }
+        }
+    }
+    const int cnt = 1 << reg_vars;
+    size_t base_idx = ((size_t)blockIdx.x << nv) + ((size_t)tid << reg_vars);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < cnt) st_elem(out, base_idx + i, e[i]);
+}
+
+// ---- element-wise helpers (tests + host glue) --------------------------------------------------
+// op: 0 add, 1 sub, 2 mul (Montgomery), 3 mul with b's 4 low words zero (hi4 path)
+template <class F>
+__global__ void vec_op_kernel(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = ld_elem<F>(a, i), y = ld_elem<F>(b, i), z;
+    if (op == 0) z = fp_add(x, y);
+    else if (op == 1) z = fp_sub(x, y);
+    else if (op == 2) z = fp_mul(x, y);
+    else z = fp_mul_hi4(x, y.v + 4);
+    st_elem(o, i, z);
+}
+
+}  // namespace jb

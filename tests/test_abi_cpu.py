@@ -1,0 +1,96 @@
+"""CPU-side checks: the C-ABI library loads without a GPU, exports every symbol include/jolt_b200.h
+declares, fails loudly (no fallback) when no device exists, and the host glue matches the oracle."""
+import ctypes
+import pathlib
+import re
+
+import numpy as np
+import pytest
+
+import jolt_b200
+from jolt_b200 import _lib, field as F
+from jolt_b200.api import UnivariatePoly
+from oracle import bn254 as O
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+def _has_gpu():
+    return _lib.load().jb_device_count() > 0
+
+
+def test_header_symbols_exported():
+    header = (ROOT / "include" / "jolt_b200.h").read_text()
+    declared = set(re.findall(r"\b(jb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 35
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/jolt_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_version_and_status_strings():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.jb_version()
+    assert b"no CPU fallback" in lib.jb_status_str(_lib.JB_ERR_NO_DEVICE)
+
+
+def test_no_device_fails_loudly():
+    if _has_gpu():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(jolt_b200.JoltB200Error) as e:
+        jolt_b200.Session(0)
+    assert e.value.status == _lib.JB_ERR_NO_DEVICE
+
+
+def test_field_helpers_match_oracle():
+    vals = O.random_fr(7, 20) + [0, 1, O.R_MOD - 1]
+    limbs = F.ints_to_limbs(vals)
+    assert [list(map(int, row)) for row in limbs] == [O.to_mont_limbs(v) for v in vals]
+    assert F.limbs_to_ints(limbs) == vals
+    assert list(F.challenge_from_bytes(bytes.fromhex("dae623d2aa29f41845b9a32a1d819bb6"))) == \
+        O.challenge_to_mont_limbs(*O.challenge_limbs(bytes.fromhex("dae623d2aa29f41845b9a32a1d819bb6")))
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 7])
+def test_univariate_from_evals_matches_oracle(deg):
+    coeffs = O.random_fr(100 + deg, deg + 1)
+    ev = [O.uni_evaluate(coeffs, x) for x in range(deg + 1)]
+    poly = UnivariatePoly.from_evals(ev)
+    assert poly.coefficients == coeffs == O.uni_from_evals(ev)
+    x = O.random_fr(5, 1)[0]
+    assert poly.evaluate(x) == O.uni_evaluate(coeffs, x)
+    assert poly.compress() == O.uni_compress(coeffs)
+    hint = (ev[0] + ev[1]) % O.R_MOD
+    assert UnivariatePoly.from_evals_and_hint(hint, [ev[0]] + ev[2:]).coefficients == coeffs
+
+
+class _OracleMember:
+    """host-only stand-in so the engine (host logic) can be tested without a GPU"""
+    def __init__(self, tables):
+        self.inner = O.ProductMember(tables)
+    def num_rounds(self):
+        return self.inner.num_rounds()
+    def prove_round(self, b, rnd, claim):
+        return UnivariatePoly(self.inner.prove_round(b, rnd, claim))
+    def finish_rounds(self, b):
+        self.inner.finish_rounds(b)
+
+
+def test_engine_host_logic_matches_oracle_engine():
+    # two members of different lengths (front-loaded padding, prover.rs:246-280)
+    t_a = [O.random_fr(1, 16), O.random_fr(2, 16)]
+    t_b = [O.dense_member_with_sum(2, 555, 41)]
+    claim_a = sum(x * y for x, y in zip(*t_a)) % O.R_MOD
+    desc = [dict(input_claim=claim_a, coefficient=3, rounds=4, offset=0),
+            dict(input_claim=555, coefficient=5, rounds=2, offset=2)]
+    total = (3 * claim_a + 5 * 555 * 4) % O.R_MOD
+    pts = O.synthetic_point(4, 401)
+    want = O.prove_batch(desc, [O.ProductMember(t_a), O.ProductMember(t_b)], 4, 2, total, lambda r, c: pts[r])
+    got = jolt_b200.prove_batch([jolt_b200.BatchMember(**d) for d in desc], [_OracleMember(t_a), _OracleMember(t_b)],
+                                4, 2, total, lambda r, poly: pts[r])
+    assert got.challenges == want["challenges"] and got.final_claim == want["final_claim"]
+    assert got.member_claims == want["member_claims"]
+    assert [p.coefficients for p in got.round_polynomials] == want["round_polys"]
+    with pytest.raises(jolt_b200.SumcheckError):
+        jolt_b200.prove_batch([jolt_b200.BatchMember(**desc[0])], [_OracleMember(t_a)], 4, 2, total + 1, lambda r, p: 1)

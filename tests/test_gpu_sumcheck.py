@@ -1,0 +1,166 @@
+"""Fused bind+eval ProveRounds member and the batched engine on the device vs the oracle
+(mirrors jolt-sumcheck/src/tests.rs:1123-1290, tests/roundtrip.rs:26-183, optimized/parity.rs:79-118)."""
+import numpy as np
+import pytest
+
+import jolt_b200
+from jolt_b200 import HIGH_TO_LOW, LOW_TO_HIGH, BatchMember, Polynomial, ProductMember, UnivariatePoly
+from jolt_b200 import field as F
+from oracle import bn254 as O
+from oracle import coracle as C
+from gpu_util import rand_challenge, rand_full, rand_limbs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sess():
+    s = jolt_b200.Session(0)
+    yield s
+    s.close()
+
+
+def run_lockstep(sess, tables_int, order, challenges):
+    """parity.rs:79-118 shape: drive the oracle member and the GPU member with identical
+    (bind, round, claim); assert coefficient equality every round."""
+    m = len(tables_int)
+    n = len(tables_int[0]).bit_length() - 1
+    ref = O.ProductMember(tables_int, order)
+    gpu = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tables_int], order)
+    assert gpu.num_rounds() == n and gpu.degree() == m
+    claim = sum(np.prod([t[i] for t in tables_int], dtype=object) for i in range(1 << n)) % O.R_MOD
+    assert claim != 0, "reject zero initial claim (parity.rs)"
+    bind = None
+    for rnd in range(n):
+        want = ref.prove_round(bind, rnd, claim)
+        got = gpu.prove_round(bind, rnd, claim)
+        assert got.coefficients == want, f"round {rnd}"
+        assert (got.evaluate(0) + got.evaluate(1)) % O.R_MOD == claim
+        bind = challenges[rnd]
+        claim = got.evaluate(bind)
+    ref.finish_rounds(bind)
+    gpu.finish_rounds(bind)
+    assert gpu.final_evals() == ref.final_evals()
+    assert np.prod(gpu.final_evals(), dtype=object) % O.R_MOD == claim
+    return gpu
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+@pytest.mark.parametrize("order", [HIGH_TO_LOW, LOW_TO_HIGH])
+def test_product_member_lockstep(sess, m, order):
+    n = 9
+    tabs = [O.random_fr(500 + 10 * m + j, 1 << n) for j in range(m)]
+    run_lockstep(sess, tabs, order, O.synthetic_point(n, 401))
+
+
+def test_lockstep_125bit_challenges(sess):
+    n = 8
+    tabs = [O.random_fr(900 + j, 1 << n) for j in range(2)]
+    ch = [O.from_mont_limbs(rand_challenge(40 + i)) for i in range(n)]
+    for order in (HIGH_TO_LOW, LOW_TO_HIGH):
+        run_lockstep(sess, tabs, order, ch)
+
+
+def test_dense_member_fixture(sess):
+    # tests.rs:1129-1135: evals = from_u64(seed + 31 i + 11), evals[0] += sum - current
+    nr, total = 4, 90210
+    evals = O.dense_member_with_sum(nr, total, 41)
+    run_lockstep(sess, [evals], HIGH_TO_LOW, O.synthetic_point(nr, 401))
+
+
+def test_roundtrip_degree2_and_3_fixtures(sess):
+    # tests/roundtrip.rs:99-160 inputs
+    f = [i + 1 for i in range(16)]
+    g = [i * 3 + 7 for i in range(16)]
+    run_lockstep(sess, [f, g], HIGH_TO_LOW, O.random_fr(1, 4))
+    f = [i + 1 for i in range(8)]
+    g = [i * 2 + 3 for i in range(8)]
+    h = [i + 10 for i in range(8)]
+    run_lockstep(sess, [f, g, h], HIGH_TO_LOW, O.random_fr(2, 3))
+
+
+def test_round_check_failure_is_an_error(sess):
+    tabs = [O.random_fr(1, 16), O.random_fr(2, 16)]
+    gpu = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs])
+    with pytest.raises(jolt_b200.SumcheckError, match="RoundCheckFailed"):
+        gpu.prove_round(None, 0, 12345)
+
+
+def test_member_misuse_errors(sess):
+    tabs = [O.random_fr(1, 4)]
+    gpu = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs])
+    with pytest.raises(jolt_b200.JoltB200Error, match="NotFullyBound"):
+        gpu.final_evals()
+    with pytest.raises(jolt_b200.JoltB200Error):   # round index out of sequence
+        gpu.prove_round_evals(None, 1)
+    a = Polynomial.from_ints(sess, O.random_fr(1, 4))
+    b = Polynomial.from_ints(sess, O.random_fr(1, 8))
+    with pytest.raises(jolt_b200.JoltB200Error):   # length mismatch
+        ProductMember(sess, [a, b])
+
+
+def test_engine_on_gpu_matches_oracle_engine(sess):
+    # batch of two members with different lengths + front-loaded padding (prover.rs:246-343)
+    t_a = [O.random_fr(1, 64), O.random_fr(2, 64)]
+    t_b = [O.dense_member_with_sum(3, 555, 41)]
+    claim_a = sum(x * y for x, y in zip(*t_a)) % O.R_MOD
+    desc = [dict(input_claim=claim_a, coefficient=O.random_fr(8, 1)[0], rounds=6, offset=0),
+            dict(input_claim=555, coefficient=O.random_fr(9, 1)[0], rounds=3, offset=3)]
+    total = (desc[0]["coefficient"] * claim_a + desc[1]["coefficient"] * 555 * 8) % O.R_MOD
+    pts = O.synthetic_point(6, 401)
+    want = O.prove_batch(desc, [O.ProductMember(t_a), O.ProductMember(t_b)], 6, 2, total, lambda r, c: pts[r])
+    ma = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in t_a])
+    mb = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in t_b])
+    got = jolt_b200.prove_batch([BatchMember(**d) for d in desc], [ma, mb], 6, 2, total, lambda r, poly: pts[r])
+    assert got.challenges == want["challenges"] and got.final_claim == want["final_claim"]
+    assert got.member_claims == want["member_claims"]
+    assert [p.coefficients for p in got.round_polynomials] == want["round_polys"]
+    assert ma.final_evals() == [O.evaluate(t, pts) for t in t_a]
+
+
+@pytest.mark.parametrize("order", [HIGH_TO_LOW, LOW_TO_HIGH])
+def test_sumcheck_2pow16_vs_c_oracle(sess, order):
+    """BASELINE config 1: 2^16 sumcheck, every round polynomial and the final eval compared
+    limb-for-limb with the 1-thread C oracle; m = 2."""
+    n, m = 16, 2
+    tabs = [rand_limbs(0xB200 + j, 1 << n) for j in range(m)]
+    gpu = ProductMember(sess, [Polynomial.new(sess, t) for t in tabs], order)
+    cur = [t.copy() for t in tabs]
+    bind = None
+    for rnd in range(n):
+        if bind is not None:
+            cur = [C.bind(t, bind, order) for t in cur]
+        want = C.mont_to_ints(C.product_round_evals(cur, m, order))
+        got = gpu.prove_round_evals(bind, rnd, (want[0] + want[1]) % O.R_MOD)
+        assert got == want, f"round {rnd}"
+        bind = rand_challenge(1000 + rnd) if rnd % 2 else rand_full(1000 + rnd)
+    cur = [C.bind(t, bind, order) for t in cur]
+    gpu.finish_rounds(bind)
+    assert gpu.final_evals() == [C.mont_to_ints(t)[0] for t in cur]
+
+
+def test_sumcheck_2pow22_first_rounds_vs_c_oracle(sess):
+    """BASELINE config 2 size: rounds 0-2 at 2^22 (m = 2) vs the threaded C oracle, then the
+    size-independent property: all 22 rounds keep s(0)+s(1)==claim and end at prod f_j(point)."""
+    n, m = 22, 2
+    thr = C.max_threads()
+    tabs = [rand_limbs(0xB200 + j, 1 << n) for j in range(m)]
+    gpu = ProductMember(sess, [Polynomial.new(sess, t) for t in tabs], LOW_TO_HIGH)
+    cur = tabs
+    bind, claim = None, None
+    for rnd in range(n):
+        if rnd <= 2:
+            if bind is not None:
+                cur = [C.bind(t, bind, LOW_TO_HIGH, thr) for t in cur]
+            want = C.mont_to_ints(C.product_round_evals(cur, m, LOW_TO_HIGH, thr))
+            claim = (want[0] + want[1]) % O.R_MOD if claim is None else claim
+            got = gpu.prove_round_evals(bind, rnd, claim)
+            assert got == want
+        else:
+            got = gpu.prove_round_evals(bind, rnd, claim)   # round check enforced inside the ABI
+        poly = UnivariatePoly.from_evals(got)
+        bind = rand_challenge(2000 + rnd)
+        claim = poly.evaluate(F.from_limbs(bind))
+    gpu.finish_rounds(bind)
+    fe = gpu.final_evals()
+    assert fe[0] * fe[1] % O.R_MOD == claim
