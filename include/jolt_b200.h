@@ -110,7 +110,35 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
 int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null, size_t round,
                                    void* device_lanes_out);
 int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
+/* The host half of the above (carry-propagate + fold mod r) on `count` x 8 host lanes; needs no device. */
+int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out_elems);
+/* Copies table j of a member (current, possibly partly bound contents) to caller device memory -
+ * used to all-gather the shards once they are small (jolt_b200/dist.py). */
+int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t cap_elems, size_t* len_out);
 void jb_member_destroy(jb_member* mem);
+
+/* ---- batched engine: jolt_sumcheck::prove_batch (crates/jolt-sumcheck/src/prover.rs:193-362) over
+ *      device members, SequentialRounds traversal. BatchMember = batch.rs:24-71. The transcript stays
+ *      with the caller: `absorb` receives each round's batched polynomial (trimmed coefficients, 4
+ *      limbs each) and returns the challenge (recorder.absorb_round, recorder.rs:118-130); a non-zero
+ *      return aborts. Outputs = ProvedBatch (prover.rs:153-157) + the round polynomials, zero-padded
+ *      to max_degree+1 coefficients per round. ---------------------------------------------------- */
+typedef struct jb_batch_member {
+    uint64_t input_claim[4];
+    uint64_t coefficient[4];
+    size_t rounds;
+    size_t offset;
+} jb_batch_member;
+typedef int (*jb_absorb_round_fn)(void* user, size_t round, const uint64_t* coeffs, size_t ncoeffs,
+                                  uint64_t challenge_out[4]);
+int jb_prove_batch(jb_member** members, const jb_batch_member* desc, size_t n_members, size_t max_num_vars,
+                   size_t max_degree, const uint64_t claimed_sum[4], int check_member_rounds,
+                   jb_absorb_round_fn absorb, void* user, uint64_t* out_challenges, uint64_t out_final_claim[4],
+                   uint64_t* out_member_claims, uint64_t* out_round_polys, size_t* out_round_poly_lens);
+/* A deterministic stand-in transcript for benches/tests: 125-bit challenge [0,0,lo,hi] from the round
+ * polynomial via SplitMix64; `user` -> uint64_t seed. (Fiat-Shamir itself is out of scope.) */
+int jb_absorb_round_splitmix125(void* user, size_t round, const uint64_t* coeffs, size_t ncoeffs,
+                                uint64_t challenge_out[4]);
 
 /* ---- G1 MSM: JoltGroup::msm (crates/jolt-crypto/src/ec/group.rs:70; impl
  *      ec/bn254/mod.rs:195-212) and kzg_commit (crates/jolt-hyperkzg/src/kzg.rs:15-27) ------- */
@@ -131,6 +159,13 @@ int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, 
 /* ---- raw element-wise ops (parity harness for bn254_differential.rs:75-99) -----------------
  * field: 0 = Fr, 1 = Fq; op: 0 add, 1 sub, 2 mul, 3 mul-by-[0,0,lo,hi]. Host buffers. */
 int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* ---- observability (specs/clean-slate-prover.md:585-587 asks device backends for device-event
+ * timing): when enabled, launches of the streaming kernels over >= min_items items are bracketed
+ * by CUDA events on the context's stream. collect() synchronises and drains them.
+ * kind: 0 fused bind+eval, 1 bind, 2 eval-only, 3 eq, 4 msm bucket accumulation. */
+int jb_ctx_timing_enable(jb_ctx* ctx, int on, uint64_t min_items);
+int jb_ctx_timing_collect(jb_ctx* ctx, int* kinds, uint64_t* items, int* m, double* ms, size_t cap, size_t* count);
 
 /* ---- diagnostics (no reference counterpart): sustained Montgomery-product rate of the integer
  * pipes, used for the ALU ceiling quoted beside the HBM roofline in DESIGN.md.

@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     SumcheckError,
     UnivariatePoly,
     prove_batch,
+    prove_batch_native,
 )
 
 DensePolynomial = Polynomial  # legacy name (jolt-prover-legacy/src/poly/dense_mlpoly.rs:20)

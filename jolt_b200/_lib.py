@@ -45,7 +45,13 @@ SIGNATURES = {
     "jb_member_final_evals": (ctypes.c_int, [c_void_p, c_u64p]),
     "jb_member_prove_round_partials": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_void_p]),
     "jb_partials_finalize": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_u64p]),
+    "jb_lanes_reduce_host": (ctypes.c_int, [c_u64p, c_size_t, c_u64p]),
+    "jb_member_export_table": (ctypes.c_int, [c_void_p, c_size_t, c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_member_destroy": (None, [c_void_p]),
+    "jb_prove_batch": (ctypes.c_int, [ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_size_t, c_size_t, c_u64p,
+                                      ctypes.c_int, c_void_p, c_void_p, c_u64p, c_u64p, c_u64p, c_u64p,
+                                      ctypes.POINTER(c_size_t)]),
+    "jb_absorb_round_splitmix125": (ctypes.c_int, [c_void_p, c_size_t, c_u64p, c_size_t, c_u64p]),
     "jb_srs_upload_affine": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p]),
     "jb_srs_upload_jacobian": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p]),
     "jb_srs_len": (ctypes.c_int, [c_void_p, ctypes.c_uint64, ctypes.POINTER(c_size_t)]),
@@ -53,6 +59,9 @@ SIGNATURES = {
     "jb_srs_free": (ctypes.c_int, [c_void_p, ctypes.c_uint64]),
     "jb_msm_g1": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_u64p, c_size_t, c_u64p]),
     "jb_msm_g1_table": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, ctypes.c_uint64, c_size_t, c_u64p]),
+    "jb_ctx_timing_enable": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_uint64]),
+    "jb_ctx_timing_collect": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int), c_u64p, ctypes.POINTER(ctypes.c_int),
+                                             ctypes.POINTER(ctypes.c_double), c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_diag_mul_throughput": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_double)]),
     "jb_vec_op": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_u64p, c_u64p, c_u64p, c_size_t]),
@@ -67,6 +76,13 @@ class JoltB200Error(RuntimeError):
         self.status = status
         super().__init__(f"jolt_b200 status {status}: {detail}")
 
+
+class BatchMemberC(ctypes.Structure):
+    _fields_ = [("input_claim", ctypes.c_uint64 * 4), ("coefficient", ctypes.c_uint64 * 4),
+                ("rounds", c_size_t), ("offset", c_size_t)]
+
+
+ABSORB_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_void_p, c_size_t, c_u64p, c_size_t, c_u64p)
 
 _lib = None
 

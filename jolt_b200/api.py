@@ -65,6 +65,20 @@ class Session:
     def launch_count(self) -> int:
         return int(self.lib.jb_ctx_launch_count(self.h))
 
+    def timing_enable(self, on: bool = True, min_items: int = 0):
+        self.check(self.lib.jb_ctx_timing_enable(self.h, 1 if on else 0, min_items))
+
+    def timing_collect(self, cap: int = 4096) -> list[dict]:
+        kinds = (ctypes.c_int * cap)()
+        items = (ctypes.c_uint64 * cap)()
+        ms_m = (ctypes.c_int * cap)()
+        ms = (ctypes.c_double * cap)()
+        cnt = ctypes.c_size_t()
+        self.check(self.lib.jb_ctx_timing_collect(self.h, kinds, items, ms_m, ms, cap, ctypes.byref(cnt)))
+        names = {0: "fused_bind_eval", 1: "bind", 2: "eval_only", 3: "eq", 4: "msm_accumulate"}
+        return [dict(kind=names.get(kinds[i], str(kinds[i])), items=int(items[i]), m=int(ms_m[i]), ms=float(ms[i]))
+                for i in range(cnt.value)]
+
     def close(self):
         if self.h:
             self.lib.jb_ctx_destroy(self.h)
@@ -363,3 +377,51 @@ def prove_batch(members_desc: list[BatchMember], members: list, max_num_vars: in
         if b is not None:
             m.finish_rounds(b)
     return ProvedBatch(challenges, running, claims, polys)
+
+
+def prove_batch_native(members_desc: list[BatchMember], members: list[ProductMember], max_num_vars: int,
+                       max_degree: int, claimed_sum: int, absorb_round=None, seed: int = 0,
+                       check_member_rounds: bool = True) -> ProvedBatch:
+    """The same engine run by the C++ host layer (jolt_b200/csrc/sumcheck_host.cu) in one ABI call:
+    no Python in the round loop. absorb_round=None uses the built-in SplitMix stand-in transcript
+    (jb_absorb_round_splitmix125, seeded with `seed`)."""
+    lib = _lib.load()
+    n = len(members)
+    desc = (_lib.BatchMemberC * n)()
+    for i, d in enumerate(members_desc):
+        desc[i].input_claim[:] = [int(x) for x in F.to_limbs(d.input_claim)]
+        desc[i].coefficient[:] = [int(x) for x in F.to_limbs(d.coefficient)]
+        desc[i].rounds = d.rounds
+        desc[i].offset = d.offset
+    handles = (ctypes.c_void_p * n)(*[m.h for m in members])
+    seed_c = ctypes.c_uint64(seed)
+    if absorb_round is None:
+        fn = ctypes.cast(lib.jb_absorb_round_splitmix125, ctypes.c_void_p)
+        user = ctypes.cast(ctypes.byref(seed_c), ctypes.c_void_p)
+        keep = None
+    else:
+        def _cb(_user, rnd, coeffs, ncoeffs, out):
+            poly = UnivariatePoly([F.from_limbs([coeffs[4 * k + i] for i in range(4)]) for k in range(ncoeffs)])
+            c = F.to_limbs(absorb_round(rnd, poly))
+            for i in range(4):
+                out[i] = int(c[i])
+            return 0
+        keep = _lib.ABSORB_FN(_cb)
+        fn = ctypes.cast(keep, ctypes.c_void_p)
+        user = None
+    ch = np.zeros((max_num_vars, 4), dtype=np.uint64)
+    fin = np.zeros(4, dtype=np.uint64)
+    mc = np.zeros((n, 4), dtype=np.uint64)
+    rp = np.zeros((max_num_vars, max_degree + 1, 4), dtype=np.uint64)
+    lens = (ctypes.c_size_t * max(max_num_vars, 1))()
+    cs = F.to_limbs(claimed_sum)
+    st = lib.jb_prove_batch(handles, ctypes.cast(desc, ctypes.c_void_p), n, max_num_vars, max_degree, _p(cs),
+                            1 if check_member_rounds else 0, fn, user, _p(ch), _p(fin), _p(mc), _p(rp), lens)
+    if st != _lib.JB_OK:
+        sess = members[0].s
+        detail = sess.lib.jb_last_error(sess.h).decode() or sess.lib.jb_status_str(st).decode()
+        if st == _lib.JB_ERR_ROUND_CHECK:
+            raise SumcheckError("RoundCheckFailed: " + detail)
+        raise JoltB200Error(st, detail)
+    polys = [UnivariatePoly(F.limbs_to_ints(rp[r, : lens[r]])) for r in range(max_num_vars)]
+    return ProvedBatch(F.limbs_to_ints(ch), F.from_limbs(fin), F.limbs_to_ints(mc), polys)

@@ -58,7 +58,9 @@ template <int ORDER, bool HI4>
 int launch_bind(jb_ctx* c, const uint64_t* in, uint64_t* out, size_t half, const BindScalar& s) {
     static int per_sm = blocks_per_sm(bind_kernel<ORDER, HI4>);
     int grid = grid_for(c, half, per_sm);
+    int tix = c->timing_begin(1, half, 1);
     bind_kernel<ORDER, HI4><<<grid, 256, 0, c->stream>>>(in, out, half, s);
+    c->timing_end(tix);
     c->launches++;
     return c->check(cudaGetLastError(), "bind_kernel launch");
 }
@@ -90,7 +92,9 @@ template <int M, int ORDER, bool BIND, bool HI4>
 int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, int* grid_out) {
     static int per_sm = blocks_per_sm(fused_round_kernel<M, ORDER, BIND, HI4>);
     int grid = grid_for(c, pairs, per_sm);
+    int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
     fused_round_kernel<M, ORDER, BIND, HI4><<<grid, 256, 0, c->stream>>>(tp, pairs, s, c->d_partial);
+    c->timing_end(tix);
     c->launches++;
     *grid_out = grid;
     return c->check(cudaGetLastError(), "fused_round_kernel launch");
@@ -174,7 +178,7 @@ int jb_device_count(void) {
     return n;
 }
 
-int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
+static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** out) {
     if (!out) return JB_ERR_INVALID;
     *out = nullptr;
     int n = jb_device_count();
@@ -184,7 +188,7 @@ int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
     if (!c) return JB_ERR_OOM;
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete c; return JB_ERR_CUDA; }
-    if (cuda_stream) {
+    if (borrow) {  // a null handle is the legacy default stream
         c->stream = (cudaStream_t)cuda_stream;
         c->owns_stream = false;
     } else {
@@ -211,7 +215,11 @@ int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
     return JB_OK;
 }
 
-int jb_ctx_create(int device, jb_ctx** out) { return jb_ctx_create_on_stream(device, nullptr, out); }
+int jb_ctx_create(int device, jb_ctx** out) { return ctx_create_impl(device, false, nullptr, out); }
+
+int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
+    return ctx_create_impl(device, true, cuda_stream, out);
+}
 
 void jb_ctx_destroy(jb_ctx* c) {
     if (!c) return;
@@ -240,6 +248,38 @@ int jb_ctx_synchronize(jb_ctx* c) {
 }
 
 uint64_t jb_ctx_launch_count(jb_ctx* c) { return c ? c->launches : 0; }
+
+int jb_ctx_timing_enable(jb_ctx* c, int on, uint64_t min_items) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    c->timing = on != 0;
+    c->timing_min_items = min_items;
+    return JB_OK;
+}
+
+int jb_ctx_timing_collect(jb_ctx* c, int* kinds, uint64_t* items, int* ms_m, double* ms, size_t cap, size_t* count) {
+    if (!c || !count) return JB_ERR_INVALID;
+    Guard g(c);
+    int st = c->check(cudaStreamSynchronize(c->stream), "timing sync");
+    if (st != JB_OK) return st;
+    size_t n = 0;
+    for (auto& t : c->timed) {
+        float f = 0;
+        cudaEventElapsedTime(&f, t.e0, t.e1);
+        if (n < cap) {
+            if (kinds) kinds[n] = t.kind;
+            if (items) items[n] = t.items;
+            if (ms_m) ms_m[n] = t.m;
+            if (ms) ms[n] = f;
+            ++n;
+        }
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    c->timed.clear();
+    *count = n;
+    return JB_OK;
+}
 
 // ---- tables ------------------------------------------------------------------------------
 int jb_table_alloc(jb_ctx* c, size_t len, jb_table* out) {
@@ -523,16 +563,11 @@ int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind, size_t 
     return member_round(mem, bind, lanes_out);
 }
 
-int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint64_t* out) {
-    if (!c || !device_lanes || !out || count == 0 || count * 64 > JB_SMALL_BYTES) return JB_ERR_INVALID;
-    Guard g(c);
-    int st = c->check(cudaMemcpyAsync(c->h_small, device_lanes, count * 64, cudaMemcpyDeviceToHost, c->stream),
-                      "partials D2H");
-    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "partials sync");
-    if (st != JB_OK) return st;
-    // carry-propagate the 8 x (32-bit limb sums) and reduce mod r: O(count) host work.
+// carry-propagate 8 x (sums of 32-bit limbs) and fold mod r: O(count) host work, no device needed.
+int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out) {
+    if (!lanes || !out) return JB_ERR_INVALID;
     for (size_t k = 0; k < count; ++k) {
-        const uint64_t* lane = c->h_small + 8 * k;
+        const uint64_t* lane = lanes + 8 * k;
         uint32_t w[10];
         unsigned __int128 carry = 0;
         for (int i = 0; i < 8; ++i) {
@@ -542,7 +577,7 @@ int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint
         }
         w[8] = (uint32_t)carry;
         w[9] = (uint32_t)(carry >> 32);
-        // value < 2^32 * r < 2^286; fold by subtracting (r << k) from the top down
+        // value < 2^32 * r < 2^286; fold by subtracting (r << sh) from the top down
         uint64_t v[5] = {(uint64_t)w[0] | ((uint64_t)w[1] << 32), (uint64_t)w[2] | ((uint64_t)w[3] << 32),
                          (uint64_t)w[4] | ((uint64_t)w[5] << 32), (uint64_t)w[6] | ((uint64_t)w[7] << 32),
                          (uint64_t)w[8] | ((uint64_t)w[9] << 32)};
@@ -567,6 +602,28 @@ int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint
         std::memcpy(out + 4 * k, v, 32);
     }
     return JB_OK;
+}
+
+int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint64_t* out) {
+    if (!c || !device_lanes || !out || count == 0 || count * 64 > JB_SMALL_BYTES) return JB_ERR_INVALID;
+    Guard g(c);
+    int st = c->check(cudaMemcpyAsync(c->h_small, device_lanes, count * 64, cudaMemcpyDeviceToHost, c->stream),
+                      "partials D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "partials sync");
+    if (st != JB_OK) return st;
+    return jb_lanes_reduce_host(c->h_small, count, out);
+}
+
+// Copies table j of a member (its current, possibly partly bound, contents) into caller device memory.
+int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t cap_elems, size_t* len_out) {
+    if (!mem || !device_dst) return JB_ERR_INVALID;
+    jb_ctx* c = mem->ctx;
+    Guard g(c);
+    if (j >= (size_t)mem->m) return c->fail(JB_ERR_INVALID, "export_table: table index out of range");
+    if (cap_elems < mem->len) return c->fail(JB_ERR_INVALID, "export_table: destination too small");
+    if (len_out) *len_out = mem->len;
+    return c->check(cudaMemcpyAsync(device_dst, mem->tables[j].buf, mem->len * 32, cudaMemcpyDeviceToDevice, c->stream),
+                    "export_table D2D");
 }
 
 int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {

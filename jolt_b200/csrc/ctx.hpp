@@ -7,6 +7,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/jolt_b200.h"
 
@@ -36,6 +37,15 @@ struct Srs {
 
 struct MsmWorkspace;  // msm.cu
 
+// Optional per-launch CUDA-event timing of the dominant kernels (bench.py's roofline figure is
+// measured live, on this stream, inside the timed region).
+struct TimedLaunch {
+    cudaEvent_t e0, e1;
+    int kind;        // 0 = fused bind+eval, 1 = bind, 2 = eval-only, 3 = eq, 4 = msm bucket accumulation
+    uint64_t items;  // pairs / outputs / terms
+    int m;
+};
+
 struct jb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -51,6 +61,23 @@ struct jb_ctx {
     uint64_t* d_small = nullptr;    // device staging
     uint64_t* h_small = nullptr;    // pinned host staging
     MsmWorkspace* msm = nullptr;
+    bool timing = false;
+    uint64_t timing_min_items = 0;
+    std::vector<TimedLaunch> timed;
+
+    // returns an index into `timed` (or -1): call before the launch, then timing_end(idx) after it
+    int timing_begin(int kind, uint64_t items, int m) {
+        if (!timing || items < timing_min_items || timed.size() >= 4096) return -1;
+        TimedLaunch t;
+        t.kind = kind; t.items = items; t.m = m;
+        if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return -1;
+        cudaEventRecord(t.e0, stream);
+        timed.push_back(t);
+        return (int)timed.size() - 1;
+    }
+    void timing_end(int idx) {
+        if (idx >= 0) cudaEventRecord(timed[idx].e1, stream);
+    }
 
     int fail(int status, const char* what) {
         err = what;

@@ -163,3 +163,21 @@ def eval_univariate(coeffs: np.ndarray, u: np.ndarray) -> np.ndarray:
     lib().orc_eval_univariate(_p(out), _p(coeffs), ctypes.c_size_t(coeffs.shape[0]),
                               _p(np.ascontiguousarray(u, dtype=np.uint64)))
     return out
+
+
+# ---- synthetic inputs shared by the parity tests and bench.py's CPU leg -------------------------
+def rand_limbs(seed: int, n: int) -> np.ndarray:
+    """n canonical Montgomery elements from numpy's PCG64: draw 256 bits and clear the top 3, so the
+    raw value < 2^253 < p - every such limb pattern is a valid canonical Montgomery representative."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64(((1 << 64) - 1) >> 3)
+    return a
+
+
+def rand_challenge(seed: int) -> np.ndarray:
+    """125-bit challenge as raw Montgomery limbs [0,0,lo,hi] (jolt-field/src/bn254/mod.rs:172-184)."""
+    from . import bn254 as O
+    st, lo = O.splitmix64(seed)
+    st, hi = O.splitmix64(st)
+    return np.array(O.challenge_to_mont_limbs(lo, hi), dtype=np.uint64)

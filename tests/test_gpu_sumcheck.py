@@ -116,6 +116,33 @@ def test_engine_on_gpu_matches_oracle_engine(sess):
     assert got.member_claims == want["member_claims"]
     assert [p.coefficients for p in got.round_polynomials] == want["round_polys"]
     assert ma.final_evals() == [O.evaluate(t, pts) for t in t_a]
+    # the C++ engine (one ABI call, no Python in the round loop) must agree as well
+    ma2 = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in t_a])
+    mb2 = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in t_b])
+    nat = jolt_b200.prove_batch_native([BatchMember(**d) for d in desc], [ma2, mb2], 6, 2, total, lambda r, poly: pts[r])
+    assert nat.challenges == want["challenges"] and nat.final_claim == want["final_claim"]
+    assert nat.member_claims == want["member_claims"]
+    assert [p.coefficients for p in nat.round_polynomials] == want["round_polys"]
+    assert ma2.final_evals() == ma.final_evals()
+    with pytest.raises(jolt_b200.SumcheckError):
+        mc = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in t_a])
+        jolt_b200.prove_batch_native([BatchMember(**desc[0])], [mc], 6, 2, total + 1)
+
+
+def test_native_engine_splitmix_transcript_is_deterministic(sess):
+    tabs = [O.random_fr(11, 256), O.random_fr(12, 256)]
+    claim = sum(x * y for x, y in zip(*tabs)) % O.R_MOD
+    runs = []
+    for _ in range(2):
+        mem = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs], LOW_TO_HIGH)
+        res = jolt_b200.prove_batch_native([BatchMember(claim, 1, 8, 0)], [mem], 8, 2, claim, seed=7)
+        runs.append((res.challenges, res.final_claim, mem.final_evals()))
+    assert runs[0] == runs[1]
+    ch, fin, fe = runs[0]
+    # challenges are 125-bit [0,0,lo,hi] limbs; LowToHigh binds the last variable first
+    assert all(list(F.to_limbs(c))[:2] == [0, 0] for c in ch)
+    assert fe == [O.evaluate(t, list(reversed(ch))) for t in tabs]
+    assert fe[0] * fe[1] % O.R_MOD == fin
 
 
 @pytest.mark.parametrize("order", [HIGH_TO_LOW, LOW_TO_HIGH])

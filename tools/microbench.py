@@ -25,7 +25,8 @@ except Exception:
     pass
 
 torch.cuda.set_device(0)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
 sess = jolt_b200.Session(0, cuda_stream=stream.cuda_stream)
 lib = sess.lib
 results = []
