@@ -26,6 +26,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 import pathlib
 
@@ -39,8 +40,8 @@ UNIT = "field-ops/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=22, help="log2 entries per table per GPU")
     ap.add_argument("--m", type=int, default=2, help="tables in the product (degree)")
@@ -77,50 +78,50 @@ def config(args, world):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~2 ms period; the
+    nvidia-smi loop of B200_PROFILING.md is too coarse for a timed region of tens of ms)."""
 
     def __init__(self, index: int):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
+        self.samples, self.reasons, self.smax, self._stop = [], set(), None, False
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+
+    def _run(self):
+        nv = self.nv
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        if self.thread is None:
             return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, smax = [], set(), None
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); smax = float(f[2])
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            busy = sorted(s for s in sm if smax is None or s > 0.3 * smax) or sorted(sm)
-            out.update(sm_mhz=busy[len(busy) // 2], sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        self._stop = True
+        self.thread.join(timeout=2)
+        if self.samples:
+            s = sorted(self.samples)
+            out.update(sm_mhz=s[len(s) // 2], reasons=sorted(self.reasons), samples=len(s))
         return out
 
 
@@ -236,7 +237,7 @@ def run_ours(args):
     else:
         from jolt_b200.dist import lanes_to_ints
         lanes = torch.zeros((m + 1) * 8, dtype=torch.int64, device="cuda")
-        sess.check(sess.lib.jb_member_prove_round_partials(probe.h, None, 0, lanes.data_ptr()))
+        sess.check(sess.lib.jb_member_prove_round_partials(probe.h, None, 0, 0, lanes.data_ptr()))
         dist.all_reduce(lanes)
         ev = lanes_to_ints(lanes.cpu().numpy().view(np.uint64))
     claim = (ev[0] + ev[1]) % F.R_MOD

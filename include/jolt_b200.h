@@ -60,6 +60,9 @@ int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out);
 void jb_ctx_destroy(jb_ctx* ctx);
 const char* jb_last_error(jb_ctx* ctx);
 int jb_ctx_synchronize(jb_ctx* ctx);
+/* 1: members compute s(1) and check every round against the claim (reference tier); 0 (default):
+ * s(1) = claim - s(0) (optimized tier). Proof-invariant: both yield identical round polynomials. */
+int jb_ctx_set_verify_rounds(jb_ctx* ctx, int on);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches claim). */
 uint64_t jb_ctx_launch_count(jb_ctx* ctx);
 
@@ -96,18 +99,21 @@ int jb_member_num_rounds(jb_member* mem, size_t* rounds);
 int jb_member_degree(jb_member* mem, size_t* degree);
 /* prove_round(bind, round, previous_claim): binds `bind_or_null` (NULL on the first active round)
  * and returns the evaluations s(0..degree) (degree+1 elements) of the round polynomial, fused in
- * one pass over the tables. Returns JB_ERR_ROUND_CHECK if s(0)+s(1) != previous_claim
- * (naive.rs:301-308); pass previous_claim_or_null == NULL to skip the check. */
+ * one pass over the tables. With a claim, s(1) is derived as previous_claim - s(0) (the optimized
+ * tier's convention, jolt-kernels/src/optimized/support.rs:450-460) unless
+ * jb_ctx_set_verify_rounds(ctx, 1) is in force, in which case every point is computed and
+ * JB_ERR_ROUND_CHECK is returned if s(0)+s(1) != previous_claim (the reference tier,
+ * naive.rs:301-308). Without a claim every point is computed and nothing is checked. */
 int jb_member_prove_round(jb_member* mem, const uint64_t* bind_or_null, size_t round,
                           const uint64_t* previous_claim_or_null, uint64_t* out_evals);
 /* finish_rounds(bind): the terminal bind. */
 int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]);
 /* The m fully bound table values (SumcheckKernel::output_claims, kernel.rs:72-126). */
 int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
-/* Multi-GPU: like prove_round but leaves this rank's degree+1 partial sums on the device as
- * (degree+1) x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32
+/* Multi-GPU: like prove_round but leaves this rank's partial sums - s(0..degree), or with skip_t1
+ * s(0), s(2), .., s(degree) - on the device as count x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32
  * ranks); the caller all-reduces that buffer and calls jb_partials_finalize. No round check. */
-int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null, size_t round,
+int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null, size_t round, int skip_t1,
                                    void* device_lanes_out);
 int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
 /* The host half of the above (carry-propagate + fold mod r) on `count` x 8 host lanes; needs no device. */

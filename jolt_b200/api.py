@@ -65,6 +65,11 @@ class Session:
     def launch_count(self) -> int:
         return int(self.lib.jb_ctx_launch_count(self.h))
 
+    def set_verify_rounds(self, on: bool = True):
+        """on: members compute s(1) and check s(0)+s(1)==claim (reference tier, naive.rs:301-308);
+        off (default): s(1) = claim - s(0) (optimized tier, support.rs:450-460)."""
+        self.check(self.lib.jb_ctx_set_verify_rounds(self.h, 1 if on else 0))
+
     def timing_enable(self, on: bool = True, min_items: int = 0):
         self.check(self.lib.jb_ctx_timing_enable(self.h, 1 if on else 0, min_items))
 

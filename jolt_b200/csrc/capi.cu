@@ -49,7 +49,6 @@ int blocks_per_sm(K kernel) {
 int grid_for(jb_ctx* c, size_t items, int per_sm) {
     size_t need = (items + 255) / 256;
     size_t cap = (size_t)c->sm_count * per_sm;
-    if (cap > JB_MAX_PARTIAL_BLOCKS) cap = JB_MAX_PARTIAL_BLOCKS;
     size_t g = need < cap ? need : cap;
     return g < 1 ? 1 : (int)g;
 }
@@ -88,40 +87,52 @@ int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
     return st;
 }
 
-template <int M, int ORDER, bool BIND, bool HI4>
-int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, int* grid_out) {
-    static int per_sm = blocks_per_sm(fused_round_kernel<M, ORDER, BIND, HI4>);
-    int grid = grid_for(c, pairs, per_sm);
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
+int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
+    static int per_sm = blocks_per_sm(fused_round_kernel<M, ORDER, BIND, HI4, SKIP1>);
+    // a thread may run at most FUSED_MAX_ITERS iterations (512-bit accumulator headroom)
+    size_t need = (pairs + 255) / 256;
+    size_t resident = (size_t)c->sm_count * per_sm;
+    size_t min_grid = (need + FUSED_MAX_ITERS - 1) / FUSED_MAX_ITERS;
+    size_t grid = need < resident ? need : resident;
+    if (grid < min_grid) grid = min_grid;
+    if (grid < 1) grid = 1;
+    constexpr int K = FusedShape<M, SKIP1>::K;
+    int st = c->ensure_partial(grid * K);
+    if (st != JB_OK) return st;
+    out.partial = c->d_partial;
     int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
-    fused_round_kernel<M, ORDER, BIND, HI4><<<grid, 256, 0, c->stream>>>(tp, pairs, s, c->d_partial);
+    fused_round_kernel<M, ORDER, BIND, HI4, SKIP1><<<(unsigned)grid, 256, 0, c->stream>>>(tp, pairs, s, out);
     c->timing_end(tix);
     c->launches++;
-    *grid_out = grid;
     return c->check(cudaGetLastError(), "fused_round_kernel launch");
 }
 
-template <int M, int ORDER>
+template <int M, int ORDER, bool SKIP1>
 int dispatch_fused2(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
-                    int* grid) {
-    if (!bind) return launch_fused<M, ORDER, false, false>(c, tp, pairs, s, grid);
-    return hi4 ? launch_fused<M, ORDER, true, true>(c, tp, pairs, s, grid)
-               : launch_fused<M, ORDER, true, false>(c, tp, pairs, s, grid);
+                    const RoundOut& out) {
+    if (!bind) return launch_fused<M, ORDER, false, false, SKIP1>(c, tp, pairs, s, out);
+    return hi4 ? launch_fused<M, ORDER, true, true, SKIP1>(c, tp, pairs, s, out)
+               : launch_fused<M, ORDER, true, false, SKIP1>(c, tp, pairs, s, out);
 }
 
 template <int M>
-int dispatch_fused1(jb_ctx* c, int order, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
-                    const BindScalar& s, int* grid) {
-    return order == JB_HIGH_TO_LOW ? dispatch_fused2<M, ORDER_HIGH_TO_LOW>(c, tp, pairs, bind, hi4, s, grid)
-                                   : dispatch_fused2<M, ORDER_LOW_TO_HIGH>(c, tp, pairs, bind, hi4, s, grid);
+int dispatch_fused1(jb_ctx* c, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
+                    const BindScalar& s, const RoundOut& out) {
+    if (order == JB_HIGH_TO_LOW)
+        return skip1 ? dispatch_fused2<M, ORDER_HIGH_TO_LOW, true>(c, tp, pairs, bind, hi4, s, out)
+                     : dispatch_fused2<M, ORDER_HIGH_TO_LOW, false>(c, tp, pairs, bind, hi4, s, out);
+    return skip1 ? dispatch_fused2<M, ORDER_LOW_TO_HIGH, true>(c, tp, pairs, bind, hi4, s, out)
+                 : dispatch_fused2<M, ORDER_LOW_TO_HIGH, false>(c, tp, pairs, bind, hi4, s, out);
 }
 
-int dispatch_fused(jb_ctx* c, int m, int order, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
-                   const BindScalar& s, int* grid) {
+int dispatch_fused(jb_ctx* c, int m, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
+                   const BindScalar& s, const RoundOut& out) {
     switch (m) {
-        case 1: return dispatch_fused1<1>(c, order, tp, pairs, bind, hi4, s, grid);
-        case 2: return dispatch_fused1<2>(c, order, tp, pairs, bind, hi4, s, grid);
-        case 3: return dispatch_fused1<3>(c, order, tp, pairs, bind, hi4, s, grid);
-        case 4: return dispatch_fused1<4>(c, order, tp, pairs, bind, hi4, s, grid);
+        case 1: return dispatch_fused1<1>(c, order, skip1, tp, pairs, bind, hi4, s, out);
+        case 2: return dispatch_fused1<2>(c, order, skip1, tp, pairs, bind, hi4, s, out);
+        case 3: return dispatch_fused1<3>(c, order, skip1, tp, pairs, bind, hi4, s, out);
+        case 4: return dispatch_fused1<4>(c, order, skip1, tp, pairs, bind, hi4, s, out);
         default: return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
     }
 }
@@ -204,9 +215,12 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
         uint64_t thresh = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
     }
-    bool ok = cudaMalloc((void**)&c->d_partial, (size_t)JB_MAX_PARTIAL_BLOCKS * JB_MAX_EVALS * 32) == cudaSuccess &&
-              cudaMalloc((void**)&c->d_small, JB_SMALL_BYTES) == cudaSuccess &&
-              cudaMallocHost((void**)&c->h_small, JB_SMALL_BYTES) == cudaSuccess;
+    bool ok = cudaMalloc((void**)&c->d_small, JB_SMALL_BYTES) == cudaSuccess &&
+              cudaMallocHost((void**)&c->h_small, JB_SMALL_BYTES) == cudaSuccess &&
+              cudaHostAlloc((void**)&c->h_result, 1024, cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer((void**)&c->d_result_alias, c->h_result, 0) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_counter, 64) == cudaSuccess && cudaMemset(c->d_counter, 0, 64) == cudaSuccess;
+    if (ok) std::memset(c->h_result, 0, 1024);
     if (!ok) {
         jb_ctx_destroy(c);
         return JB_ERR_OOM;
@@ -232,9 +246,11 @@ void jb_ctx_destroy(jb_ctx* c) {
     }
     c->srs.clear();
     c->msm_release();
-    if (c->d_partial) cudaFree(c->d_partial);
+    if (c->d_partial) cudaFreeAsync(c->d_partial, c->stream);
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->d_counter) cudaFree(c->d_counter);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -479,7 +495,7 @@ int jb_member_degree(jb_member* mem, size_t* degree) {
 
 // Runs the fused pass; on return d_small[0..m] holds the m+1 sums (canonical) or, if lanes_out,
 // lanes_out holds them widened to one 32-bit limb per u64.
-static int member_round(jb_member* mem, const uint64_t* bind, void* lanes_out) {
+static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* lanes_out) {
     jb_ctx* c = mem->ctx;
     bool do_bind = bind != nullptr;
     bool hi4 = false;
@@ -507,8 +523,19 @@ static int member_round(jb_member* mem, const uint64_t* bind, void* lanes_out) {
             tp.out[j] = t.alt;
         }
     }
-    int grid = 0;
-    int st = dispatch_fused(c, mem->m, mem->order, tp, pairs, do_bind, hi4, s, &grid);
+    RoundOut ro;
+    ro.partial = nullptr;  // set by launch_fused
+    ro.counter = c->d_counter;
+    ro.lanes = lanes_out ? 1 : 0;
+    ro.seq = ++c->result_seq;
+    if (lanes_out) {
+        ro.result = (uint64_t*)lanes_out;
+        ro.flag = nullptr;
+    } else {
+        ro.result = c->d_result_alias;
+        ro.flag = c->d_result_alias + 64;
+    }
+    int st = dispatch_fused(c, mem->m, mem->order, skip1, tp, pairs, do_bind, hi4, s, ro);
     if (st != JB_OK) return st;
     if (do_bind) {
         for (int j = 0; j < mem->m; ++j) {
@@ -517,14 +544,26 @@ static int member_round(jb_member* mem, const uint64_t* bind, void* lanes_out) {
         }
         mem->len = len;
     }
-    int K = mem->m + 1;
-    if (lanes_out) {
-        sum_partials_lanes_kernel<<<1, 256, 0, c->stream>>>(c->d_partial, grid, K, (uint64_t*)lanes_out);
-    } else {
-        sum_partials_kernel<<<1, 256, 0, c->stream>>>(c->d_partial, grid, K, c->d_small);
+    return JB_OK;
+}
+
+// Spin until the last block of the round's launch has published `seq` (results are then visible).
+static int wait_round_result(jb_ctx* c) {
+    volatile uint64_t* flag = c->h_result + 64;
+    const uint64_t want = c->result_seq;
+    uint64_t spins = 0;
+    while (*flag != want) {
+        if ((++spins & 0xfffff) == 0) {  // every ~1M spins make sure the stream has not died
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return c->check(e, "round kernel failed");
+            if (e == cudaSuccess && *flag != want) return c->fail(JB_ERR_CUDA, "round kernel finished without publishing its result");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
     }
-    c->launches++;
-    return c->check(cudaGetLastError(), "sum_partials launch");
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return JB_OK;
 }
 
 int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
@@ -538,13 +577,24 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
         while (l > 1) { l >>= 1; --bound; }  // bound = rounds already bound
     }
     if (round != bound + (bind ? 1 : 0)) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
-    int st = member_round(mem, bind, nullptr);
+    // With a claim and round verification off (the default, = the reference's optimized tier) the
+    // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
+    // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
+    const bool skip1 = claim != nullptr && !c->verify_rounds;
+    int st = member_round(mem, bind, skip1, nullptr);
     if (st != JB_OK) return st;
-    int K = mem->m + 1;
-    st = c->check(cudaMemcpyAsync(c->h_small, c->d_small, (size_t)K * 32, cudaMemcpyDeviceToHost, c->stream), "round D2H");
-    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "round sync");
+    const int M = mem->m;
+    st = wait_round_result(c);
     if (st != JB_OK) return st;
-    std::memcpy(out_evals, c->h_small, (size_t)K * 32);
+    if (skip1) {
+        HostFr s0 = HostFr::from_limbs(c->h_result);
+        HostFr s1 = HostFr::from_limbs(claim) - s0;
+        s0.store(out_evals);
+        s1.store(out_evals + 4);
+        if (M > 1) std::memcpy(out_evals + 8, c->h_result + 4, (size_t)(M - 1) * 32);
+        return JB_OK;
+    }
+    std::memcpy(out_evals, c->h_result, (size_t)(M + 1) * 32);
     if (claim) {
         HostFr s0 = HostFr::from_limbs(out_evals), s1 = HostFr::from_limbs(out_evals + 4);
         if ((s0 + s1) != HostFr::from_limbs(claim)) {
@@ -556,11 +606,18 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     return JB_OK;
 }
 
-int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind, size_t round, void* lanes_out) {
+int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind, size_t round, int skip_t1, void* lanes_out) {
     (void)round;
     if (!mem || !lanes_out) return JB_ERR_INVALID;
     Guard g(mem->ctx);
-    return member_round(mem, bind, lanes_out);
+    return member_round(mem, bind, skip_t1 != 0, lanes_out);
+}
+
+int jb_ctx_set_verify_rounds(jb_ctx* c, int on) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    c->verify_rounds = on != 0;
+    return JB_OK;
 }
 
 // carry-propagate 8 x (sums of 32-bit limbs) and fold mod r: O(count) host work, no device needed.

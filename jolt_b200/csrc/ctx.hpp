@@ -11,7 +11,6 @@
 
 #include "../../include/jolt_b200.h"
 
-constexpr int JB_MAX_PARTIAL_BLOCKS = 148 * 8;  // per-block partial-sum slots (grid cap for fused passes)
 constexpr int JB_MAX_EVALS = 8;                 // degree + 1 <= 8
 constexpr size_t JB_SMALL_BYTES = 4096;         // staging for round evaluations / points
 
@@ -57,9 +56,16 @@ struct jb_ctx {
     uint64_t next_id = 1;
     std::string err;
     uint64_t launches = 0;
-    uint64_t* d_partial = nullptr;  // JB_MAX_PARTIAL_BLOCKS * JB_MAX_EVALS elements
+    uint64_t* d_partial = nullptr;  // per-block partial sums of the running fused pass
+    size_t partial_cap = 0;         // in elements
+    bool verify_rounds = false;     // compute s(1) and check s(0)+s(1)==claim instead of deriving s(1)
     uint64_t* d_small = nullptr;    // device staging
     uint64_t* h_small = nullptr;    // pinned host staging
+    // zero-copy round results: pinned + mapped; [0, 64) u64 results, [64] sequence flag
+    uint64_t* h_result = nullptr;
+    uint64_t* d_result_alias = nullptr;  // device address of h_result
+    unsigned int* d_counter = nullptr;   // last-block ticket counter (zero between launches)
+    uint64_t result_seq = 0;
     MsmWorkspace* msm = nullptr;
     bool timing = false;
     uint64_t timing_min_items = 0;
@@ -114,6 +120,16 @@ struct jb_ctx {
         t.alt_owned = true;
         int st = dev_alloc((void**)&t.alt, elems * 32);
         if (st == JB_OK) t.alt_cap = elems;
+        return st;
+    }
+    int ensure_partial(size_t elems) {
+        if (elems <= partial_cap) return JB_OK;
+        if (d_partial) dev_free(d_partial);
+        d_partial = nullptr;
+        partial_cap = 0;
+        size_t want = elems < 8192 ? 8192 : elems;
+        int st = dev_alloc((void**)&d_partial, want * 32);
+        if (st == JB_OK) partial_cap = want;
         return st;
     }
     void release(Table& t) {

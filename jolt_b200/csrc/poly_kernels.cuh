@@ -91,6 +91,72 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], uint32_t* smem) {
     }
 }
 
+// Where a fused pass leaves its M+1 round sums. The last block to finish (ticket from `counter`)
+// folds the per-block partials, so a round is ONE launch; the totals go either to host-mapped
+// pinned memory followed by a sequence flag the host spins on (no memcpy, no stream sync - the
+// Fiat-Shamir round trip is the latency floor of a sumcheck), or to device lanes for NCCL.
+struct RoundOut {
+    uint64_t* partial;    // gridDim.x * K canonical elements
+    unsigned int* counter;  // zero on entry, reset to zero by the last block
+    uint64_t* result;     // lanes == 0: K canonical elements (host-mapped); lanes == 1: K*8 u64 device lanes
+    volatile uint64_t* flag;  // host-mapped; set to `seq` after the results are visible (may be null)
+    uint64_t seq;
+    int lanes;
+};
+
+template <class F>
+__device__ __forceinline__ F ld_elem_cg(const uint64_t* base, size_t idx) {
+    F r;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(base) + idx * 8;
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                   "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+// Called by every thread of every block after thread 0 holds the block's K sums in acc[].
+template <int K>
+__device__ __forceinline__ void round_epilogue(Fr (&acc)[K], uint32_t* smem, const RoundOut& out) {
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < K; ++t) st_elem(out.partial, (size_t)blockIdx.x * K + t, acc[t]);
+        __threadfence();
+        unsigned int ticket = atomicAdd(out.counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    Fr tot[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        tot[t] = Fr::zero();
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+            tot[t] = fp_add(tot[t], ld_elem_cg<Fr>(out.partial, (size_t)b * K + t));
+    }
+    block_sum<K>(tot, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < K; ++t) {
+            if (out.lanes) {
+#pragma unroll
+                for (int w = 0; w < 8; ++w) out.result[t * 8 + w] = tot[t].v[w];
+            } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+                    out.result[t * 4 + w] = (uint64_t)tot[t].v[2 * w] | ((uint64_t)tot[t].v[2 * w + 1] << 32);
+            }
+        }
+        *out.counter = 0;
+        if (out.flag) {
+            __threadfence_system();
+            *out.flag = out.seq;
+        }
+    }
+}
+
 struct TablePtrs {
     const uint64_t* in[4];
     uint64_t* out[4];
@@ -98,20 +164,41 @@ struct TablePtrs {
 
 // Fused pass for a product-of-M member:
 //   BIND: first fold every table under `s` (writing the bound table), then
-//   evaluate s(t) = sum_y prod_j (lo_j(y) + t (hi_j(y) - lo_j(y))), t = 0..M, over the BOUND tables.
+//   evaluate s(t) = sum_y prod_j (lo_j(y) + t (hi_j(y) - lo_j(y))) over the BOUND tables, for
+//   t = 0..M, or - SKIP1, the reference's optimized-tier convention
+//   (jolt-kernels/src/optimized/support.rs:450-460) - for t in {0, 2, .., M}, the host deriving
+//   s(1) = previous_claim - s(0).
 // `pairs` = number of y indices = (bound length)/2. Layout:
 //   HighToLow, BIND : reads e[y], e[y+P], e[y+2P], e[y+3P] (P = pairs); writes e'[y], e'[y+P] in place
 //   LowToHigh, BIND : reads e[4y..4y+3]; writes out[2y], out[2y+1]   (out-of-place)
 //   no BIND         : reads the pair only, writes nothing
-// Each block writes its M+1 partial sums to partial[blockIdx.x*(M+1) + t] (canonical limbs);
-// sum_partials_kernel folds them. No atomics, deterministic values.
-template <int M, int ORDER, bool BIND, bool HI4>
-__global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s,
-                                                          uint64_t* partial) {
-    __shared__ uint32_t smem[8 * (M + 1) * 8];
-    Fr acc[M + 1];
+// The last factor of every product is multiplied in WITHOUT reduction into a 512-bit per-thread
+// accumulator (mul_wide_acc) and reduced once after the loop, so a thread may run at most
+// FUSED_MAX_ITERS iterations (the host sizes the grid accordingly). M == 1 has no product and
+// accumulates plain field sums. Each block then writes its sums and the last block folds them
+// (round_epilogue). All sums are exact field values, so the reduction order does not matter.
+constexpr int FUSED_MAX_ITERS = 8;
+
+template <int M, bool SKIP1>
+struct FusedShape {
+    static constexpr int K = SKIP1 ? M : M + 1;  // number of evaluation points produced
+};
+
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
+__global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
+    constexpr int K = FusedShape<M, SKIP1>::K;
+    __shared__ uint32_t smem[8 * K * 8];
+    uint32_t wide[M == 1 ? 1 : K][16];
+    Fr sum1[M == 1 ? K : 1];
+    if (M == 1) {
 #pragma unroll
-    for (int t = 0; t <= M; ++t) acc[t] = Fr::zero();
+        for (int e = 0; e < K; ++e) sum1[e] = Fr::zero();
+    } else {
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+#pragma unroll
+            for (int w = 0; w < 16; ++w) wide[e][w] = 0;
+    }
 
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
@@ -150,57 +237,34 @@ __global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t p
                 }
             }
             cur[j] = lo;
-            dlt[j] = fp_sub(hi, lo);
+            if (!(M == 1 && SKIP1)) dlt[j] = fp_sub(hi, lo);
         }
+        int e = 0;
 #pragma unroll
         for (int t = 0; t <= M; ++t) {
-            Fr prod = cur[0];
+            if (!(SKIP1 && t == 1)) {
+                if (M == 1) {
+                    sum1[e] = fp_add(sum1[e], cur[0]);
+                } else {
+                    Fr prod = cur[0];
 #pragma unroll
-            for (int j = 1; j < M; ++j) prod = fp_mul(prod, cur[j]);
-            acc[t] = fp_add(acc[t], prod);
-            if (t < M) {
+                    for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, cur[j]);
+                    mul_wide_acc(wide[e], prod.v, cur[M - 1].v);
+                }
+                ++e;
+            }
+            if (t < M && !(M == 1 && SKIP1)) {
 #pragma unroll
                 for (int j = 0; j < M; ++j) cur[j] = fp_add(cur[j], dlt[j]);
             }
         }
     }
-    block_sum<M + 1>(acc, smem);
-    if (threadIdx.x == 0) {
+    Fr acc[K];
 #pragma unroll
-        for (int t = 0; t <= M; ++t) st_elem(partial, (size_t)blockIdx.x * (M + 1) + t, acc[t]);
-    }
-}
-
-// out[t] = sum_b partial[b*K + t], one block. K <= 8.
-__global__ void __launch_bounds__(256) sum_partials_kernel(const uint64_t* partial, int nblocks, int K,
-                                                           uint64_t* out) {
-    __shared__ uint32_t smem[8 * 8];
-    for (int t = 0; t < K; ++t) {
-        Fr acc[1] = {Fr::zero()};
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
-            acc[0] = fp_add(acc[0], ld_elem_rw<Fr>(partial, (size_t)b * K + t));
-        block_sum<1>(acc, smem);
-        if (threadIdx.x == 0) st_elem(out, t, acc[0]);
-        __syncthreads();
-    }
-}
-
-// Multi-GPU variant: the K block-reduced sums leave as 8 u64 lanes each holding one 32-bit limb,
-// so an integer ncclSum over ranks is exact; the carry + mod-r fold happens after the all-reduce.
-__global__ void __launch_bounds__(256) sum_partials_lanes_kernel(const uint64_t* partial, int nblocks, int K,
-                                                                 uint64_t* lanes) {
-    __shared__ uint32_t smem[8 * 8];
-    for (int t = 0; t < K; ++t) {
-        Fr acc[1] = {Fr::zero()};
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x)
-            acc[0] = fp_add(acc[0], ld_elem_rw<Fr>(partial, (size_t)b * K + t));
-        block_sum<1>(acc, smem);
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) lanes[t * 8 + w] = acc[0].v[w];
-        }
-        __syncthreads();
-    }
+    for (int e = 0; e < K; ++e) acc[e] = (M == 1) ? sum1[e] : reduce_wide<FrParams>(wide[e]);
+    block_sum<K>(acc, smem);
+    __syncthreads();  // smem is reused by the last block's fold
+    round_epilogue<K>(acc, smem, out);
 }
 
 // ---- eq-table expansion --------------------------------------------------------------------

@@ -69,21 +69,23 @@ class ShardedProductSumcheck:
 
     def prove(self, claimed_sum: int | None = None):
         torch, lib, mem, m = self.torch, self.s.lib, self.mem, self.m
-        K = m + 1
-        lanes = torch.zeros(K * 8, dtype=torch.int64, device="cuda")
-        out = np.empty((K, 4), dtype=np.uint64)
+        lanes = torch.zeros((m + 1) * 8, dtype=torch.int64, device="cuda")
+        out = np.empty((m + 1, 4), dtype=np.uint64)
         challenges, polys = [], []
         bind, claim = None, claimed_sum
         sharded_rounds = self.log_n - self.gather_log
         for rnd in range(sharded_rounds):
             b = None if bind is None else F.to_limbs(bind)
+            skip = claim is not None  # s(1) = claim - s(0): one point fewer to compute and to reduce
+            cnt = m if skip else m + 1
             self.s.check(lib.jb_member_prove_round_partials(mem.h, _p(b) if b is not None else None, rnd,
-                                                            ctypes.c_void_p(lanes.data_ptr())))
-            self.dist.all_reduce(lanes)  # integer sum of 32-bit limbs: exact
-            self.s.check(lib.jb_partials_finalize(self.s.h, ctypes.c_void_p(lanes.data_ptr()), K, _p(out)))
-            poly = UnivariatePoly.from_evals(F.limbs_to_ints(out))
-            if claim is not None and (poly.evaluate(0) + poly.evaluate(1)) % F.R_MOD != claim:
-                raise SumcheckError(f"RoundCheckFailed {{ round: {rnd} }}")
+                                                            1 if skip else 0, ctypes.c_void_p(lanes.data_ptr())))
+            self.dist.all_reduce(lanes[: cnt * 8])  # integer sum of 32-bit limbs: exact
+            self.s.check(lib.jb_partials_finalize(self.s.h, ctypes.c_void_p(lanes.data_ptr()), cnt, _p(out)))
+            ev = F.limbs_to_ints(out[:cnt])
+            if skip:
+                ev.insert(1, (claim - ev[0]) % F.R_MOD)
+            poly = UnivariatePoly.from_evals(ev)
             c = splitmix_challenge(self.seed, poly)
             claim = poly.evaluate(c)
             challenges.append(c)

@@ -20,8 +20,8 @@ def sess():
 @pytest.mark.parametrize("fld,p", [(0, O.R_MOD), (1, O.Q_MOD)])
 def test_vec_ops_bit_exact(sess, fld, p):
     n = 1 << 20
-    a = rand_limbs(11 + fld, n, p)
-    b = rand_limbs(22 + fld, n, p)
+    a = rand_limbs(11 + fld, n)   # raw < 2^253 < both moduli: canonical for Fr and Fq
+    b = rand_limbs(22 + fld, n)
     edge = C.ints_to_mont([e % p for e in EDGE_INTS], p)
     k = len(EDGE_INTS)
     # all edge x edge pairs up front

@@ -80,10 +80,37 @@ def test_roundtrip_degree2_and_3_fixtures(sess):
 
 
 def test_round_check_failure_is_an_error(sess):
+    # reference tier behaviour (naive.rs:301-308): with round verification on, a wrong claim is an error
     tabs = [O.random_fr(1, 16), O.random_fr(2, 16)]
     gpu = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs])
-    with pytest.raises(jolt_b200.SumcheckError, match="RoundCheckFailed"):
-        gpu.prove_round(None, 0, 12345)
+    sess.set_verify_rounds(True)
+    try:
+        with pytest.raises(jolt_b200.SumcheckError, match="RoundCheckFailed"):
+            gpu.prove_round(None, 0, 12345)
+    finally:
+        sess.set_verify_rounds(False)
+
+
+@pytest.mark.parametrize("m", [1, 2, 3])
+def test_verify_and_hint_modes_agree(sess, m):
+    """s(1) derived from the claim (optimized tier) == s(1) computed (reference tier) == no claim at all."""
+    n = 8
+    tabs = [O.random_fr(700 + j, 1 << n) for j in range(m)]
+    ch = O.random_fr(5, n)
+    outs = []
+    for mode in ("hint", "verify", "noclaim"):
+        sess.set_verify_rounds(mode == "verify")
+        gpu = ProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs], LOW_TO_HIGH)
+        claim = sum(np.prod([t[i] for t in tabs], dtype=object) for i in range(1 << n)) % O.R_MOD
+        bind, seq = None, []
+        for rnd in range(n):
+            ev = gpu.prove_round_evals(bind, rnd, None if mode == "noclaim" else claim)
+            seq.append(ev)
+            bind = ch[rnd]
+            claim = UnivariatePoly.from_evals(ev).evaluate(bind)
+        outs.append(seq)
+    sess.set_verify_rounds(False)
+    assert outs[0] == outs[1] == outs[2]
 
 
 def test_member_misuse_errors(sess):
