@@ -25,12 +25,31 @@ HostFr UnivariatePoly::evaluate(const HostFr& x) const {
 // Interpolation on nodes 0..n-1. The reference solves the Vandermonde system by Gaussian
 // elimination (univariate.rs:470-487); the interpolant is unique, so Newton's divided
 // differences on equally spaced nodes give identical coefficients.
+namespace {
+// 1/k! for k < 32, computed once (a field inversion is ~400 multiplications - far too slow to
+// repeat on the per-round latency path).
+const HostFr* inverse_factorials() {
+    static HostFr table[32];
+    static bool init = [] {
+        HostFr f = HostFr::one();
+        table[0] = f;
+        for (uint64_t k = 1; k < 32; ++k) {
+            f = f * HostFr::from_u64(k);
+            table[k] = f.inverse();
+        }
+        return true;
+    }();
+    (void)init;
+    return table;
+}
+}  // namespace
+
 UnivariatePoly UnivariatePoly::from_evals(const std::vector<HostFr>& evals) {
     const size_t n = evals.size();
     std::vector<HostFr> diff(evals), newton(n, HostFr::zero());
-    HostFr fact_inv = HostFr::one();
+    const HostFr* inv_fact = inverse_factorials();
     for (size_t k = 0; k < n; ++k) {
-        if (k > 1) fact_inv = fact_inv * HostFr::from_u64(k).inverse();
+        const HostFr fact_inv = k < 32 ? inv_fact[k] : HostFr::zero();
         newton[k] = diff[0] * fact_inv;  // k-th forward difference / k!
         for (size_t i = 0; i + 1 < diff.size(); ++i) diff[i] = diff[i + 1] - diff[i];
         if (!diff.empty()) diff.pop_back();
@@ -110,7 +129,7 @@ int prove_batch(const BatchPrelude& prelude, std::vector<ProveRounds*>& members,
     const size_t max_num_vars = prelude.max_num_vars;
     if (max_num_vars > 0 && prelude.max_degree < 1) return fail(JB_ERR_INVALID, "ZeroBatchDegree");
 
-    const HostFr two_inv = HostFr::from_u64(2).inverse();
+    static const HostFr two_inv = HostFr::from_u64(2).inverse();
     std::vector<HostFr> member_claims(members.size());
     for (size_t i = 0; i < members.size(); ++i) {
         HostFr c = prelude.members[i].input_claim;  // input_claim * 2^(max - rounds)
