@@ -155,9 +155,11 @@ int jb_srs_upload_jacobian(jb_ctx* ctx, const uint64_t* xyz_limbs, size_t n, jb_
 int jb_srs_len(jb_ctx* ctx, jb_srs s, size_t* n);
 int jb_srs_download_affine(jb_ctx* ctx, jb_srs s, uint64_t* out_xy, size_t n);
 int jb_srs_free(jb_ctx* ctx, jb_srs s);
-/* sum_i scalars[i] * bases[offset + i], i < n; scalars = host Montgomery limbs. Result as Jacobian
- * X, Y, Z (Z = 1, or Z = 0 for the identity). n == 0 -> identity (group_laws.rs:143-146);
- * offset + n > srs length -> JB_ERR_LENGTH (mod.rs:200-204). */
+/* sum_i scalars[i] * bases[offset + i], i < n; scalars = host Montgomery limbs (any Fr value, the
+ * canonical integer is used, mod.rs:208). Result: a Jacobian representative X, Y, Z of the group
+ * value (x = X/Z^2, y = Y/Z^3; Z = 0 for the identity) - `Bn254G1` equality is projective, so no
+ * normalisation is needed (or paid for) at the boundary. n == 0 -> identity (group_laws.rs:143-146);
+ * offset + n > srs length -> JB_ERR_LENGTH (the reference panics, mod.rs:200-204). */
 int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);

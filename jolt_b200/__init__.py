@@ -14,12 +14,16 @@ from .api import (  # noqa: F401
     LOW_TO_HIGH,
     BatchMember,
     EqPolynomial,
+    G1Bases,
     Polynomial,
     ProductMember,
     ProvedBatch,
     Session,
     SumcheckError,
     UnivariatePoly,
+    g1_affine_limbs,
+    g1_jacobian_to_affine,
+    msm,
     prove_batch,
     prove_batch_native,
 )

@@ -430,3 +430,87 @@ def prove_batch_native(members_desc: list[BatchMember], members: list[ProductMem
         raise JoltB200Error(st, detail)
     polys = [UnivariatePoly(F.limbs_to_ints(rp[r, : lens[r]])) for r in range(max_num_vars)]
     return ProvedBatch(F.limbs_to_ints(ch), F.from_limbs(fin), F.limbs_to_ints(mc), polys)
+
+
+# ---- G1 / MSM ---------------------------------------------------------------------------------------
+def g1_jacobian_to_affine(xyz_limbs) -> tuple[int, int] | None:
+    """Host normalisation of the ABI's Jacobian result (x = X/Z^2, y = Y/Z^3); None = identity."""
+    a = np.ascontiguousarray(xyz_limbs, dtype=np.uint64).reshape(3, 4)
+    X, Y, Z = (F.from_limbs(a[i], F.Q_MOD) for i in range(3))
+    if Z == 0:
+        return None
+    zi = pow(Z, -1, F.Q_MOD)
+    return X * zi * zi % F.Q_MOD, Y * zi * zi * zi % F.Q_MOD
+
+
+def g1_affine_limbs(points) -> np.ndarray:
+    """[(x, y) | None] -> (n, 8) Montgomery limbs; the identity is x = y = 0."""
+    out = np.zeros((len(points), 8), dtype=np.uint64)
+    for i, P in enumerate(points):
+        if P is not None:
+            out[i, :4] = F.to_limbs(P[0], F.Q_MOD)
+            out[i, 4:] = F.to_limbs(P[1], F.Q_MOD)
+    return out
+
+
+class G1Bases:
+    """Device-resident affine G1 bases: the `bases: &[Bn254G1]` argument of JoltGroup::msm
+    (crates/jolt-crypto/src/ec/group.rs:70) / HyperKZGProverSetup::g1_powers (scheme.rs:60-66),
+    normalised once instead of per call (mod.rs:205)."""
+
+    def __init__(self, session: Session, handle: int, n: int):
+        self.s, self.handle, self.n = session, handle, n
+
+    @classmethod
+    def from_affine(cls, session: Session, xy_limbs: np.ndarray) -> "G1Bases":
+        a = np.ascontiguousarray(xy_limbs, dtype=np.uint64).reshape(-1, 8)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_srs_upload_affine(session.h, _p(a) if a.shape[0] else None, a.shape[0], ctypes.byref(h)))
+        return cls(session, h.value, a.shape[0])
+
+    @classmethod
+    def from_jacobian(cls, session: Session, xyz_limbs: np.ndarray) -> "G1Bases":
+        a = np.ascontiguousarray(xyz_limbs, dtype=np.uint64).reshape(-1, 12)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_srs_upload_jacobian(session.h, _p(a) if a.shape[0] else None, a.shape[0], ctypes.byref(h)))
+        return cls(session, h.value, a.shape[0])
+
+    def __len__(self):
+        n = ctypes.c_size_t()
+        self.s.check(self.s.lib.jb_srs_len(self.s.h, self.handle, ctypes.byref(n)))
+        return n.value
+
+    def affine(self) -> np.ndarray:
+        out = np.empty((self.n, 8), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_srs_download_affine(self.s.h, self.handle, _p(out), self.n))
+        return out
+
+    def msm(self, scalars, offset: int = 0) -> np.ndarray:
+        """sum_i scalars[i] * bases[offset + i] as 12 Jacobian limbs. `scalars`: (n, 4) Montgomery
+        limbs on the host, or a device-resident Polynomial. Length mismatch raises (mod.rs:200-204)."""
+        out = np.zeros(12, dtype=np.uint64)
+        if isinstance(scalars, Polynomial):
+            n = len(scalars)
+            self.s.check(self.s.lib.jb_msm_g1_table(self.s.h, self.handle, offset, scalars.handle, n, _p(out)))
+        else:
+            a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+            self.s.check(self.s.lib.jb_msm_g1(self.s.h, self.handle, offset, _p(a) if a.shape[0] else None, a.shape[0], _p(out)))
+        return out
+
+    def free(self):
+        if self.handle:
+            self.s.check(self.s.lib.jb_srs_free(self.s.h, self.handle))
+            self.handle = 0
+
+
+def msm(session: Session, bases_xy_limbs: np.ndarray, scalars_limbs: np.ndarray) -> np.ndarray:
+    """JoltGroup::msm(bases, scalars): one-shot form (uploads the bases for this call)."""
+    b = np.ascontiguousarray(bases_xy_limbs, dtype=np.uint64).reshape(-1, 8)
+    s = np.ascontiguousarray(scalars_limbs, dtype=np.uint64).reshape(-1, 4)
+    if b.shape[0] != s.shape[0]:
+        raise JoltB200Error(_lib.JB_ERR_LENGTH, "msm: bases/scalars length mismatch")
+    g = G1Bases.from_affine(session, b)
+    try:
+        return g.msm(s)
+    finally:
+        g.free()

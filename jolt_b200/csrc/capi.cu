@@ -104,7 +104,9 @@ int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar&
     if (st != JB_OK) return st;
     out.partial = c->d_partial;
     int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
-    fused_round_kernel<M, ORDER, BIND, HI4, SKIP1><<<(unsigned)grid, 256, 0, c->stream>>>(tp, pairs, s, out);
+    // latency path: a round of <= 32 pairs runs as one warp (no barriers, no shared-memory stage)
+    const unsigned block = pairs <= 32 ? 32u : 256u;
+    fused_round_kernel<M, ORDER, BIND, HI4, SKIP1><<<(unsigned)grid, block, 0, c->stream>>>(tp, pairs, s, out);
     c->timing_end(tix);
     c->launches++;
     return c->check(cudaGetLastError(), "fused_round_kernel launch");
@@ -128,24 +130,9 @@ int dispatch_fused1(jb_ctx* c, int order, bool skip1, const TablePtrs& tp, size_
                  : dispatch_fused2<M, ORDER_LOW_TO_HIGH, false>(c, tp, pairs, bind, hi4, s, out);
 }
 
-constexpr size_t LEAN_MAX_PAIRS = 1 << 13;  // below this a round is latency-, not bandwidth-bound
-
-int launch_lean(jb_ctx* c, int m, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind,
-                const BindScalar& s, RoundOut out) {
-    size_t grid = (pairs + 255) / 256;
-    int K = skip1 ? m : m + 1;
-    int st = c->ensure_partial(grid * K);
-    if (st != JB_OK) return st;
-    out.partial = c->d_partial;
-    lean_round_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(tp, pairs, s, out, m, order, bind ? 1 : 0, skip1 ? 1 : 0);
-    c->launches++;
-    return c->check(cudaGetLastError(), "lean_round_kernel launch");
-}
-
 int dispatch_fused(jb_ctx* c, int m, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
                    const BindScalar& s, const RoundOut& out) {
     if (m < 1 || m > 4) return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
-    if (pairs <= LEAN_MAX_PAIRS && !c->no_lean) return launch_lean(c, m, order, skip1, tp, pairs, bind, s, out);
     switch (m) {
         case 1: return dispatch_fused1<1>(c, order, skip1, tp, pairs, bind, hi4, s, out);
         case 2: return dispatch_fused1<2>(c, order, skip1, tp, pairs, bind, hi4, s, out);
@@ -227,7 +214,6 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
-    c->no_lean = std::getenv("JB_NO_LEAN") != nullptr;  // diagnostics: force the streaming kernel for every round
     // keep freed blocks in the pool (ProofSession "device memory pools")
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

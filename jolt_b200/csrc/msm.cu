@@ -1,14 +1,460 @@
-// G1 MSM entry points - placeholder until the Pippenger kernels land (returns JB_ERR_UNSUPPORTED).
+// BN254 G1 multi-scalar multiplication (Pippenger bucket method) for sm_100a.
+// Replaces JoltGroup::msm (crates/jolt-crypto/src/ec/group.rs:70, impl ec/bn254/mod.rs:195-212 ->
+// ark_ec::VariableBaseMSM::msm_bigint) and therefore kzg_commit (crates/jolt-hyperkzg/src/kzg.rs:15-27).
+// The result is defined by value: sum_i [s_i] P_i with s_i the canonical integer of the scalar
+// (into_bigint, mod.rs:208); any schedule is admissible (specs/clean-slate-prover.md:565-571).
+//
+// Pipeline (all on the context's stream, integer pipes only - there is no dense contraction here):
+//   1. digits     : scalar -> canonical (one Montgomery product) -> signed base-2^c digits
+//                   d_w in [-2^(c-1), 2^(c-1)], + per-(window, bucket) histogram (global REDs)
+//   2. scan       : exclusive prefix of the histogram -> bucket offsets
+//   3. scatter    : point indices (with the digit's sign) into bucket order (one atomic each)
+//   4. accumulate : one thread per (window, bucket): XYZZ += +-P (mixed add, 8M + 2S); the hot kernel
+//   5. segments   : per (window, 16-bucket segment) running sums -> sum_b weight(b) * B_b
+//   6. windows    : per-window tree sum of the segment results, then 2^(c w) by doubling
+//   7. final      : sum of the window points -> Jacobian (X, Y, Z)
+// Affine bases live on the device for the lifetime of the SRS handle (HyperKZGProverSetup::g1_powers,
+// crates/jolt-hyperkzg/src/scheme.rs:60-66): the per-call `into_affine` of the reference
+// (mod.rs:205) becomes a one-time normalisation at upload.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <vector>
+
 #include "ctx.hpp"
+#include "ec.cuh"
+
+using namespace jb;
+
+namespace {
+
+constexpr int MSM_SEG = 16;  // buckets per reduction segment
+
+struct MsmPlan {
+    int c;        // window bits
+    int W;        // windows
+    int B;        // buckets per window = 2^(c-1)
+    int T;        // segments per window
+};
+
+MsmPlan plan_for(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    int c = lg - 4;  // ~ 2^5 points per bucket
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    MsmPlan p;
+    p.c = c;
+    p.W = (254 + c - 1) / c;
+    if (254 - (p.W - 1) * c > c - 1) p.W += 1;  // top window: data < 2^(c-1), so data + carry <= 2^(c-1) = B
+    p.B = 1 << (c - 1);
+    p.T = (p.B + MSM_SEG - 1) / MSM_SEG;
+    return p;
+}
+
+// ---- 1. digits ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars, const uint64_t* bases, size_t n, int c,
+                                                         int W, int B, uint32_t* digits, unsigned int* hist) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr k = fp_from_mont(ld_elem<Fr>(scalars, i));  // canonical integer limbs
+    // identity bases contribute nothing
+    bool skip = ld_elem<Fq>(bases, 2 * i).is_zero() && ld_elem<Fq>(bases, 2 * i + 1).is_zero();
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << c) - 1u;
+    for (int w = 0; w < W; ++w) {
+        int bit = w * c;
+        int word = bit >> 5, off = bit & 31;
+        uint32_t d = 0;
+        if (word < 8) {
+            d = k.v[word] >> off;
+            if (off + c > 32 && word + 1 < 8) d |= k.v[word + 1] << (32 - off);
+        }
+        d = (d & mask) + carry;
+        uint32_t enc = 0;
+        if (d > (uint32_t)B) {  // d in (2^(c-1), 2^c]: use d - 2^c < 0 and carry one up
+            uint32_t neg = (1u << c) - d;  // |d - 2^c| in [0, 2^(c-1))
+            carry = 1;
+            if (neg) enc = neg | 0x80000000u;
+        } else {
+            carry = 0;
+            if (d) enc = d;
+        }
+        if (skip) enc = 0;
+        digits[(size_t)w * n + i] = enc;
+        if (enc) atomicAdd(&hist[(size_t)w * B + ((enc & 0x7fffffffu) - 1)], 1u);
+    }
+}
+
+// ---- 2. exclusive scan (one block; the histogram is at most 17 * 2^15 counters) --------------------
+__global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned int* hist, unsigned int* offsets, size_t total) {
+    __shared__ unsigned int sums[1024];
+    const size_t per = (total + 1023) / 1024;
+    const size_t lo = (size_t)threadIdx.x * per;
+    const size_t hi = lo + per < total ? lo + per : total;
+    unsigned int s = 0;
+    for (size_t k = lo; k < hi; ++k) s += hist[k];
+    sums[threadIdx.x] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned int v = threadIdx.x >= d ? sums[threadIdx.x - d] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned int run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
+    for (size_t k = lo; k < hi; ++k) {
+        unsigned int cnt = hist[k];
+        offsets[k] = run;
+        run += cnt;
+        hist[k] = 0;  // reused as the scatter cursor
+    }
+    if (threadIdx.x == 1023) offsets[total] = sums[1023];
+}
+
+// ---- 3. scatter -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B,
+                                                          const unsigned int* offsets, unsigned int* cursor,
+                                                          uint32_t* sorted) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < W; ++w) {
+        uint32_t enc = digits[(size_t)w * n + i];
+        if (!enc) continue;
+        size_t slot = (size_t)w * B + ((enc & 0x7fffffffu) - 1);
+        unsigned int pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
+        sorted[pos] = (uint32_t)i | (enc & 0x80000000u);
+    }
+}
+
+// ---- 4. bucket accumulation: the hot kernel ---------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bases, const uint32_t* sorted,
+                                                             const unsigned int* offsets, size_t nbuckets,
+                                                             uint64_t* buckets) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nbuckets) return;
+    unsigned int lo = offsets[t], hi = offsets[t + 1];
+    XYZZ acc = XYZZ::inf();
+    for (unsigned int k = lo; k < hi; ++k) {
+        uint32_t e = sorted[k];
+        size_t idx = e & 0x7fffffffu;
+        Fq px = ld_elem<Fq>(bases, 2 * idx);
+        Fq py = ld_elem<Fq>(bases, 2 * idx + 1);
+        xyzz_add_affine(acc, px, py, (e >> 31) != 0);
+    }
+    st_xyzz(buckets, t, acc);
+}
+
+// ---- 5. segment sums: G = sum_{b in segment} (b + 1) * B_b ---------------------------------------------
+__global__ void __launch_bounds__(128) msm_segment_kernel(const uint64_t* buckets, int W, int B, int T,
+                                                          uint64_t* seg_out) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)W * T) return;
+    int w = (int)(t / T), seg = (int)(t % T);
+    int lo = seg * MSM_SEG;
+    int hi = lo + MSM_SEG < B ? lo + MSM_SEG : B;
+    XYZZ run = XYZZ::inf(), acc = XYZZ::inf();
+    for (int b = hi - 1; b >= lo; --b) {
+        XYZZ bk = ld_xyzz(buckets, (size_t)w * B + b);
+        xyzz_add(run, bk);
+        xyzz_add(acc, run);
+    }
+    // acc = sum (b - lo + 1) B_b ; add lo * run (double-and-add, lo < 2^15)
+    if (lo && !run.is_inf()) {
+        XYZZ m = XYZZ::inf();
+        for (int bit = 15; bit >= 0; --bit) {
+            xyzz_double(m);
+            if ((lo >> bit) & 1) xyzz_add(m, run);
+        }
+        xyzz_add(acc, m);
+    }
+    st_xyzz(seg_out, t, acc);
+}
+
+// block-wide tree sum of XYZZ points through shared memory (word-major: conflict-free)
+__device__ __forceinline__ void smem_put(uint32_t* sm, int tid, const XYZZ& p) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        sm[(0 * 8 + w) * 256 + tid] = p.x.v[w];
+        sm[(1 * 8 + w) * 256 + tid] = p.y.v[w];
+        sm[(2 * 8 + w) * 256 + tid] = p.zz.v[w];
+        sm[(3 * 8 + w) * 256 + tid] = p.zzz.v[w];
+    }
+}
+__device__ __forceinline__ XYZZ smem_get(const uint32_t* sm, int tid) {
+    XYZZ p;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        p.x.v[w] = sm[(0 * 8 + w) * 256 + tid];
+        p.y.v[w] = sm[(1 * 8 + w) * 256 + tid];
+        p.zz.v[w] = sm[(2 * 8 + w) * 256 + tid];
+        p.zzz.v[w] = sm[(3 * 8 + w) * 256 + tid];
+    }
+    return p;
+}
+
+// ---- 6. per-window sum of the T segment points, then 2^(c w) -----------------------------------------
+__global__ void __launch_bounds__(256) msm_window_kernel(const uint64_t* seg, int T, int c, uint64_t* win_out) {
+    __shared__ uint32_t sm[32 * 256];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    XYZZ acc = XYZZ::inf();
+    for (int k = tid; k < T; k += 256) xyzz_add(acc, ld_xyzz(seg, (size_t)w * T + k));
+    smem_put(sm, tid, acc);
+    __syncthreads();
+    for (int half = 128; half > 0; half >>= 1) {
+        if (tid < half) {
+            XYZZ o = smem_get(sm, tid + half);
+            xyzz_add(acc, o);
+            smem_put(sm, tid, acc);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int k = 0; k < c * w; ++k) xyzz_double(acc);
+        st_xyzz(win_out, w, acc);
+    }
+}
+
+// ---- 7. final: sum of the W window points -> Jacobian (X Z'^2-scaled): Z = ZZ*ZZZ ------------------------
+__global__ void __launch_bounds__(32) msm_final_kernel(const uint64_t* win, int W, uint64_t* out_xyz) {
+    __shared__ uint32_t sm[32 * 256];
+    const int tid = threadIdx.x;
+    XYZZ acc = tid < W ? ld_xyzz(win, tid) : XYZZ::inf();
+    smem_put(sm, tid, acc);
+    __syncwarp();
+    for (int half = 16; half > 0; half >>= 1) {
+        if (tid < half) {
+            XYZZ o = smem_get(sm, tid + half);
+            xyzz_add(acc, o);
+            smem_put(sm, tid, acc);
+        }
+        __syncwarp();
+    }
+    if (tid == 0) {
+        // x = X/ZZ, y = Y/ZZZ. With Z = ZZ*ZZZ: X_j = x Z^2 = X ZZ ZZZ^2, Y_j = y Z^3 = Y ZZ^3 ZZZ^2.
+        Fq X, Y, Z;
+        if (acc.is_inf()) {
+            X = Fq::one();
+            Y = Fq::one();
+            Z = Fq::zero();
+        } else {
+            Fq zzz2 = fp_sqr(acc.zzz);
+            Fq zz2 = fp_sqr(acc.zz);
+            X = fp_mul(fp_mul(acc.x, acc.zz), zzz2);
+            Y = fp_mul(fp_mul(acc.y, fp_mul(zz2, acc.zz)), zzz2);
+            Z = fp_mul(acc.zz, acc.zzz);
+        }
+        st_elem(out_xyz, 0, X);
+        st_elem(out_xyz, 1, Y);
+        st_elem(out_xyz, 2, Z);
+    }
+}
+
+// ---- SRS helpers ------------------------------------------------------------------------------------------
+// Jacobian (X, Y, Z) -> affine (x, y) = (X/Z^2, Y/Z^3); Z == 0 -> identity (0, 0). One inversion per thread.
+__global__ void __launch_bounds__(128) jacobian_to_affine_kernel(const uint64_t* xyz, size_t n, uint64_t* xy) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq X = ld_elem<Fq>(xyz, 3 * i), Y = ld_elem<Fq>(xyz, 3 * i + 1), Z = ld_elem<Fq>(xyz, 3 * i + 2);
+    Fq x = Fq::zero(), y = Fq::zero();
+    if (!Z.is_zero()) {
+        Fq zi = fq_inverse(Z);
+        Fq zi2 = fp_sqr(zi);
+        x = fp_mul(X, zi2);
+        y = fp_mul(Y, fp_mul(zi2, zi));
+    }
+    st_elem(xy, 2 * i, x);
+    st_elem(xy, 2 * i + 1, y);
+}
+
+bool canonical_q(const uint64_t* a) {
+    static const uint64_t Q[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL,
+                                  0x30644e72e131a029ULL};
+    for (int i = 3; i >= 0; --i)
+        if (a[i] != Q[i]) return a[i] < Q[i];
+    return false;
+}
+
+struct Guard {
+    std::lock_guard<std::mutex> lk;
+    explicit Guard(jb_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+};
+
+int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
+    const MsmPlan p = plan_for(n);
+    const size_t nb = (size_t)p.W * p.B;
+    uint32_t *digits = nullptr, *sorted = nullptr;
+    unsigned int *hist = nullptr, *offsets = nullptr;
+    uint64_t *buckets = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
+    int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&hist, nb * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&offsets, (nb + 1) * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&buckets, nb * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)p.W * p.T * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)p.W * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
+    if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
+    if (st == JB_OK) {
+        unsigned g = (unsigned)((n + 255) / 256);
+        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, digits, hist);
+        msm_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets, nb);
+        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, offsets, hist, sorted);
+        int tix = c->timing_begin(4, n, p.c);
+        msm_accumulate_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(d_bases, sorted, offsets, nb, buckets);
+        c->timing_end(tix);
+        msm_segment_kernel<<<(unsigned)(((size_t)p.W * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, p.W, p.B, p.T, seg);
+        msm_window_kernel<<<p.W, 256, 0, c->stream>>>(seg, p.T, p.c, win);
+        msm_final_kernel<<<1, 32, 0, c->stream>>>(win, p.W, d_out);
+        c->launches += 7;
+        st = c->check(cudaGetLastError(), "msm kernels");
+    }
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm sync");
+    if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
+    c->dev_free(digits);
+    c->dev_free(sorted);
+    c->dev_free(hist);
+    c->dev_free(offsets);
+    c->dev_free(buckets);
+    c->dev_free(seg);
+    c->dev_free(win);
+    c->dev_free(d_out);
+    return st;
+}
+
+void identity_xyz(uint64_t out[12]) {
+    // Montgomery one for X and Y, Z = 0 (G1Projective::zero() is (1, 1, 0))
+    static const uint64_t ONE_Q[4] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL,
+                                      0x0e0a77c19a07df2fULL};
+    std::memcpy(out, ONE_Q, 32);
+    std::memcpy(out + 4, ONE_Q, 32);
+    std::memset(out + 8, 0, 32);
+}
+
+}  // namespace
 
 void jb_ctx::msm_release() {}
 
 extern "C" {
-int jb_srs_upload_affine(jb_ctx* c, const uint64_t*, size_t, jb_srs*) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_srs_upload_jacobian(jb_ctx* c, const uint64_t*, size_t, jb_srs*) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_srs_len(jb_ctx* c, jb_srs, size_t*) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_srs_download_affine(jb_ctx* c, jb_srs, uint64_t*, size_t) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_srs_free(jb_ctx* c, jb_srs) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_msm_g1(jb_ctx* c, jb_srs, size_t, const uint64_t*, size_t, uint64_t*) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
-int jb_msm_g1_table(jb_ctx* c, jb_srs, size_t, jb_table, size_t, uint64_t*) { return c ? c->fail(JB_ERR_UNSUPPORTED, "msm not built") : JB_ERR_INVALID; }
+
+int jb_srs_upload_affine(jb_ctx* c, const uint64_t* xy, size_t n, jb_srs* out) {
+    if (!c || !out || (n && !xy)) return JB_ERR_INVALID;
+    Guard g(c);
+    for (size_t i = 0; i < n * 2; ++i)
+        if (!canonical_q(xy + 4 * i)) return c->fail(JB_ERR_INVALID, "srs: coordinate limbs not canonical (>= q)");
+    Srs s;
+    s.n = n;
+    int st = c->dev_alloc((void**)&s.xy, (n ? n : 1) * 64);
+    if (st != JB_OK) return st;
+    if (n) {
+        st = c->check(cudaMemcpyAsync(s.xy, xy, n * 64, cudaMemcpyHostToDevice, c->stream), "srs H2D");
+        if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "srs H2D sync");
+        if (st != JB_OK) {
+            c->dev_free(s.xy);
+            return st;
+        }
+    }
+    *out = c->next_id++;
+    c->srs[*out] = s;
+    return JB_OK;
 }
+
+int jb_srs_upload_jacobian(jb_ctx* c, const uint64_t* xyz, size_t n, jb_srs* out) {
+    if (!c || !out || (n && !xyz)) return JB_ERR_INVALID;
+    Guard g(c);
+    for (size_t i = 0; i < n * 3; ++i)
+        if (!canonical_q(xyz + 4 * i)) return c->fail(JB_ERR_INVALID, "srs: coordinate limbs not canonical (>= q)");
+    Srs s;
+    s.n = n;
+    uint64_t* d_xyz = nullptr;
+    int st = c->dev_alloc((void**)&s.xy, (n ? n : 1) * 64);
+    if (st != JB_OK) return st;
+    if (n) {
+        st = c->dev_alloc((void**)&d_xyz, n * 96);
+        if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_xyz, xyz, n * 96, cudaMemcpyHostToDevice, c->stream), "srs H2D");
+        if (st == JB_OK) {
+            jacobian_to_affine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(d_xyz, n, s.xy);
+            c->launches++;
+            st = c->check(cudaGetLastError(), "jacobian_to_affine launch");
+        }
+        if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "srs sync");
+        if (d_xyz) c->dev_free(d_xyz);
+        if (st != JB_OK) {
+            c->dev_free(s.xy);
+            return st;
+        }
+    }
+    *out = c->next_id++;
+    c->srs[*out] = s;
+    return JB_OK;
+}
+
+int jb_srs_len(jb_ctx* c, jb_srs h, size_t* n) {
+    if (!c || !n) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    *n = it->second.n;
+    return JB_OK;
+}
+
+int jb_srs_download_affine(jb_ctx* c, jb_srs h, uint64_t* out_xy, size_t n) {
+    if (!c || !out_xy) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    if (n > it->second.n) return c->fail(JB_ERR_INVALID, "srs download: n exceeds length");
+    int st = c->check(cudaMemcpyAsync(out_xy, it->second.xy, n * 64, cudaMemcpyDeviceToHost, c->stream), "srs D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "srs D2H sync");
+    return st;
+}
+
+int jb_srs_free(jb_ctx* c, jb_srs h) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    c->dev_free(it->second.xy);
+    c->srs.erase(it);
+    return JB_OK;
+}
+
+int jb_msm_g1(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    if (!c || !out_xyz || (n && !scalars)) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    if (offset + n > it->second.n) return c->fail(JB_ERR_LENGTH, "msm: bases/scalars length mismatch");
+    if (n == 0) {
+        identity_xyz(out_xyz);
+        return JB_OK;
+    }
+    if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+    uint64_t* d_s = nullptr;
+    int st = c->dev_alloc((void**)&d_s, n * 32);
+    if (st != JB_OK) return st;
+    st = c->check(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, c->stream), "msm scalars H2D");
+    if (st == JB_OK) st = msm_device(c, it->second.xy + 8 * offset, d_s, n, out_xyz);
+    c->dev_free(d_s);
+    return st;
+}
+
+int jb_msm_g1_table(jb_ctx* c, jb_srs h, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]) {
+    if (!c || !out_xyz) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    Table* t = c->find(scalars);
+    if (!t) return c->fail(JB_ERR_INVALID, "unknown table handle");
+    if (n > t->len || offset + n > it->second.n) return c->fail(JB_ERR_LENGTH, "msm: bases/scalars length mismatch");
+    if (n == 0) {
+        identity_xyz(out_xyz);
+        return JB_OK;
+    }
+    if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+    return msm_device(c, it->second.xy + 8 * offset, t->buf, n, out_xyz);
+}
+
+}  // extern "C"

@@ -69,6 +69,11 @@ __device__ __forceinline__ Fr warp_sum(Fr x) {
 template <int K>
 __device__ __forceinline__ void block_sum(Fr (&acc)[K], uint32_t* smem) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    if (nwarps == 1) {  // latency path: a one-warp block needs no shared-memory stage
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         acc[k] = warp_sum(acc[k]);
@@ -115,10 +120,34 @@ __device__ __forceinline__ F ld_elem_cg(const uint64_t* base, size_t idx) {
     return r;
 }
 
+// Thread 0 of the finishing block: write the K totals, then (host-mapped mode) raise the flag.
+template <int K>
+__device__ __forceinline__ void publish_round(const Fr (&tot)[K], const RoundOut& out) {
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+        if (out.lanes) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) out.result[t * 8 + w] = tot[t].v[w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                out.result[t * 4 + w] = (uint64_t)tot[t].v[2 * w] | ((uint64_t)tot[t].v[2 * w + 1] << 32);
+        }
+    }
+    if (out.flag) {
+        __threadfence_system();
+        *out.flag = out.seq;
+    }
+}
+
 // Called by every thread of every block after thread 0 holds the block's K sums in acc[].
 template <int K>
 __device__ __forceinline__ void round_epilogue(Fr (&acc)[K], uint32_t* smem, const RoundOut& out) {
     __shared__ bool is_last;
+    if (gridDim.x == 1) {  // latency path: nothing to fold, publish the block's sums directly
+        if (threadIdx.x == 0) publish_round<K>(acc, out);
+        return;
+    }
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int t = 0; t < K; ++t) st_elem(out.partial, (size_t)blockIdx.x * K + t, acc[t]);
@@ -138,22 +167,8 @@ __device__ __forceinline__ void round_epilogue(Fr (&acc)[K], uint32_t* smem, con
     }
     block_sum<K>(tot, smem);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int t = 0; t < K; ++t) {
-            if (out.lanes) {
-#pragma unroll
-                for (int w = 0; w < 8; ++w) out.result[t * 8 + w] = tot[t].v[w];
-            } else {
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    out.result[t * 4 + w] = (uint64_t)tot[t].v[2 * w] | ((uint64_t)tot[t].v[2 * w + 1] << 32);
-            }
-        }
         *out.counter = 0;
-        if (out.flag) {
-            __threadfence_system();
-            *out.flag = out.seq;
-        }
+        publish_round<K>(tot, out);
     }
 }
 
@@ -265,142 +280,6 @@ __global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t p
     block_sum<K>(acc, smem);
     __syncthreads();  // smem is reused by the last block's fold
     round_epilogue<K>(acc, smem, out);
-}
-
-// ---- latency path: the same fused round for SMALL tables ---------------------------------------
-// Once a round has only a few thousand pairs its cost is the host round trip, not bandwidth, and
-// a cold launch of the fully unrolled kernel above is dominated by instruction fetch (~40 KB of
-// straight-line code executed once). This variant keeps the arithmetic out of line and the loops
-// rolled (a few KB of code); one pair per thread, same RoundOut protocol, same values.
-__device__ __noinline__ Fr fr_mul_ni(const Fr& a, const Fr& b) { return fp_mul(a, b); }
-__device__ __noinline__ Fr fr_add_ni(const Fr& a, const Fr& b) { return fp_add(a, b); }
-__device__ __noinline__ Fr fr_sub_ni(const Fr& a, const Fr& b) { return fp_sub(a, b); }
-
-__device__ __forceinline__ Fr warp_sum_ni(Fr x) {
-#pragma unroll 1
-    for (int off = 16; off > 0; off >>= 1) {
-        Fr y;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) y.v[k] = __shfl_down_sync(0xffffffffu, x.v[k], off);
-        x = fr_add_ni(x, y);
-    }
-    return x;
-}
-
-// blockDim.x == 256. acc[0..K) per thread -> thread 0 of the block holds the block totals.
-__device__ __forceinline__ void block_sum_ni(Fr* acc, int K, uint32_t* smem) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        Fr x = warp_sum_ni(acc[k]);
-        if (lane == 0) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) smem[(warp * K + k) * 8 + w] = x.v[w];
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            Fr x = Fr::zero();
-            if (lane < 8) {
-#pragma unroll
-                for (int w = 0; w < 8; ++w) x.v[w] = smem[(lane * K + k) * 8 + w];
-            }
-            acc[k] = warp_sum_ni(x);
-        }
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) lean_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out,
-                                                         int M, int order, int bind, int skip1) {
-    __shared__ uint32_t smem[8 * 5 * 8];
-    __shared__ bool is_last;
-    const int K = skip1 ? M : M + 1;
-    Fr acc[5];
-#pragma unroll
-    for (int e = 0; e < 5; ++e) acc[e] = Fr::zero();
-    Fr sv;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sv.v[i] = s.w[i];
-    const size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (y < pairs) {
-        Fr cur[4], dlt[4];
-#pragma unroll 1
-        for (int j = 0; j < M; ++j) {
-            Fr lo, hi;
-            if (bind) {
-                size_t ia, ib, ic, id, oa, ob;  // (a, b) -> lo, (c, d) -> hi
-                if (order == ORDER_HIGH_TO_LOW) { ia = y; ib = y + 2 * pairs; ic = y + pairs; id = y + 3 * pairs; oa = y; ob = y + pairs; }
-                else { ia = 4 * y; ib = 4 * y + 1; ic = 4 * y + 2; id = 4 * y + 3; oa = 2 * y; ob = 2 * y + 1; }
-                Fr a = ld_elem_rw<Fr>(tp.in[j], ia), b = ld_elem_rw<Fr>(tp.in[j], ib);
-                Fr c = ld_elem_rw<Fr>(tp.in[j], ic), d = ld_elem_rw<Fr>(tp.in[j], id);
-                lo = fr_add_ni(a, fr_mul_ni(fr_sub_ni(b, a), sv));
-                hi = fr_add_ni(c, fr_mul_ni(fr_sub_ni(d, c), sv));
-                st_elem(tp.out[j], oa, lo);
-                st_elem(tp.out[j], ob, hi);
-            } else {
-                size_t il = order == ORDER_HIGH_TO_LOW ? y : 2 * y;
-                size_t ih = order == ORDER_HIGH_TO_LOW ? y + pairs : 2 * y + 1;
-                lo = ld_elem_rw<Fr>(tp.in[j], il);
-                hi = ld_elem_rw<Fr>(tp.in[j], ih);
-            }
-            cur[j] = lo;
-            dlt[j] = fr_sub_ni(hi, lo);
-        }
-        int e = 0;
-#pragma unroll 1
-        for (int t = 0; t <= M; ++t) {
-            if (!(skip1 && t == 1)) {
-                Fr prod = cur[0];
-#pragma unroll 1
-                for (int j = 1; j < M; ++j) prod = fr_mul_ni(prod, cur[j]);
-                acc[e] = prod;
-                ++e;
-            }
-#pragma unroll 1
-            for (int j = 0; j < M; ++j) cur[j] = fr_add_ni(cur[j], dlt[j]);
-        }
-    }
-    block_sum_ni(acc, K, smem);
-    if (gridDim.x > 1) {
-        if (threadIdx.x == 0) {
-#pragma unroll 1
-            for (int t = 0; t < K; ++t) st_elem(out.partial, (size_t)blockIdx.x * K + t, acc[t]);
-            __threadfence();
-            is_last = (atomicAdd(out.counter, 1u) == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-#pragma unroll 1
-        for (int t = 0; t < K; ++t) {
-            Fr x = Fr::zero();
-            for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-                x = fr_add_ni(x, ld_elem_cg<Fr>(out.partial, (size_t)b * K + t));
-            acc[t] = x;
-        }
-        block_sum_ni(acc, K, smem);
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll 1
-        for (int t = 0; t < K; ++t) {
-            if (out.lanes) {
-#pragma unroll
-                for (int w = 0; w < 8; ++w) out.result[t * 8 + w] = acc[t].v[w];
-            } else {
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    out.result[t * 4 + w] = (uint64_t)acc[t].v[2 * w] | ((uint64_t)acc[t].v[2 * w + 1] << 32);
-            }
-        }
-        if (gridDim.x > 1) *out.counter = 0;
-        if (out.flag) {
-            __threadfence_system();
-            *out.flag = out.seq;
-        }
-    }
 }
 
 // ---- eq-table expansion --------------------------------------------------------------------

@@ -1,0 +1,128 @@
+"""G1 MSM on the device vs the oracle (mirrors crates/jolt-crypto/tests/group_laws.rs:12-146 and
+SURVEY.md Appendix B): msm == naive sum (n <= 2^10), == oracle Pippenger (larger n), edge cases.
+G1/MSM parity is unpinned by golden vectors (the reference holds none): results are compared as
+affine (x, y) integers against the oracle."""
+import numpy as np
+import pytest
+
+import jolt_b200
+from jolt_b200 import G1Bases, Polynomial, g1_affine_limbs, g1_jacobian_to_affine
+from oracle import bn254 as O
+from oracle import coracle as C
+from gpu_util import rand_limbs
+
+pytestmark = pytest.mark.gpu
+
+G = np.array(O.to_mont_limbs(1, O.Q_MOD) + O.to_mont_limbs(2, O.Q_MOD), dtype=np.uint64)
+
+
+@pytest.fixture(scope="module")
+def sess():
+    s = jolt_b200.Session(0)
+    yield s
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def srs_bases():
+    """SRS-like bases beta^i * G (scheme.rs:54-73), 2^14 of them, from the C oracle."""
+    beta = C.ints_to_mont([O.random_fr(0x4D534D, 1)[0]])[0]
+    return C.g1_powers(1 << 14, G, beta)
+
+
+def oracle_affine(xy, inf):
+    return None if inf else (O.from_mont_limbs(xy[:4], O.Q_MOD), O.from_mont_limbs(xy[4:], O.Q_MOD))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 257, 1024])
+def test_msm_matches_naive(sess, srs_bases, n):
+    sc = rand_limbs(0x5CA1A2 + n, n)
+    got = g1_jacobian_to_affine(G1Bases.from_affine(sess, srs_bases[:n]).msm(sc))
+    assert got == oracle_affine(*C.g1_msm_naive(srs_bases[:n], sc))
+    assert O.g1_is_on_curve(got)
+
+
+@pytest.mark.parametrize("n", [1 << 12, 1 << 14])
+def test_msm_matches_oracle_pippenger(sess, srs_bases, n):
+    sc = rand_limbs(0x5CA1A2 + n, n)
+    bases = G1Bases.from_affine(sess, srs_bases[:n])
+    want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+    assert g1_jacobian_to_affine(bases.msm(sc)) == want
+    # scalars already on the device (a folded HyperKZG polynomial): same value
+    assert g1_jacobian_to_affine(bases.msm(Polynomial.new(sess, sc))) == want
+    # offset windows of the SRS (kzg_commit uses g1_powers[..len])
+    half = n // 2
+    want2 = oracle_affine(*C.g1_msm_pippenger(srs_bases[half:n], sc[:half], 0, C.max_threads()))
+    assert g1_jacobian_to_affine(bases.msm(sc[:half], offset=half)) == want2
+
+
+def test_msm_empty_single_and_mismatch(sess, srs_bases):
+    bases = G1Bases.from_affine(sess, srs_bases[:8])
+    assert g1_jacobian_to_affine(bases.msm(np.zeros((0, 4), dtype=np.uint64))) is None          # group_laws.rs:143
+    k = O.random_fr(3, 1)[0]
+    one = g1_jacobian_to_affine(bases.msm(C.ints_to_mont([k])))                                  # group_laws.rs:135
+    assert one == O.g1_scalar_mul(O.G1_GEN, k)
+    with pytest.raises(jolt_b200.JoltB200Error, match="length mismatch"):                        # mod.rs:200-204
+        bases.msm(rand_limbs(1, 9))
+    with pytest.raises(jolt_b200.JoltB200Error, match="length mismatch"):
+        jolt_b200.msm(sess, srs_bases[:4], rand_limbs(1, 5))
+
+
+def test_msm_edge_scalars_and_bases(sess):
+    # zero scalars, scalar 1 and r-1, repeated bases, P and -P with equal scalars, identity bases
+    pts = [O.g1_scalar_mul(O.G1_GEN, k) for k in (1, 2, 3, 5, 7, 11, 13, 17)]
+    pts[2] = pts[1]                      # repeated base -> the doubling branch inside a bucket
+    pts[4] = O.g1_neg(pts[3])            # P and -P
+    pts[6] = None                        # identity base
+    sc = [0, 1, 1, 12345, 12345, O.R_MOD - 1, 999, (1 << 253) + 7]
+    want = O.g1_msm_naive(pts, sc)
+    got = g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs(pts), C.ints_to_mont(sc)))
+    assert got == want
+    # all-zero scalars and all-cancelling terms give the identity
+    assert g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs(pts), C.ints_to_mont([0] * 8))) is None
+    assert g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs([pts[3], pts[4]]), C.ints_to_mont([77, 77]))) is None
+    # many copies of one base with one scalar: every term lands in the same buckets (P + P doubling chain)
+    n = 300
+    got = g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs([pts[0]] * n), C.ints_to_mont([5] * n)))
+    assert got == O.g1_scalar_mul(O.G1_GEN, 5 * n)
+
+
+def test_msm_small_scalars_u64(sess, srs_bases):
+    # the msm_u64 shape of the legacy facade (jolt-prover-legacy/src/msm/mod.rs:35-79): small integers
+    n = 1 << 10
+    vals = [(i * 2654435761) % (1 << 32) for i in range(n)]
+    sc = C.ints_to_mont(vals)
+    want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+    assert g1_jacobian_to_affine(G1Bases.from_affine(sess, srs_bases[:n]).msm(sc)) == want
+
+
+def test_jacobian_upload_normalises(sess):
+    pts = [O.g1_scalar_mul(O.G1_GEN, k) for k in (3, 9, 27)]
+    zs = O.random_fr(5, 3, O.Q_MOD)
+    jac = np.zeros((4, 12), dtype=np.uint64)
+    for i, ((x, y), z) in enumerate(zip(pts, zs)):
+        jac[i, :4] = O.to_mont_limbs(x * z * z % O.Q_MOD, O.Q_MOD)
+        jac[i, 4:8] = O.to_mont_limbs(y * z * z * z % O.Q_MOD, O.Q_MOD)
+        jac[i, 8:] = O.to_mont_limbs(z, O.Q_MOD)
+    jac[3, :4] = O.to_mont_limbs(1, O.Q_MOD)
+    jac[3, 4:8] = O.to_mont_limbs(1, O.Q_MOD)          # (1, 1, 0): the identity
+    bases = G1Bases.from_jacobian(sess, jac)
+    assert (bases.affine() == g1_affine_limbs(pts + [None])).all()
+    sc = [2, 3, 4, 5]
+    assert g1_jacobian_to_affine(bases.msm(C.ints_to_mont(sc))) == O.g1_msm_naive(pts + [None], sc)
+
+
+def test_msm_linearity_large(sess, srs_bases):
+    """Size-independent property at 2^14 (homomorphism, commit_open_verify.rs:131-188):
+    msm(a*s + b*t) == a*msm(s) + b*msm(t)."""
+    n = 1 << 14
+    s, t = rand_limbs(1, n), rand_limbs(2, n)
+    a, b = O.random_fr(3, 2)
+    A = np.tile(C.ints_to_mont([a]), (n, 1))
+    Bm = np.tile(C.ints_to_mont([b]), (n, 1))
+    comb = C.f_vec(0, 0, C.f_vec(0, 2, s, A), C.f_vec(0, 2, t, Bm))
+    bases = G1Bases.from_affine(sess, srs_bases)
+    lhs = g1_jacobian_to_affine(bases.msm(comb))
+    ps, pt = g1_jacobian_to_affine(bases.msm(s)), g1_jacobian_to_affine(bases.msm(t))
+    rhs = O.g1_add(O.g1_scalar_mul(ps, a), O.g1_scalar_mul(pt, b))
+    assert lhs == rhs
