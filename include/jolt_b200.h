@@ -152,6 +152,9 @@ int jb_absorb_round_splitmix125(void* user, size_t round, const uint64_t* coeffs
 int jb_srs_upload_affine(jb_ctx* ctx, const uint64_t* xy_limbs, size_t n, jb_srs* out);
 /* Jacobian bases as JoltGroup::msm receives them; normalised on device (batch inversion). */
 int jb_srs_upload_jacobian(jb_ctx* ctx, const uint64_t* xyz_limbs, size_t n, jb_srs* out);
+/* Synthetic bases generated on the device: bases[i] = (i + 1) * base (affine base point). Valid,
+ * distinct curve points with a closed form for checking: msm(s) == (sum_i s_i (i+1)) * base. */
+int jb_srs_generate_multiples(jb_ctx* ctx, const uint64_t base_xy[8], size_t n, jb_srs* out);
 int jb_srs_len(jb_ctx* ctx, jb_srs s, size_t* n);
 int jb_srs_download_affine(jb_ctx* ctx, jb_srs s, uint64_t* out_xy, size_t n);
 int jb_srs_free(jb_ctx* ctx, jb_srs s);

@@ -475,6 +475,14 @@ class G1Bases:
         session.check(session.lib.jb_srs_upload_jacobian(session.h, _p(a) if a.shape[0] else None, a.shape[0], ctypes.byref(h)))
         return cls(session, h.value, a.shape[0])
 
+    @classmethod
+    def generate_multiples(cls, session: Session, base_xy_limbs: np.ndarray, n: int) -> "G1Bases":
+        """bases[i] = (i + 1) * base, generated on the device (synthetic SRS for benches/tests)."""
+        b = np.ascontiguousarray(base_xy_limbs, dtype=np.uint64).reshape(8)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_srs_generate_multiples(session.h, _p(b), n, ctypes.byref(h)))
+        return cls(session, h.value, n)
+
     def __len__(self):
         n = ctypes.c_size_t()
         self.s.check(self.s.lib.jb_srs_len(self.s.h, self.handle, ctypes.byref(n)))

@@ -220,7 +220,8 @@ __global__ void __launch_bounds__(256) msm_window_kernel(const uint64_t* seg, in
 __global__ void __launch_bounds__(32) msm_final_kernel(const uint64_t* win, int W, uint64_t* out_xyz) {
     __shared__ uint32_t sm[32 * 256];
     const int tid = threadIdx.x;
-    XYZZ acc = tid < W ? ld_xyzz(win, tid) : XYZZ::inf();
+    XYZZ acc = XYZZ::inf();
+    for (int k = tid; k < W; k += 32) xyzz_add(acc, ld_xyzz(win, k));  // W can reach 64 for small windows
     smem_put(sm, tid, acc);
     __syncwarp();
     for (int half = 16; half > 0; half >>= 1) {
@@ -266,6 +267,34 @@ __global__ void __launch_bounds__(128) jacobian_to_affine_kernel(const uint64_t*
     }
     st_elem(xy, 2 * i, x);
     st_elem(xy, 2 * i + 1, y);
+}
+
+// bases[i] = (i + 1) * base, affine. Each thread seeds (start + 1) * base by double-and-add, then
+// walks GEN_RUN consecutive multiples; one Fermat inversion per emitted point (one-off SRS work).
+constexpr int GEN_RUN = 32;
+__global__ void __launch_bounds__(128) gen_multiples_kernel(const uint64_t* base_xy, size_t n, uint64_t* out_xy) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t start = t * GEN_RUN;
+    if (start >= n) return;
+    Fq bx = ld_elem_rw<Fq>(base_xy, 0), by = ld_elem_rw<Fq>(base_xy, 1);
+    XYZZ acc = XYZZ::inf();
+    uint64_t k = start + 1;
+    for (int bit = 40; bit >= 0; --bit) {
+        xyzz_double(acc);
+        if ((k >> bit) & 1) xyzz_add_affine(acc, bx, by, false);
+    }
+    for (int j = 0; j < GEN_RUN && start + j < n; ++j) {
+        Fq x = Fq::zero(), y = Fq::zero();
+        if (!acc.is_inf()) {
+            Fq i3 = fq_inverse(acc.zzz);
+            Fq tz = fp_mul(acc.zz, i3);  // ZZ/ZZZ = 1/Z
+            x = fp_mul(acc.x, fp_sqr(tz));
+            y = fp_mul(acc.y, i3);
+        }
+        st_elem(out_xy, 2 * (start + j), x);
+        st_elem(out_xy, 2 * (start + j) + 1, y);
+        xyzz_add_affine(acc, bx, by, false);
+    }
 }
 
 bool canonical_q(const uint64_t* a) {
@@ -385,6 +414,33 @@ int jb_srs_upload_jacobian(jb_ctx* c, const uint64_t* xyz, size_t n, jb_srs* out
             c->dev_free(s.xy);
             return st;
         }
+    }
+    *out = c->next_id++;
+    c->srs[*out] = s;
+    return JB_OK;
+}
+
+int jb_srs_generate_multiples(jb_ctx* c, const uint64_t base_xy[8], size_t n, jb_srs* out) {
+    if (!c || !out || !base_xy || n == 0) return JB_ERR_INVALID;
+    Guard g(c);
+    if (!canonical_q(base_xy) || !canonical_q(base_xy + 4)) return c->fail(JB_ERR_INVALID, "srs: base limbs not canonical");
+    Srs s;
+    s.n = n;
+    uint64_t* d_base = nullptr;
+    int st = c->dev_alloc((void**)&s.xy, n * 64);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_base, 64);
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_base, base_xy, 64, cudaMemcpyHostToDevice, c->stream), "srs base H2D");
+    if (st == JB_OK) {
+        size_t threads = (n + GEN_RUN - 1) / GEN_RUN;
+        gen_multiples_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, c->stream>>>(d_base, n, s.xy);
+        c->launches++;
+        st = c->check(cudaGetLastError(), "gen_multiples launch");
+    }
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "srs generate sync");
+    if (d_base) c->dev_free(d_base);
+    if (st != JB_OK) {
+        if (s.xy) c->dev_free(s.xy);
+        return st;
     }
     *out = c->next_id++;
     c->srs[*out] = s;

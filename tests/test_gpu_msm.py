@@ -126,3 +126,34 @@ def test_msm_linearity_large(sess, srs_bases):
     ps, pt = g1_jacobian_to_affine(bases.msm(s)), g1_jacobian_to_affine(bases.msm(t))
     rhs = O.g1_add(O.g1_scalar_mul(ps, a), O.g1_scalar_mul(pt, b))
     assert lhs == rhs
+
+
+def _weighted_sum(sc_limbs: np.ndarray) -> int:
+    """sum_i s_i * (i + 1) mod r from Montgomery limbs, vectorised over 32-bit words."""
+    a = np.ascontiguousarray(sc_limbs, dtype=np.uint64).reshape(-1, 4)
+    n = a.shape[0]
+    wts = np.arange(1, n + 1, dtype=object)
+    total = 0
+    for limb in range(4):
+        for half in range(2):
+            words = ((a[:, limb] >> np.uint64(32 * half)) & np.uint64(0xFFFFFFFF)).astype(object)
+            total += int((words * wts).sum()) << (64 * limb + 32 * half)
+    return total * pow(1 << 256, -1, O.R_MOD) % O.R_MOD
+
+
+def test_generated_multiples_are_multiples(sess):
+    bases = G1Bases.generate_multiples(sess, G, 100)
+    xy = bases.affine()
+    for i in (0, 1, 31, 32, 33, 63, 64, 99):
+        assert oracle_affine(xy[i], False) == O.g1_scalar_mul(O.G1_GEN, i + 1)
+
+
+@pytest.mark.parametrize("log_n", [16, 20])
+def test_msm_closed_form_at_scale(sess, log_n):
+    """BASELINE config 3 size (2^20): bases (i+1)*G make the MSM a single scalar multiplication,
+    msm(s) == (sum_i s_i (i+1)) * G - an exact, size-independent check."""
+    n = 1 << log_n
+    bases = G1Bases.generate_multiples(sess, G, n)
+    sc = rand_limbs(0x5CA1A2, n)
+    got = g1_jacobian_to_affine(bases.msm(sc))
+    assert got == O.g1_scalar_mul(O.G1_GEN, _weighted_sum(sc))
