@@ -214,34 +214,33 @@ def run_ours(args):
         return t
 
     if world > 1:
-        from jolt_b200.dist import ShardedProductSumcheck
+        from jolt_b200.dist import init_comm, prove_sharded, sharded_claim
+        if args.order != "l2h":
+            raise SystemExit("bench.py: index sharding uses LowToHigh binding (contiguous blocks keep pairs local)")
+        init_comm(sess, dist)
 
     def one_step(bufs, seed):
         polys = [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in bufs]
-        mem = ProductMember(sess, polys, order)
         if world == 1:
+            mem = ProductMember(sess, polys, order)
             res = jolt_b200.prove_batch_native([BatchMember(claim, 1, args.log_n, 0)], [mem], args.log_n, m, claim,
                                                seed=seed)
             fe = mem.final_evals()
+            mem.close()
         else:
-            res, fe = ShardedProductSumcheck(sess, mem, m, args.log_n, dist, seed).prove(claim)
-        mem.close()
+            res, fe = prove_sharded(sess, polys, claim, seed)
         return res, fe
 
     # ---- value arm: inputs resident in HBM, one fresh copy per step ------------------------------
     base = [synth(0xB200 + 16 * rank + j) for j in range(m)]
     # the input claim (known from the previous protocol stage in a real proof): sum_x prod_j f_j(x)
-    probe = ProductMember(sess, [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in base], order)
     if world == 1:
+        probe = ProductMember(sess, [Polynomial.wrap_device(sess, b.clone().data_ptr(), n) for b in base], order)
         ev = probe.prove_round_evals(None, 0)
+        claim = (ev[0] + ev[1]) % F.R_MOD
+        probe.close()
     else:
-        from jolt_b200.dist import lanes_to_ints
-        lanes = torch.zeros((m + 1) * 8, dtype=torch.int64, device="cuda")
-        sess.check(sess.lib.jb_member_prove_round_partials(probe.h, None, 0, 0, lanes.data_ptr()))
-        dist.all_reduce(lanes)
-        ev = lanes_to_ints(lanes.cpu().numpy().view(np.uint64))
-    claim = (ev[0] + ev[1]) % F.R_MOD
-    probe.close()
+        claim = sharded_claim(sess, [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in base], dist)
     copies = [[b.clone() for b in base] for _ in range(K + W)]
     torch.cuda.synchronize()
     for w in range(W):
@@ -280,13 +279,13 @@ def run_ours(args):
 
     def e2e_step():
         polys = [Polynomial.new(sess, h) for h in host_np]
-        mem = ProductMember(sess, polys, order)
         if world == 1:
+            mem = ProductMember(sess, polys, order)
             res = jolt_b200.prove_batch_native([BatchMember(claim, 1, args.log_n, 0)], [mem], args.log_n, m, claim, seed=7)
             fe = mem.final_evals()
+            mem.close()
         else:
-            res, fe = ShardedProductSumcheck(sess, mem, m, args.log_n, dist, 7).prove(claim)
-        mem.close()
+            res, fe = prove_sharded(sess, polys, claim, 7)
         return res, fe
 
     e2e_res, e2e_fe = e2e_step()

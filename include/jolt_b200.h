@@ -123,6 +123,20 @@ int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out_elem
 int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t cap_elems, size_t* len_out);
 void jb_member_destroy(jb_member* mem);
 
+/* ---- multi-GPU: one process per GPU; the caller owns rendezvous (torch.distributed
+ * broadcasts the 128-byte NCCL unique id), the context issues the per-round collectives itself on its
+ * stream. libnccl is resolved at run time (pass NULL to use the copy already loaded in the process). */
+int jb_comm_unique_id(uint8_t out[128], const char* libnccl_path_or_null);
+int jb_comm_init(jb_ctx* ctx, int nranks, int rank, const uint8_t id[128], const char* libnccl_path_or_null);
+int jb_comm_destroy(jb_ctx* ctx);
+/* An index-sharded ProveRounds member: this rank's m tables are the contiguous block `rank` of the
+ * global tables (LowToHigh binding keeps every pair local). It reports log2(local len) + log2(nranks)
+ * rounds and is driven by the same jb_member_prove_round / jb_prove_batch as a local member: each early
+ * round costs ONE all-reduce of <= 40 u64; when a shard is 2^gather_log long the shards are
+ * all-gathered once and every rank finishes the remaining rounds redundantly (identical results on all
+ * ranks, identical to the single-GPU member over the global tables). `previous_claim` is the GLOBAL claim. */
+int jb_sharded_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, size_t gather_log, jb_member** out);
+
 /* ---- batched engine: jolt_sumcheck::prove_batch (crates/jolt-sumcheck/src/prover.rs:193-362) over
  *      device members, SequentialRounds traversal. BatchMember = batch.rs:24-71. The transcript stays
  *      with the caller: `absorb` receives each round's batched polynomial (trimmed coefficients, 4

@@ -242,6 +242,7 @@ int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
 
 void jb_ctx_destroy(jb_ctx* c) {
     if (!c) return;
+    jb_comm_destroy(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& kv : c->tables) c->release(kv.second);
@@ -255,6 +256,7 @@ void jb_ctx_destroy(jb_ctx* c) {
     if (c->d_small) cudaFree(c->d_small);
     if (c->h_small) cudaFreeHost(c->h_small);
     if (c->h_result) cudaFreeHost(c->h_result);
+    if (c->d_lanes) cudaFree(c->d_lanes);
     if (c->d_counter) cudaFree(c->d_counter);
     if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -450,8 +452,15 @@ struct jb_member {
     std::vector<Table> tables;
     int m;
     int order;
-    size_t rounds;  // total
-    size_t len;     // current table length
+    size_t rounds;  // total (for a sharded member: local rounds + log2(world))
+    size_t len;     // current (local) table length
+    size_t rounds_done = 0;  // prove_round calls completed
+    // index-sharded member: this rank holds the contiguous block `rank` of the global
+    // tables; rounds run with one all-reduce each until the shard is `gather_len` long, then the
+    // shards are all-gathered into `tail`, which finishes the remaining rounds locally.
+    bool sharded = false;
+    size_t gather_len = 0;
+    jb_member* tail = nullptr;
 };
 
 int jb_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, jb_member** out) {
@@ -571,35 +580,21 @@ static int wait_round_result(jb_ctx* c) {
     return JB_OK;
 }
 
-int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
+static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
+                               uint64_t* out_evals);
+
+// Assembles s(0..M) from the K published values (skip1: s(1) = claim - s(0)); checks the claim in verify mode.
+static int assemble_evals(jb_ctx* c, int M, bool skip1, const uint64_t* vals, const uint64_t* claim, size_t round,
                           uint64_t* out_evals) {
-    if (!mem || !out_evals) return JB_ERR_INVALID;
-    jb_ctx* c = mem->ctx;
-    Guard g(c);
-    size_t bound = mem->rounds;
-    {
-        size_t l = mem->len;
-        while (l > 1) { l >>= 1; --bound; }  // bound = rounds already bound
-    }
-    if (round != bound + (bind ? 1 : 0)) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
-    // With a claim and round verification off (the default, = the reference's optimized tier) the
-    // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
-    // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
-    const bool skip1 = claim != nullptr && !c->verify_rounds;
-    int st = member_round(mem, bind, skip1, nullptr);
-    if (st != JB_OK) return st;
-    const int M = mem->m;
-    st = wait_round_result(c);
-    if (st != JB_OK) return st;
     if (skip1) {
-        HostFr s0 = HostFr::from_limbs(c->h_result);
+        HostFr s0 = HostFr::from_limbs(vals);
         HostFr s1 = HostFr::from_limbs(claim) - s0;
         s0.store(out_evals);
         s1.store(out_evals + 4);
-        if (M > 1) std::memcpy(out_evals + 8, c->h_result + 4, (size_t)(M - 1) * 32);
+        if (M > 1) std::memcpy(out_evals + 8, vals + 4, (size_t)(M - 1) * 32);
         return JB_OK;
     }
-    std::memcpy(out_evals, c->h_result, (size_t)(M + 1) * 32);
+    std::memcpy(out_evals, vals, (size_t)(M + 1) * 32);
     if (claim) {
         HostFr s0 = HostFr::from_limbs(out_evals), s1 = HostFr::from_limbs(out_evals + 4);
         if ((s0 + s1) != HostFr::from_limbs(claim)) {
@@ -608,6 +603,111 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
             return c->fail(JB_ERR_ROUND_CHECK, buf);
         }
     }
+    return JB_OK;
+}
+
+int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
+                          uint64_t* out_evals) {
+    if (!mem || !out_evals) return JB_ERR_INVALID;
+    jb_ctx* c = mem->ctx;
+    if (mem->sharded) {
+        int st = sharded_prove_round(mem, bind, round, claim, out_evals);
+        if (st == JB_OK) mem->rounds_done++;
+        return st;
+    }
+    Guard g(c);
+    if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
+    if ((mem->rounds_done == 0) != (bind == nullptr))
+        return c->fail(JB_ERR_INVALID, "prove_round: bind must be absent exactly on the first round");
+    // With a claim and round verification off (the default, = the reference's optimized tier) the
+    // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
+    // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
+    const bool skip1 = claim != nullptr && !c->verify_rounds;
+    int st = member_round(mem, bind, skip1, nullptr);
+    if (st != JB_OK) return st;
+    st = wait_round_result(c);
+    if (st != JB_OK) return st;
+    st = assemble_evals(c, mem->m, skip1, c->h_result, claim, round, out_evals);
+    if (st == JB_OK) mem->rounds_done++;
+    return st;
+}
+
+// ---- index-sharded member ----------------------------------------------------------------------
+static int gather_into_tail(jb_member* mem) {
+    jb_ctx* c = mem->ctx;
+    const size_t len = mem->len, G = (size_t)c->world;
+    jb_member* tail = new (std::nothrow) jb_member();
+    if (!tail) return JB_ERR_OOM;
+    tail->ctx = c;
+    tail->m = mem->m;
+    tail->order = JB_LOW_TO_HIGH;
+    tail->len = len * G;
+    tail->rounds = 0;
+    while (((size_t)1 << tail->rounds) < tail->len) ++tail->rounds;
+    for (int j = 0; j < mem->m; ++j) {
+        Table t;
+        int st = c->dev_alloc((void**)&t.buf, tail->len * 32);
+        if (st != JB_OK) { delete tail; return st; }
+        t.cap = t.len = tail->len;
+        tail->tables.push_back(t);
+        // rank order == global order for contiguous blocks under LowToHigh binding
+        st = c->comm_allgather(mem->tables[j].buf, t.buf, len * 4);
+        if (st != JB_OK) { delete tail; return st; }
+    }
+    mem->tail = tail;
+    return JB_OK;
+}
+
+static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
+                               uint64_t* out_evals) {
+    jb_ctx* c = mem->ctx;
+    {
+        Guard g(c);
+        if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
+        if (!mem->tail) {
+            const size_t len_after = bind ? mem->len / 2 : mem->len;
+            if (len_after > mem->gather_len) {
+                // a sharded round: local fused pass -> lanes -> ONE all-reduce -> publish -> host fold
+                const bool skip1 = claim != nullptr && !c->verify_rounds;
+                const int K = skip1 ? mem->m : mem->m + 1;
+                int st = member_round(mem, bind, skip1, c->d_lanes);
+                if (st == JB_OK) st = c->comm_allreduce_lanes(c->d_lanes, (size_t)K * 8);
+                if (st == JB_OK) st = c->publish_lanes(c->d_lanes, K * 8);
+                if (st == JB_OK) st = wait_round_result(c);
+                if (st != JB_OK) return st;
+                uint64_t vals[JB_MAX_EVALS * 4];
+                st = jb_lanes_reduce_host(c->h_result, (size_t)K, vals);
+                if (st != JB_OK) return st;
+                return assemble_evals(c, mem->m, skip1, vals, claim, round, out_evals);
+            }
+            // the shard is small: apply the pending bind, gather, continue on the tail
+            if (bind) {
+                for (int j = 0; j < mem->m; ++j) {
+                    int st = bind_table(c, mem->tables[j], bind, mem->order);
+                    if (st != JB_OK) return st;
+                }
+                mem->len /= 2;
+                bind = nullptr;
+            }
+            int st = gather_into_tail(mem);
+            if (st != JB_OK) return st;
+        }
+    }
+    return jb_member_prove_round(mem->tail, bind, mem->tail->rounds_done, claim, out_evals);
+}
+
+int jb_sharded_member_create(jb_ctx* c, const jb_table* handles, size_t m, size_t gather_log, jb_member** out) {
+    if (!c || !out) return JB_ERR_INVALID;
+    if (!c->nccl_comm) return c->fail(JB_ERR_INVALID, "sharded member: no communicator (jb_comm_init)");
+    int st = jb_member_create(c, handles, m, JB_LOW_TO_HIGH, out);
+    if (st != JB_OK) return st;
+    jb_member* mem = *out;
+    size_t log_g = 0;
+    while ((1 << log_g) < c->world) ++log_g;
+    mem->sharded = true;
+    mem->gather_len = (size_t)1 << gather_log;
+    if (mem->gather_len > mem->len) mem->gather_len = mem->len;
+    mem->rounds += log_g;
     return JB_OK;
 }
 
@@ -691,6 +791,10 @@ int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t ca
 int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     if (!mem || !bind) return JB_ERR_INVALID;
     jb_ctx* c = mem->ctx;
+    if (mem->sharded) {
+        if (!mem->tail) return c->fail(JB_ERR_INVALID, "finish_rounds: sharded member has not reached its tail");
+        return jb_member_finish_rounds(mem->tail, bind);
+    }
     Guard g(c);
     if (mem->len < 2) return c->fail(JB_ERR_INVALID, "finish_rounds: member already fully bound");
     for (int j = 0; j < mem->m; ++j) {
@@ -704,6 +808,10 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
 int jb_member_final_evals(jb_member* mem, uint64_t* out) {
     if (!mem || !out) return JB_ERR_INVALID;
     jb_ctx* c = mem->ctx;
+    if (mem->sharded) {
+        if (!mem->tail) return c->fail(JB_ERR_INVALID, "NotFullyBound (sharded member before its tail)");
+        return jb_member_final_evals(mem->tail, out);
+    }
     Guard g(c);
     if (mem->len != 1) {
         char buf[96];
@@ -725,6 +833,7 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out) {
 
 void jb_member_destroy(jb_member* mem) {
     if (!mem) return;
+    if (mem->tail) jb_member_destroy(mem->tail);
     {
         Guard g(mem->ctx);
         for (auto& t : mem->tables) mem->ctx->release(t);

@@ -67,6 +67,13 @@ struct jb_ctx {
     unsigned int* d_counter = nullptr;   // last-block ticket counter (zero between launches)
     uint64_t result_seq = 0;
     MsmWorkspace* msm = nullptr;
+    // multi-GPU (comm.cu): NCCL communicator + the lanes buffer the per-round all-reduce runs on
+    void* nccl_comm = nullptr;
+    int world = 1, rank = 0;
+    uint64_t* d_lanes = nullptr;
+    int comm_allreduce_lanes(uint64_t* d_lanes_buf, size_t n_u64);
+    int comm_allgather(const uint64_t* d_send, uint64_t* d_recv, size_t n_u64_per_rank);
+    int publish_lanes(const uint64_t* d_lanes_buf, int n_u64);
     bool timing = false;
     uint64_t timing_min_items = 0;
     std::vector<TimedLaunch> timed;

@@ -53,68 +53,59 @@ def splitmix_challenge(seed: int, poly: UnivariatePoly) -> int:
     return F.from_limbs(out)
 
 
-class ShardedProductSumcheck:
-    """Drives one rank's shard (a ProductMember over its contiguous block, LowToHigh)."""
+def init_comm(sess: Session, dist) -> None:
+    """Creates the context's NCCL communicator: rank 0 draws the unique id, torch.distributed (the
+    rendezvous the launcher already set up) broadcasts it, every rank joins. Per-round collectives are
+    then issued by the C++ side directly on the context's stream."""
+    import torch
+    lib = sess.lib
+    buf = (ctypes.c_uint8 * 128)()
+    if dist.get_rank() == 0:
+        st = lib.jb_comm_unique_id(buf, None)
+        if st != _lib.JB_OK:
+            raise RuntimeError(f"jb_comm_unique_id failed ({st}): libnccl not loadable")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, src=0)
+    host = t.cpu().numpy().tobytes()
+    buf = (ctypes.c_uint8 * 128).from_buffer_copy(host)
+    sess.check(lib.jb_comm_init(sess.h, dist.get_world_size(), dist.get_rank(), buf, None))
 
-    def __init__(self, sess: Session, member: ProductMember, m: int, log_n_local: int, dist, seed: int,
-                 gather_log: int = GATHER_LOG):
-        import torch
-        self.torch = torch
-        self.s, self.mem, self.m, self.log_n, self.dist, self.seed = sess, member, m, log_n_local, dist, seed
-        self.world = dist.get_world_size()
-        self.rank = dist.get_rank()
-        assert self.world & (self.world - 1) == 0, "world size must be a power of two"
-        self.log_g = self.world.bit_length() - 1
-        self.gather_log = min(gather_log, log_n_local)
 
-    def prove(self, claimed_sum: int | None = None):
-        torch, lib, mem, m = self.torch, self.s.lib, self.mem, self.m
-        lanes = torch.zeros((m + 1) * 8, dtype=torch.int64, device="cuda")
-        out = np.empty((m + 1, 4), dtype=np.uint64)
-        challenges, polys = [], []
-        bind, claim = None, claimed_sum
-        sharded_rounds = self.log_n - self.gather_log
-        for rnd in range(sharded_rounds):
-            b = None if bind is None else F.to_limbs(bind)
-            skip = claim is not None  # s(1) = claim - s(0): one point fewer to compute and to reduce
-            cnt = m if skip else m + 1
-            self.s.check(lib.jb_member_prove_round_partials(mem.h, _p(b) if b is not None else None, rnd,
-                                                            1 if skip else 0, ctypes.c_void_p(lanes.data_ptr())))
-            self.dist.all_reduce(lanes[: cnt * 8])  # integer sum of 32-bit limbs: exact
-            self.s.check(lib.jb_partials_finalize(self.s.h, ctypes.c_void_p(lanes.data_ptr()), cnt, _p(out)))
-            ev = F.limbs_to_ints(out[:cnt])
-            if skip:
-                ev.insert(1, (claim - ev[0]) % F.R_MOD)
-            poly = UnivariatePoly.from_evals(ev)
-            c = splitmix_challenge(self.seed, poly)
-            claim = poly.evaluate(c)
-            challenges.append(c)
-            polys.append(poly)
-            bind = c
-        # apply the pending bind, then gather the (now small) shards: rank order == global order
-        if bind is not None:
-            self.s.check(lib.jb_member_finish_rounds(mem.h, _p(F.to_limbs(bind))))
-        shard = 1 << self.gather_log
-        gathered = []
-        for j in range(m):
-            local = torch.empty((shard, 4), dtype=torch.int64, device="cuda")
-            n_out = ctypes.c_size_t()
-            self.s.check(lib.jb_member_export_table(mem.h, j, ctypes.c_void_p(local.data_ptr()), shard, ctypes.byref(n_out)))
-            assert n_out.value == shard
-            full = torch.empty((self.world * shard, 4), dtype=torch.int64, device="cuda")
-            self.dist.all_gather_into_tensor(full, local)
-            gathered.append(full)
-        tail_polys = [Polynomial.wrap_device(self.s, g.data_ptr(), g.shape[0]) for g in gathered]
-        tail = ProductMember(self.s, tail_polys, LOW_TO_HIGH)
-        tail_rounds = self.gather_log + self.log_g
-        if claim is None:  # no sharded round ran: derive the claim from the gathered tables
-            ev = tail.prove_round_evals(None, 0)
-            claim = (ev[0] + ev[1]) % F.R_MOD
-            tail.close()
-            tail = ProductMember(self.s, [Polynomial.wrap_device(self.s, g.data_ptr(), g.shape[0]) for g in gathered],
-                                 LOW_TO_HIGH)
-        res = prove_batch_native([BatchMember(claim, 1, tail_rounds, 0)], [tail], tail_rounds, m, claim, seed=self.seed)
-        fe = tail.final_evals()
-        tail.close()
-        self._keep = gathered
-        return ProvedBatch(challenges + res.challenges, res.final_claim, res.member_claims, polys + res.round_polynomials), fe
+class ShardedProductMember(ProductMember):
+    """ProveRounds member over this rank's contiguous block of the global tables (jb_sharded_member_create).
+    Reports log2(local) + log2(world) rounds; `previous_claim` is the global claim."""
+
+    def __init__(self, session: Session, polys: list[Polynomial], gather_log: int = GATHER_LOG):
+        self.s = session
+        handles = np.array([p.handle for p in polys], dtype=np.uint64)
+        h = ctypes.c_void_p()
+        session.check(session.lib.jb_sharded_member_create(session.h, _p(handles), len(polys), gather_log, ctypes.byref(h)))
+        for p in polys:
+            p.handle = 0
+        self.h = h
+        self.m = len(polys)
+
+
+def sharded_claim(sess: Session, polys: list[Polynomial], dist) -> int:
+    """sum_x prod_j f_j(x) over the GLOBAL tables: one eval-only pass per rank + one all-reduce."""
+    import torch
+    m = len(polys)
+    probe = ProductMember(sess, [p.clone() for p in polys], LOW_TO_HIGH)
+    lanes = torch.zeros((m + 1) * 8, dtype=torch.int64, device="cuda")
+    sess.check(sess.lib.jb_member_prove_round_partials(probe.h, None, 0, 0, ctypes.c_void_p(lanes.data_ptr())))
+    sess.synchronize()
+    dist.all_reduce(lanes)
+    ev = lanes_to_ints(lanes.cpu().numpy().view(np.uint64))
+    probe.close()
+    return (ev[0] + ev[1]) % F.R_MOD
+
+
+def prove_sharded(sess: Session, polys: list[Polynomial], claim: int, seed: int, gather_log: int = GATHER_LOG):
+    """One index-sharded product sumcheck through the C++ engine (jb_prove_batch): no Python in the
+    round loop. Returns (ProvedBatch, final_evals); identical on every rank."""
+    mem = ShardedProductMember(sess, polys, gather_log)
+    rounds = mem.num_rounds()
+    res = prove_batch_native([BatchMember(claim, 1, rounds, 0)], [mem], rounds, mem.m, claim, seed=seed)
+    fe = mem.final_evals()
+    mem.close()
+    return res, fe

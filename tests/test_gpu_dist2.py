@@ -22,7 +22,7 @@ def _worker(rank, world, port, log_n_local, m, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import jolt_b200
     from jolt_b200 import LOW_TO_HIGH, Polynomial, ProductMember
-    from jolt_b200.dist import ShardedProductSumcheck
+    from jolt_b200.dist import init_comm, prove_sharded, sharded_claim
     from oracle.coracle import rand_limbs
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -30,8 +30,10 @@ def _worker(rank, world, port, log_n_local, m, q):
     n = 1 << log_n_local
     glob = [rand_limbs(900 + j, n * world) for j in range(m)]
     shard = [g[rank * n:(rank + 1) * n] for g in glob]          # contiguous block per rank
-    mem = ProductMember(sess, [Polynomial.new(sess, s) for s in shard], LOW_TO_HIGH)
-    res, fe = ShardedProductSumcheck(sess, mem, m, log_n_local, dist, seed=11, gather_log=6).prove(None)
+    init_comm(sess, dist)
+    polys = [Polynomial.new(sess, s) for s in shard]
+    claim = sharded_claim(sess, polys, dist)
+    res, fe = prove_sharded(sess, polys, claim, seed=11, gather_log=6)
     q.put((rank, res.challenges, res.final_claim, fe, [p.coefficients for p in res.round_polynomials]))
     dist.barrier()
     dist.destroy_process_group()

@@ -93,6 +93,7 @@ for lg in sizes:
     del buf
 
 # --- fused rounds ------------------------------------------------------------------------------
+eval_ms = {}
 for lg in ([22, 24] if quick else [20, 22, 24, 26]):
     n = 1 << lg
     for m in (1, 2, 3):
@@ -107,12 +108,16 @@ for lg in ([22, 24] if quick else [20, 22, 24, 26]):
                     if mode == "eval_only":
                         mem.prove_round_evals(None, 0)
                     else:
-                        # pretend round 0 happened: bind + eval in one pass
                         out = np.empty((m + 1, 4), dtype=np.uint64)
                         r = ch125 if mode.endswith("c125") else full
+                        sess.check(lib.jb_member_prove_round(mem.h, None, 0, None, _p(out)))
                         sess.check(lib.jb_member_prove_round(mem.h, _p(r), 1, None, _p(out)))
                     mem.close()
                 med, best = timed(one)
+                if mode != "eval_only":   # subtract the eval-only round 0 that had to precede the fused pass
+                    med, best = med - eval_ms[(m, oname)], best - eval_ms[(m, oname)]
+                else:
+                    eval_ms[(m, oname)] = med
                 bytes_ = m * (64 * (n // 2) if mode == "eval_only" else 48 * n)
                 emit(kind="fused", log_n=lg, m=m, order=oname, mode=mode, ms=round(med, 4), ms_best=round(best, 4),
                      gbs=round(bytes_ / med / 1e6, 1), frac=round(bytes_ / med / 1e6 / PEAK, 3))
