@@ -88,16 +88,20 @@ int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
     return st;
 }
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
-int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
-    static int per_sm = blocks_per_sm(fused_round_kernel<M, ORDER, BIND, HI4, SKIP1>);
-    // a thread may run at most FUSED_MAX_ITERS iterations (512-bit accumulator headroom)
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int MINB>
+int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
+    auto kernel = fused_round_kernel<M, ORDER, BIND, HI4, SKIP1, MINB>;
+    constexpr size_t smem = FusedShape<M, SKIP1>::SMEM_BYTES;
+    static int per_sm = [&] {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+        return nb;
+    }();
+    // grid-stride over whole waves of resident blocks; tiny rounds take one (small) block
     size_t need = (pairs + 255) / 256;
     size_t resident = (size_t)c->sm_count * per_sm;
-    size_t min_grid = (need + FUSED_MAX_ITERS - 1) / FUSED_MAX_ITERS;
     size_t grid = need < resident ? need : resident;
-    if (grid < min_grid) grid = ((min_grid + resident - 1) / resident) * resident;  // whole waves
-    if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     constexpr int K = FusedShape<M, SKIP1>::K;
     int st = c->ensure_partial(grid * K);
@@ -106,10 +110,21 @@ int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar&
     int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
     // latency path: a round of <= 32 pairs runs as one warp (no barriers, no shared-memory stage)
     const unsigned block = pairs <= 32 ? 32u : 256u;
-    fused_round_kernel<M, ORDER, BIND, HI4, SKIP1><<<(unsigned)grid, block, 0, c->stream>>>(tp, pairs, s, out);
+    kernel<<<(unsigned)grid, block, smem, c->stream>>>(tp, pairs, s, out);
     c->timing_end(tix);
     c->launches++;
     return c->check(cudaGetLastError(), "fused_round_kernel launch");
+}
+
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
+int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, const RoundOut& out) {
+    // register budget: 3 blocks/SM (<= 85 registers) for the common shapes, 2 where the sweep is wide
+    if constexpr (M <= 2) {
+        if (c->fused_minb == 2) return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 2>(c, tp, pairs, s, out);
+        return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 3>(c, tp, pairs, s, out);
+    } else {
+        return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 2>(c, tp, pairs, s, out);
+    }
 }
 
 template <int M, int ORDER, bool SKIP1>
@@ -214,6 +229,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
+    if (const char* mb = std::getenv("JB_FUSED_MINB")) c->fused_minb = std::atoi(mb);  // tuning knob (2 or 3)
     // keep freed blocks in the pool (ProofSession "device memory pools")
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -583,25 +599,37 @@ static int wait_round_result(jb_ctx* c) {
 static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
                                uint64_t* out_evals);
 
-// Assembles s(0..M) from the K published values (skip1: s(1) = claim - s(0)); checks the claim in verify mode.
+// Assembles s(0..M) from the K published values. Kernel order: s(0), [s(1)], s(2..M-1), s(inf) for
+// M >= 2 (s(0), [s(1)] for M == 1); with skip1, s(1) = claim - s(0). s(M) is rebuilt from the leading
+// coefficient: q(t) = s(t) - s(inf) t^M has degree < M, so q(M) = sum_{i<M} (-1)^(M-1-i) C(M,i) q(i).
+// In verify mode the claim is checked (naive.rs:301-308).
 static int assemble_evals(jb_ctx* c, int M, bool skip1, const uint64_t* vals, const uint64_t* claim, size_t round,
                           uint64_t* out_evals) {
-    if (skip1) {
-        HostFr s0 = HostFr::from_limbs(vals);
-        HostFr s1 = HostFr::from_limbs(claim) - s0;
-        s0.store(out_evals);
-        s1.store(out_evals + 4);
-        if (M > 1) std::memcpy(out_evals + 8, vals + 4, (size_t)(M - 1) * 32);
-        return JB_OK;
-    }
-    std::memcpy(out_evals, vals, (size_t)(M + 1) * 32);
-    if (claim) {
-        HostFr s0 = HostFr::from_limbs(out_evals), s1 = HostFr::from_limbs(out_evals + 4);
-        if ((s0 + s1) != HostFr::from_limbs(claim)) {
-            char buf[96];
-            std::snprintf(buf, sizeof buf, "RoundCheckFailed { round: %zu }", round);
-            return c->fail(JB_ERR_ROUND_CHECK, buf);
+    HostFr ev[JB_MAX_EVALS];
+    int k = 0;
+    ev[0] = HostFr::from_limbs(vals + 4 * k++);
+    if (skip1) ev[1] = HostFr::from_limbs(claim) - ev[0];
+    else ev[1] = HostFr::from_limbs(vals + 4 * k++);
+    if (M >= 2) {
+        for (int t = 2; t < M; ++t) ev[t] = HostFr::from_limbs(vals + 4 * k++);
+        const HostFr lead = HostFr::from_limbs(vals + 4 * k++);
+        static const uint64_t binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+        HostFr qM = HostFr::zero();
+        for (int i = 0; i < M; ++i) {
+            HostFr ti = HostFr::one();  // i^M
+            for (int e = 0; e < M; ++e) ti = ti * HostFr::from_u64((uint64_t)i);
+            HostFr term = (ev[i] - lead * ti) * HostFr::from_u64(binom[M][i]);
+            qM = ((M - 1 - i) & 1) ? qM - term : qM + term;
         }
+        HostFr tM = HostFr::one();  // M^M
+        for (int e = 0; e < M; ++e) tM = tM * HostFr::from_u64((uint64_t)M);
+        ev[M] = qM + lead * tM;
+    }
+    for (int t = 0; t <= M; ++t) ev[t].store(out_evals + 4 * t);
+    if (claim && !skip1 && (ev[0] + ev[1]) != HostFr::from_limbs(claim)) {
+        char buf[96];
+        std::snprintf(buf, sizeof buf, "RoundCheckFailed { round: %zu }", round);
+        return c->fail(JB_ERR_ROUND_CHECK, buf);
     }
     return JB_OK;
 }

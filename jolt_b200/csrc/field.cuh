@@ -442,6 +442,138 @@ __device__ __forceinline__ void mul_wide_acc(uint32_t* acc, const uint32_t* a, c
           "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
 }
 
+// Shared-memory form: the 544-bit accumulator lives at acc[k * stride] (k = 0..16; one column per
+// thread, so accesses are conflict-free) and is only in registers while a product is merged - this
+// is what lets the fused round kernel run at three blocks per SM. Operands may be lazy (< 2p):
+// 17 words hold > 2^30 such products.
+__device__ __forceinline__ void mul_wide_acc_smem(uint32_t* acc, int stride, const uint32_t* a, const uint32_t* b) {
+    uint32_t E[17], O[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        chain8_top(E + i, E[i + 8], a[0], a[2], a[4], a[6], b[i]);
+        chain8_top(O + i, O[i + 8], a[1], a[3], a[5], a[7], b[i]);
+        chain8_top(O + i, O[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
+        chain8_top(E + i + 2, E[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
+    }
+    uint32_t A[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) A[k] = acc[k * stride];
+    asm("add.cc.u32 %0, %0, %17;\n\t"
+        "addc.cc.u32 %1, %1, %18;\n\t"
+        "addc.cc.u32 %2, %2, %19;\n\t"
+        "addc.cc.u32 %3, %3, %20;\n\t"
+        "addc.cc.u32 %4, %4, %21;\n\t"
+        "addc.cc.u32 %5, %5, %22;\n\t"
+        "addc.cc.u32 %6, %6, %23;\n\t"
+        "addc.cc.u32 %7, %7, %24;\n\t"
+        "addc.cc.u32 %8, %8, %25;\n\t"
+        "addc.cc.u32 %9, %9, %26;\n\t"
+        "addc.cc.u32 %10, %10, %27;\n\t"
+        "addc.cc.u32 %11, %11, %28;\n\t"
+        "addc.cc.u32 %12, %12, %29;\n\t"
+        "addc.cc.u32 %13, %13, %30;\n\t"
+        "addc.cc.u32 %14, %14, %31;\n\t"
+        "addc.cc.u32 %15, %15, %32;\n\t"
+        "addc.u32 %16, %16, 0;"
+        : "+r"(A[0]), "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]),
+          "+r"(A[8]), "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15]),
+          "+r"(A[16])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
+          "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]));
+    asm("add.cc.u32 %0, %0, %16;\n\t"
+        "addc.cc.u32 %1, %1, %17;\n\t"
+        "addc.cc.u32 %2, %2, %18;\n\t"
+        "addc.cc.u32 %3, %3, %19;\n\t"
+        "addc.cc.u32 %4, %4, %20;\n\t"
+        "addc.cc.u32 %5, %5, %21;\n\t"
+        "addc.cc.u32 %6, %6, %22;\n\t"
+        "addc.cc.u32 %7, %7, %23;\n\t"
+        "addc.cc.u32 %8, %8, %24;\n\t"
+        "addc.cc.u32 %9, %9, %25;\n\t"
+        "addc.cc.u32 %10, %10, %26;\n\t"
+        "addc.cc.u32 %11, %11, %27;\n\t"
+        "addc.cc.u32 %12, %12, %28;\n\t"
+        "addc.cc.u32 %13, %13, %29;\n\t"
+        "addc.cc.u32 %14, %14, %30;\n\t"
+        "addc.u32 %15, %15, 0;"
+        : "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]), "+r"(A[8]),
+          "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15]), "+r"(A[16])
+        : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+#pragma unroll
+    for (int k = 0; k < 17; ++k) acc[k * stride] = A[k];
+}
+
+// 544-bit accumulator (17 words at acc[k * stride]) -> canonical acc * R^-1 mod p. One-off per thread.
+template <class PR>
+__device__ __forceinline__ Fp<PR> reduce_wide17(const uint32_t* acc, int stride) {
+    uint32_t T[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) T[k] = acc[k * stride];
+    // fold the top word: 2^512 == R^2 (mod p). Twice: the first fold can carry out once more.
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        uint32_t top = T[16];
+        T[16] = 0;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint64_t t = (uint64_t)top * PR::R2(j) + T[j] + carry;
+            T[j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+#pragma unroll
+        for (int l = 8; l < 17; ++l) {
+            uint64_t t = (uint64_t)T[l] + carry;
+            T[l] = (uint32_t)t;
+            carry = t >> 32;
+        }
+    }
+    // Montgomery reduction of T[0..15] with T[16] catching the carry
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t m = T[k] * PR::INV;
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint64_t t = (uint64_t)m * PR::P(j) + T[k + j] + carry;
+            T[k + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+#pragma unroll
+        for (int l = k + 8; l < 17; ++l) {
+            uint64_t t = (uint64_t)T[l] + carry;
+            T[l] = (uint32_t)t;
+            carry = t >> 32;
+        }
+    }
+    // result = T[8..16] < 2^256 + p: subtract p while it does not fit / is not canonical
+    uint32_t r[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) r[k] = T[8 + k];
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        uint32_t t[9];
+        uint64_t borrow = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            uint64_t pj = j < 8 ? PR::P(j) : 0u;
+            uint64_t d = (uint64_t)r[j] - pj - borrow;
+            t[j] = (uint32_t)d;
+            borrow = (d >> 32) & 1u;
+        }
+        if (borrow) break;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r[j] = t[j];
+    }
+    Fp<PR> out;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out.v[k] = r[k];
+    return out;
+}
+
 // Montgomery-reduce a 512-bit accumulator (< 2^511) to the canonical element acc * R^-1 mod p.
 // Runs once per thread per kernel, so it is written for clarity, not for the multiplier pipe.
 template <class PR>

@@ -179,31 +179,40 @@ struct TablePtrs {
 
 // Fused pass for a product-of-M member:
 //   BIND: first fold every table under `s` (writing the bound table), then
-//   evaluate s(t) = sum_y prod_j (lo_j(y) + t (hi_j(y) - lo_j(y))) over the BOUND tables, for
-//   t = 0..M, or - SKIP1, the reference's optimized-tier convention
-//   (jolt-kernels/src/optimized/support.rs:450-460) - for t in {0, 2, .., M}, the host deriving
-//   s(1) = previous_claim - s(0).
+//   sweep the BOUND tables for the round polynomial s(t) = sum_y prod_j (lo_j(y) + t D_j(y)),
+//   D_j = hi_j - lo_j. The kernel emits K values, in this order:
+//     s(0), [s(1) unless SKIP1], s(2), .., s(M-1), s(inf)          (M >= 2)
+//     s(0), [s(1) unless SKIP1]                                    (M == 1)
+//   where s(inf) = sum_y prod_j D_j(y) is the leading coefficient: evaluating at infinity instead of
+//   t = M needs no lo + t*D advance at all for M = 2 (s(1) uses hi_j directly), the same trade the
+//   reference makes in UnivariatePoly::from_evals_toom / the optimized tier's skipped evaluations
+//   (jolt-poly/src/univariate.rs:219-, jolt-kernels/src/optimized/support.rs:450-460). With SKIP1
+//   the host derives s(1) = previous_claim - s(0). The host rebuilds s(M) (capi.cu, assemble_evals).
 // `pairs` = number of y indices = (bound length)/2. Layout:
 //   HighToLow, BIND : reads e[y], e[y+P], e[y+2P], e[y+3P] (P = pairs); writes e'[y], e'[y+P] in place
 //   LowToHigh, BIND : reads e[4y..4y+3]; writes out[2y], out[2y+1]   (out-of-place)
 //   no BIND         : reads the pair only, writes nothing
-// The last factor of every product is multiplied in WITHOUT reduction into a 512-bit per-thread
-// accumulator (mul_wide_acc) and reduced once after the loop, so a thread may run at most
-// FUSED_MAX_ITERS iterations (the host sizes the grid accordingly). M == 1 has no product and
-// accumulates plain field sums. Each block then writes its sums and the last block folds them
-// (round_epilogue). All sums are exact field values, so the reduction order does not matter.
-constexpr int FUSED_MAX_ITERS = 8;
-
+// The last factor of every product is multiplied in WITHOUT reduction into a 544-bit per-thread
+// accumulator kept in SHARED memory (mul_wide_acc_smem; the GPU form of the reference's
+// WideAccumulator) and reduced once after the loop, which keeps the register count low enough for
+// three blocks per SM. M == 1 has no product and accumulates plain field sums. Each block then
+// writes its sums and the last block folds them (round_epilogue). All sums are exact field values,
+// so the reduction order does not matter.
 template <int M, bool SKIP1>
 struct FusedShape {
-    static constexpr int K = SKIP1 ? M : M + 1;  // number of evaluation points produced
+    static constexpr int K = SKIP1 ? M : M + 1;  // number of values produced
+    // dynamic shared memory: K accumulators x 17 words x 256 threads (M > 1) + the block-sum scratch
+    static constexpr size_t ACC_WORDS = (M == 1) ? 0 : (size_t)K * 17 * 256;
+    static constexpr size_t SMEM_BYTES = (ACC_WORDS + 8 * K * 8) * 4;
 };
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
-__global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int MINB>
+__global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
     constexpr int K = FusedShape<M, SKIP1>::K;
-    __shared__ uint32_t smem[8 * K * 8];
-    uint32_t wide[M == 1 ? 1 : K][16];
+    extern __shared__ uint32_t dsm[];
+    uint32_t* wacc = dsm;                                   // [e][word][tid]
+    uint32_t* red = dsm + FusedShape<M, SKIP1>::ACC_WORDS;  // block_sum scratch
+    const int tid = threadIdx.x;
     Fr sum1[M == 1 ? K : 1];
     if (M == 1) {
 #pragma unroll
@@ -212,15 +221,14 @@ __global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t p
 #pragma unroll
         for (int e = 0; e < K; ++e)
 #pragma unroll
-            for (int w = 0; w < 16; ++w) wide[e][w] = 0;
+            for (int w = 0; w < 17; ++w) wacc[(e * 17 + w) * 256 + tid] = 0;
     }
 
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
-        Fr cur[M], dlt[M];
+        Fr lo[M], hi[M];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
-            Fr lo, hi;
             if (BIND) {
                 Fr a, b, c, d;
                 if (ORDER == ORDER_HIGH_TO_LOW) {
@@ -228,58 +236,82 @@ __global__ void __launch_bounds__(256) fused_round_kernel(TablePtrs tp, size_t p
                     c = ld_elem_rw<Fr>(tp.in[j], y + 2 * pairs);
                     b = ld_elem_rw<Fr>(tp.in[j], y + pairs);
                     d = ld_elem_rw<Fr>(tp.in[j], y + 3 * pairs);
-                    lo = bind_pair<HI4>(a, c, s);
-                    hi = bind_pair<HI4>(b, d, s);
-                    st_elem(tp.out[j], y, lo);
-                    st_elem(tp.out[j], y + pairs, hi);
+                    lo[j] = bind_pair<HI4>(a, c, s);
+                    hi[j] = bind_pair<HI4>(b, d, s);
+                    st_elem(tp.out[j], y, lo[j]);
+                    st_elem(tp.out[j], y + pairs, hi[j]);
                 } else {
                     a = ld_elem<Fr>(tp.in[j], 4 * y);
                     b = ld_elem<Fr>(tp.in[j], 4 * y + 1);
                     c = ld_elem<Fr>(tp.in[j], 4 * y + 2);
                     d = ld_elem<Fr>(tp.in[j], 4 * y + 3);
-                    lo = bind_pair<HI4>(a, b, s);
-                    hi = bind_pair<HI4>(c, d, s);
-                    st_elem(tp.out[j], 2 * y, lo);
-                    st_elem(tp.out[j], 2 * y + 1, hi);
+                    lo[j] = bind_pair<HI4>(a, b, s);
+                    hi[j] = bind_pair<HI4>(c, d, s);
+                    st_elem(tp.out[j], 2 * y, lo[j]);
+                    st_elem(tp.out[j], 2 * y + 1, hi[j]);
                 }
             } else {
                 if (ORDER == ORDER_HIGH_TO_LOW) {
-                    lo = ld_elem_rw<Fr>(tp.in[j], y);
-                    hi = ld_elem_rw<Fr>(tp.in[j], y + pairs);
+                    lo[j] = ld_elem_rw<Fr>(tp.in[j], y);
+                    hi[j] = ld_elem_rw<Fr>(tp.in[j], y + pairs);
                 } else {
-                    lo = ld_elem<Fr>(tp.in[j], 2 * y);
-                    hi = ld_elem<Fr>(tp.in[j], 2 * y + 1);
+                    lo[j] = ld_elem<Fr>(tp.in[j], 2 * y);
+                    hi[j] = ld_elem<Fr>(tp.in[j], 2 * y + 1);
                 }
             }
-            cur[j] = lo;
-            if (!(M == 1 && SKIP1)) dlt[j] = fp_sub(hi, lo);
         }
-        int e = 0;
+        if (M == 1) {
+            sum1[0] = fp_add(sum1[0], lo[0]);
+            if (!SKIP1) sum1[K - 1] = fp_add(sum1[K - 1], hi[0]);
+        } else {
+            int e = 0;
+            {  // t = 0
+                Fr prod = lo[0];
 #pragma unroll
-        for (int t = 0; t <= M; ++t) {
-            if (!(SKIP1 && t == 1)) {
-                if (M == 1) {
-                    sum1[e] = fp_add(sum1[e], cur[0]);
-                } else {
+                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, lo[j]);
+                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, lo[M - 1].v);
+                ++e;
+            }
+            if (!SKIP1) {  // t = 1: lo + D = hi
+                Fr prod = hi[0];
+#pragma unroll
+                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, hi[j]);
+                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, hi[M - 1].v);
+                ++e;
+            }
+            Fr dlt[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) dlt[j] = (M == 2) ? fp_sub_lazy(hi[j], lo[j]) : fp_sub(hi[j], lo[j]);
+            if (M > 2) {  // t = 2 .. M-1
+                Fr cur[M];
+#pragma unroll
+                for (int j = 0; j < M; ++j) cur[j] = hi[j];
+#pragma unroll
+                for (int t = 2; t < M; ++t) {
+#pragma unroll
+                    for (int j = 0; j < M; ++j) cur[j] = fp_add(cur[j], dlt[j]);
                     Fr prod = cur[0];
 #pragma unroll
                     for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, cur[j]);
-                    mul_wide_acc(wide[e], prod.v, cur[M - 1].v);
+                    mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, cur[M - 1].v);
+                    ++e;
                 }
-                ++e;
             }
-            if (t < M && !(M == 1 && SKIP1)) {
+            {  // t = infinity: the leading coefficient prod_j D_j
+                Fr prod = dlt[0];
 #pragma unroll
-                for (int j = 0; j < M; ++j) cur[j] = fp_add(cur[j], dlt[j]);
+                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, dlt[j]);
+                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, dlt[M - 1].v);
             }
         }
     }
     Fr acc[K];
 #pragma unroll
-    for (int e = 0; e < K; ++e) acc[e] = (M == 1) ? sum1[e] : reduce_wide<FrParams>(wide[e]);
-    block_sum<K>(acc, smem);
-    __syncthreads();  // smem is reused by the last block's fold
-    round_epilogue<K>(acc, smem, out);
+    for (int e = 0; e < K; ++e)
+        acc[e] = (M == 1) ? sum1[e] : reduce_wide17<FrParams>(wacc + (e * 17) * 256 + tid, 256);
+    block_sum<K>(acc, red);
+    __syncthreads();  // scratch is reused by the last block's fold
+    round_epilogue<K>(acc, red, out);
 }
 
 // ---- eq-table expansion --------------------------------------------------------------------
