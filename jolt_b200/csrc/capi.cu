@@ -164,18 +164,23 @@ int eq_build(jb_ctx* c, const uint64_t* d_r, size_t nvars, const uint64_t* d_sca
         c->launches++;
         return c->check(cudaGetLastError(), "eq_expand_kernel launch");
     }
+    // n > 11: prefix table over the leading n-11 variables (recursively), the block-independent table
+    // over the trailing 8, and one streaming pass that writes every output exactly once.
     size_t hi_vars = nvars - EQ_BLOCK_VARS;
-    uint64_t* d_prefix = nullptr;
+    uint64_t *d_prefix = nullptr, *d_low8 = nullptr;
     int st = c->dev_alloc((void**)&d_prefix, ((size_t)1 << hi_vars) * 32);
-    if (st != JB_OK) return st;
-    st = eq_build(c, d_r, hi_vars, d_scale, d_prefix);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_low8, 256 * 32);
+    if (st == JB_OK) st = eq_build(c, d_r, hi_vars, d_scale, d_prefix);
+    if (st == JB_OK) st = eq_build(c, d_r + 4 * (hi_vars + 3), 8, nullptr, d_low8);
     if (st == JB_OK) {
-        eq_expand_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, nullptr, d_r + 4 * hi_vars,
-                                                                                EQ_BLOCK_VARS, d_out);
+        int tix = c->timing_begin(3, (uint64_t)1 << nvars, 1);
+        eq_stream_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, d_r + 4 * hi_vars, d_low8, d_out);
+        c->timing_end(tix);
         c->launches++;
-        st = c->check(cudaGetLastError(), "eq_expand_kernel launch");
+        st = c->check(cudaGetLastError(), "eq_stream_kernel launch");
     }
-    c->dev_free(d_prefix);
+    if (d_prefix) c->dev_free(d_prefix);
+    if (d_low8) c->dev_free(d_low8);
     return st;
 }
 

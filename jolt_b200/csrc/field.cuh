@@ -625,6 +625,12 @@ __device__ __forceinline__ F ld_elem(const uint64_t* base, size_t idx) {
     return r;
 }
 
+// Software prefetch of the 128-byte line holding element idx into L2 (no register cost): issued one
+// grid-stride iteration ahead so the demand load that follows finds the line on chip.
+__device__ __forceinline__ void prefetch_l2(const uint64_t* base, size_t idx) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint32_t*>(base) + idx * 8));
+}
+
 // coherent variant for buffers written earlier in the same kernel / aliased in-place updates
 template <class F>
 __device__ __forceinline__ F ld_elem_rw(const uint64_t* base, size_t idx) {

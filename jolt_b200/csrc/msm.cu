@@ -9,7 +9,8 @@
 //                   d_w in [-2^(c-1), 2^(c-1)], + per-(window, bucket) histogram (global REDs)
 //   2. scan       : exclusive prefix of the histogram -> bucket offsets
 //   3. scatter    : point indices (with the digit's sign) into bucket order (one atomic each)
-//   4. accumulate : one thread per (window, bucket): XYZZ += +-P (mixed add, 8M + 2S); the hot kernel
+//   4. accumulate : one thread per task (a <= max(64, cnt/64)-point chunk of one bucket): XYZZ += +-P
+//                   (mixed add, 8M + 2S) - the hot kernel; split buckets are folded by a combine pass
 //   5. segments   : per (window, 16-bucket segment) running sums -> sum_b weight(b) * B_b
 //   6. windows    : per-window tree sum of the segment results, then 2^(c w) by doubling
 //   7. final      : sum of the window points -> Jacobian (X, Y, Z)
@@ -86,31 +87,66 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars
     }
 }
 
-// ---- 2. exclusive scan (one block; the histogram is at most 17 * 2^15 counters) --------------------
-__global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned int* hist, unsigned int* offsets, size_t total) {
+// ---- 2. exclusive scans (one block; the histogram is at most 17 * 2^15 counters): point offsets per
+//         bucket AND task offsets per bucket. A bucket's list is cut into q_b <= MSM_MAX_CHUNKS tasks of
+//         L_b = max(MSM_CHUNK, ceil(cnt_b / MSM_MAX_CHUNKS)) points, so no thread ever walks more than
+//         max(MSM_CHUNK, cnt/64) points: this bounds the skew of short top windows, small scalars and
+//         adversarially repeated digits, and evens out the lanes of a warp. ------------------------------
+constexpr unsigned MSM_CHUNK = 64;
+constexpr unsigned MSM_MAX_CHUNKS = 64;
+
+__device__ __forceinline__ unsigned chunk_len(unsigned cnt) {
+    unsigned l = (cnt + MSM_MAX_CHUNKS - 1) / MSM_MAX_CHUNKS;
+    return l < MSM_CHUNK ? MSM_CHUNK : l;
+}
+__device__ __forceinline__ unsigned chunk_count(unsigned cnt) {
+    return cnt ? (cnt + chunk_len(cnt) - 1) / chunk_len(cnt) : 0;
+}
+
+__global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned int* hist, unsigned int* offsets, unsigned int* toff,
+                                                        size_t total) {
     __shared__ unsigned int sums[1024];
+    __shared__ unsigned int tsums[1024];
     const size_t per = (total + 1023) / 1024;
     const size_t lo = (size_t)threadIdx.x * per;
     const size_t hi = lo + per < total ? lo + per : total;
-    unsigned int s = 0;
-    for (size_t k = lo; k < hi; ++k) s += hist[k];
+    unsigned int s = 0, ts = 0;
+    for (size_t k = lo; k < hi; ++k) {
+        s += hist[k];
+        ts += chunk_count(hist[k]);
+    }
     sums[threadIdx.x] = s;
+    tsums[threadIdx.x] = ts;
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
+    for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan over the 1024 partials
         unsigned int v = threadIdx.x >= d ? sums[threadIdx.x - d] : 0;
+        unsigned int tv = threadIdx.x >= d ? tsums[threadIdx.x - d] : 0;
         __syncthreads();
         sums[threadIdx.x] += v;
+        tsums[threadIdx.x] += tv;
         __syncthreads();
     }
     unsigned int run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
+    unsigned int trun = threadIdx.x ? tsums[threadIdx.x - 1] : 0;
     for (size_t k = lo; k < hi; ++k) {
         unsigned int cnt = hist[k];
         offsets[k] = run;
+        toff[k] = trun;
         run += cnt;
+        trun += chunk_count(cnt);
         hist[k] = 0;  // reused as the scatter cursor
     }
-    if (threadIdx.x == 1023) offsets[total] = sums[1023];
+    if (threadIdx.x == 1023) {
+        offsets[total] = sums[1023];
+        toff[total] = tsums[1023];
+    }
+}
+
+// task -> bucket map (a bucket writes its <= 64 task slots)
+__global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* toff, size_t nbuckets, uint32_t* task_bucket) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    for (unsigned t = toff[b]; t < toff[b + 1]; ++t) task_bucket[t] = (uint32_t)b;
 }
 
 // ---- 3. scatter -----------------------------------------------------------------------------------
@@ -128,13 +164,20 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
     }
 }
 
-// ---- 4. bucket accumulation: the hot kernel ---------------------------------------------------------
+// ---- 4. bucket accumulation: the hot kernel. One thread per task (a chunk of one bucket's list). A
+//         single-chunk bucket is written straight to `buckets`; chunks of a split bucket go to `partial`
+//         and are folded by msm_combine_kernel. --------------------------------------------------------
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bases, const uint32_t* sorted,
-                                                             const unsigned int* offsets, size_t nbuckets,
-                                                             uint64_t* buckets) {
+                                                             const unsigned int* offsets, const unsigned int* toff,
+                                                             const uint32_t* task_bucket, size_t nbuckets,
+                                                             uint64_t* buckets, uint64_t* partial) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nbuckets) return;
-    unsigned int lo = offsets[t], hi = offsets[t + 1];
+    if (t >= toff[nbuckets]) return;
+    const uint32_t b = task_bucket[t];
+    const unsigned int base = offsets[b], cnt = offsets[b + 1] - base;
+    const unsigned int len = chunk_len(cnt), j = (unsigned int)t - toff[b];
+    unsigned int lo = base + j * len;
+    unsigned int hi = lo + len < base + cnt ? lo + len : base + cnt;
     XYZZ acc = XYZZ::inf();
     for (unsigned int k = lo; k < hi; ++k) {
         uint32_t e = sorted[k];
@@ -143,7 +186,20 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bas
         Fq py = ld_elem<Fq>(bases, 2 * idx + 1);
         xyzz_add_affine(acc, px, py, (e >> 31) != 0);
     }
-    st_xyzz(buckets, t, acc);
+    if (toff[b + 1] - toff[b] == 1) st_xyzz(buckets, b, acc);
+    else st_xyzz(partial, t, acc);
+}
+
+// empty buckets -> identity; split buckets -> sum of their chunk partials
+__global__ void __launch_bounds__(128) msm_combine_kernel(const unsigned int* toff, size_t nbuckets, const uint64_t* partial,
+                                                          uint64_t* buckets) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    unsigned int t0 = toff[b], t1 = toff[b + 1];
+    if (t1 - t0 == 1) return;
+    XYZZ acc = XYZZ::inf();
+    for (unsigned int t = t0; t < t1; ++t) xyzz_add(acc, ld_xyzz(partial, t));
+    st_xyzz(buckets, b, acc);
 }
 
 // ---- 5. segment sums: G = sum_{b in segment} (b + 1) * B_b ---------------------------------------------
@@ -313,14 +369,19 @@ struct Guard {
 int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
     const MsmPlan p = plan_for(n);
     const size_t nb = (size_t)p.W * p.B;
-    uint32_t *digits = nullptr, *sorted = nullptr;
-    unsigned int *hist = nullptr, *offsets = nullptr;
-    uint64_t *buckets = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
+    // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
+    const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
+    uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr;
+    unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr;
+    uint64_t *buckets = nullptr, *partial = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
     int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&hist, nb * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&offsets, (nb + 1) * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&toff, (nb + 1) * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&task_bucket, max_tasks * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&buckets, nb * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&partial, max_tasks * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)p.W * p.T * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)p.W * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
@@ -328,15 +389,18 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
         msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, digits, hist);
-        msm_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets, nb);
+        msm_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets, toff, nb);
         msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, offsets, hist, sorted);
+        msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
-        msm_accumulate_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(d_bases, sorted, offsets, nb, buckets);
+        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_bases, sorted, offsets, toff,
+                                                                                      task_bucket, nb, buckets, partial);
         c->timing_end(tix);
+        msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
         msm_segment_kernel<<<(unsigned)(((size_t)p.W * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, p.W, p.B, p.T, seg);
         msm_window_kernel<<<p.W, 256, 0, c->stream>>>(seg, p.T, p.c, win);
         msm_final_kernel<<<1, 32, 0, c->stream>>>(win, p.W, d_out);
-        c->launches += 7;
+        c->launches += 9;
         st = c->check(cudaGetLastError(), "msm kernels");
     }
     if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
@@ -344,9 +408,12 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
     c->dev_free(digits);
     c->dev_free(sorted);
+    c->dev_free(task_bucket);
     c->dev_free(hist);
     c->dev_free(offsets);
+    c->dev_free(toff);
     c->dev_free(buckets);
+    c->dev_free(partial);
     c->dev_free(seg);
     c->dev_free(win);
     c->dev_free(d_out);

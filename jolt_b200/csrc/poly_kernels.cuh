@@ -41,6 +41,14 @@ template <int ORDER, bool HI4>
 __global__ void __launch_bounds__(256) bind_kernel(const uint64_t* in, uint64_t* out, size_t half, BindScalar s) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < half; i += stride) {
+        if (i + stride < half) {
+            if (ORDER == ORDER_HIGH_TO_LOW) {
+                prefetch_l2(in, i + stride);
+                prefetch_l2(in, i + stride + half);
+            } else {
+                prefetch_l2(in, 2 * (i + stride));
+            }
+        }
         Fr lo, hi;
         if (ORDER == ORDER_HIGH_TO_LOW) {
             lo = ld_elem_rw<Fr>(in, i);
@@ -226,6 +234,23 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
 
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
+        // prefetch the next iteration's lines into L2 (ncu: long-scoreboard was the top stall)
+        if (y + stride < pairs) {
+            const size_t yn = y + stride;
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (ORDER == ORDER_HIGH_TO_LOW) {
+                    prefetch_l2(tp.in[j], yn);
+                    prefetch_l2(tp.in[j], yn + pairs);
+                    if (BIND) {
+                        prefetch_l2(tp.in[j], yn + 2 * pairs);
+                        prefetch_l2(tp.in[j], yn + 3 * pairs);
+                    }
+                } else {
+                    prefetch_l2(tp.in[j], (BIND ? 4 : 2) * yn);  // 4 (or 2) consecutive elements: one line
+                }
+            }
+        }
         Fr lo[M], hi[M];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
@@ -380,6 +405,39 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (i < cnt) st_elem(out, base_idx + i, e[i]);
+}
+
+// Streaming form for n > EQ_BLOCK_VARS: out[(b << 11) | (k << 8) | t] = prefix[b] * eq3[k] * low8[t]
+// where eq3 is the table over the block's first 3 variables and low8 the (unscaled, block-independent)
+// table over its last 8, built once by eq_expand_kernel. Each thread owns one low8 entry and emits 8
+// products; every store instruction writes 32 consecutive elements per warp (1 KiB, fully coalesced).
+// 1 Montgomery product and 32 B of HBM write per output element, no reads beyond the 8 KiB low8 table.
+__global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, const uint64_t* r3,
+                                                        const uint64_t* low8, uint64_t* out) {
+    __shared__ uint32_t c8[8 * 8];
+    const int tid = threadIdx.x;
+    if (tid < 8) {
+        // c[tid] = prefix[b] * prod_i (bit_i(tid) ? r3[i] : 1 - r3[i]), bit 2 of tid <-> r3[0] (MSB first)
+        Fr v = ld_elem_rw<Fr>(prefix, blockIdx.x);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Fr ri = ld_elem_rw<Fr>(r3, i);
+            Fr hi = fp_mul(v, ri);
+            v = ((tid >> (2 - i)) & 1) ? hi : fp_sub(v, hi);
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) c8[w * 8 + tid] = v.v[w];
+    }
+    __syncthreads();
+    const Fr t = ld_elem_rw<Fr>(low8, tid);
+    const size_t base = ((size_t)blockIdx.x << EQ_BLOCK_VARS) + tid;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        Fr c;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) c.v[w] = c8[w * 8 + k];
+        st_elem(out, base + ((size_t)k << 8), fp_mul(c, t));
+    }
 }
 
 // ---- element-wise helpers (tests + host glue) --------------------------------------------------

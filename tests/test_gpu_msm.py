@@ -157,3 +157,19 @@ def test_msm_closed_form_at_scale(sess, log_n):
     sc = rand_limbs(0x5CA1A2, n)
     got = g1_jacobian_to_affine(bases.msm(sc))
     assert got == O.g1_scalar_mul(O.G1_GEN, _weighted_sum(sc))
+
+
+def test_msm_skewed_digits(sess):
+    """Every scalar equal: each window has ONE non-empty bucket holding all n points - the worst case
+    for a bucket-per-thread schedule; the chunked task plan must still be exact (and not crawl)."""
+    n = 1 << 14
+    bases = G1Bases.generate_multiples(sess, G, n)
+    k = O.random_fr(77, 1)[0]
+    sc = np.tile(C.ints_to_mont([k]), (n, 1))
+    got = g1_jacobian_to_affine(bases.msm(sc))
+    assert got == O.g1_scalar_mul(O.G1_GEN, k * (n * (n + 1) // 2) % O.R_MOD)
+    # 0/1 scalars (a flag polynomial): only the digit-1 bucket of window 0 is populated
+    bits = np.array([(i * 7 + 3) % 5 == 0 for i in range(n)])
+    sc = C.ints_to_mont([int(b) for b in bits])
+    got = g1_jacobian_to_affine(bases.msm(sc))
+    assert got == O.g1_scalar_mul(O.G1_GEN, int(sum(i + 1 for i in range(n) if bits[i])))
