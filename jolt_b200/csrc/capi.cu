@@ -157,10 +157,28 @@ int dispatch_fused(jb_ctx* c, int m, int order, bool skip1, const TablePtrs& tp,
     }
 }
 
-// eq table for `nvars` variables (device r), scale from device pointer or null; recursive prefix.
-int eq_build(jb_ctx* c, const uint64_t* d_r, size_t nvars, const uint64_t* d_scale, uint64_t* d_out) {
+// eq table for `nvars` variables (HOST limbs r, optional host scale); recursive prefix for n > 11.
+EqVars eq_vars(const uint64_t* r, size_t count, const uint64_t* scale) {
+    EqVars v;
+    std::memset(&v, 0, sizeof v);
+    for (size_t j = 0; j < count; ++j)
+        for (int w = 0; w < 4; ++w) {
+            v.r[j][2 * w] = (uint32_t)r[4 * j + w];
+            v.r[j][2 * w + 1] = (uint32_t)(r[4 * j + w] >> 32);
+        }
+    if (scale) {
+        v.has_scale = 1;
+        for (int w = 0; w < 4; ++w) {
+            v.scale[2 * w] = (uint32_t)scale[w];
+            v.scale[2 * w + 1] = (uint32_t)(scale[w] >> 32);
+        }
+    }
+    return v;
+}
+
+int eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, uint64_t* d_out) {
     if (nvars <= (size_t)EQ_BLOCK_VARS) {
-        eq_expand_kernel<<<1, 256, 0, c->stream>>>(nullptr, d_scale, d_r, (int)nvars, d_out);
+        eq_expand_kernel<<<1, 256, 0, c->stream>>>(nullptr, eq_vars(r, nvars, scale), (int)nvars, d_out);
         c->launches++;
         return c->check(cudaGetLastError(), "eq_expand_kernel launch");
     }
@@ -170,11 +188,12 @@ int eq_build(jb_ctx* c, const uint64_t* d_r, size_t nvars, const uint64_t* d_sca
     uint64_t *d_prefix = nullptr, *d_low8 = nullptr;
     int st = c->dev_alloc((void**)&d_prefix, ((size_t)1 << hi_vars) * 32);
     if (st == JB_OK) st = c->dev_alloc((void**)&d_low8, 256 * 32);
-    if (st == JB_OK) st = eq_build(c, d_r, hi_vars, d_scale, d_prefix);
-    if (st == JB_OK) st = eq_build(c, d_r + 4 * (hi_vars + 3), 8, nullptr, d_low8);
+    if (st == JB_OK) st = eq_build(c, r, hi_vars, scale, d_prefix);
+    if (st == JB_OK) st = eq_build(c, r + 4 * (hi_vars + 3), 8, nullptr, d_low8);
     if (st == JB_OK) {
         int tix = c->timing_begin(3, (uint64_t)1 << nvars, 1);
-        eq_stream_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, d_r + 4 * hi_vars, d_low8, d_out);
+        eq_stream_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, eq_vars(r + 4 * hi_vars, 3, nullptr),
+                                                                                d_low8, d_out);
         c->timing_end(tix);
         c->launches++;
         st = c->check(cudaGetLastError(), "eq_stream_kernel launch");
@@ -432,18 +451,7 @@ int jb_eq_evals(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scal
     int st = jb_table_alloc(c, (size_t)1 << nvars, out);
     if (st != JB_OK) return st;
     Guard g(c);
-    // stage r and the scale on the device (n + 1 elements)
-    uint64_t* d_r = nullptr;
-    st = c->dev_alloc((void**)&d_r, (nvars + 1) * 32);
-    if (st != JB_OK) return st;
-    std::vector<uint64_t> host((nvars + 1) * 4);
-    if (nvars) std::memcpy(host.data(), r, nvars * 32);
-    if (scale) std::memcpy(host.data() + 4 * nvars, scale, 32);
-    st = c->check(cudaMemcpyAsync(d_r, host.data(), (nvars + 1) * 32, cudaMemcpyHostToDevice, c->stream), "eq: H2D");
-    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "eq: H2D sync");  // `host` is pageable
-    if (st == JB_OK) st = eq_build(c, d_r, nvars, scale ? d_r + 4 * nvars : nullptr, c->tables[*out].buf);
-    c->dev_free(d_r);
-    return st;
+    return eq_build(c, r, nvars, scale, c->tables[*out].buf);
 }
 
 int jb_eq_evals_aligned_block(jb_ctx* c, const uint64_t* r, size_t nvars, size_t start_index, size_t block_size,

@@ -348,10 +348,22 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
 //            outputs (256 B). Total work ~ 1 mul + 1 sub per output, written once: 32 B/output.
 constexpr int EQ_BLOCK_VARS = 11;  // 2^11 outputs per block, 256 threads x 8
 
+// The point travels in the kernel-parameter space (<= 11 variables per launch): no staging buffer,
+// no host->device copy, no synchronisation on the eq path.
+struct EqVars {
+    uint32_t r[EQ_BLOCK_VARS][8];  // r[0] = most significant variable of this launch
+    uint32_t scale[8];
+    int has_scale;
+};
+__device__ __forceinline__ Fr eq_var(const EqVars& v, int j) {
+    Fr x;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x.v[w] = v.r[j][w];
+    return x;
+}
+
 __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix,  // gridDim.x prefix values (or null: scale)
-                                                        const uint64_t* scale,   // used when prefix == null (may be null: one)
-                                                        const uint64_t* r,       // nv block variables, r[0] = most significant
-                                                        int nv, uint64_t* out) {
+                                                        const __grid_constant__ EqVars ev, int nv, uint64_t* out) {
     __shared__ uint32_t tab[8 * 256];  // word-major: tab[w*256 + idx] (conflict-free)
     const int tid = threadIdx.x;
     const int reg_vars = nv < 3 ? nv : 3;
@@ -359,7 +371,10 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
     if (tid == 0) {
         Fr base = Fr::one();
         if (prefix) base = ld_elem_rw<Fr>(prefix, blockIdx.x);
-        else if (scale) base = ld_elem_rw<Fr>(scale, 0);
+        else if (ev.has_scale) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) base.v[w] = ev.scale[w];
+        }
 #pragma unroll
         for (int w = 0; w < 8; ++w) tab[w * 256] = base.v[w];
     }
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
         if (tid < cur) {
 #pragma unroll
             for (int w = 0; w < 8; ++w) v.v[w] = tab[w * 256 + tid];
-            hi = fp_mul(v, ld_elem_rw<Fr>(r, j));
+            hi = fp_mul(v, eq_var(ev, j));
         }
         __syncthreads();
         if (tid < cur) {
@@ -391,7 +406,7 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         if (j < reg_vars) {  // block-uniform
-            Fr rj = ld_elem_rw<Fr>(r, smem_vars + j);
+            Fr rj = eq_var(ev, smem_vars + j);
 #pragma unroll
             for (int i = (1 << j) - 1; i >= 0; --i) {
                 Fr hi = fp_mul(e[i], rj);
@@ -412,7 +427,7 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
 // table over its last 8, built once by eq_expand_kernel. Each thread owns one low8 entry and emits 8
 // products; every store instruction writes 32 consecutive elements per warp (1 KiB, fully coalesced).
 // 1 Montgomery product and 32 B of HBM write per output element, no reads beyond the 8 KiB low8 table.
-__global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, const uint64_t* r3,
+__global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, const __grid_constant__ EqVars ev,
                                                         const uint64_t* low8, uint64_t* out) {
     __shared__ uint32_t c8[8 * 8];
     const int tid = threadIdx.x;
@@ -421,7 +436,7 @@ __global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, 
         Fr v = ld_elem_rw<Fr>(prefix, blockIdx.x);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            Fr ri = ld_elem_rw<Fr>(r3, i);
+            Fr ri = eq_var(ev, i);
             Fr hi = fp_mul(v, ri);
             v = ((tid >> (2 - i)) & 1) ? hi : fp_sub(v, hi);
         }
