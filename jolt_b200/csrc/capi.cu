@@ -192,8 +192,12 @@ int eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, 
     if (st == JB_OK) st = eq_build(c, r + 4 * (hi_vars + 3), 8, nullptr, d_low8);
     if (st == JB_OK) {
         int tix = c->timing_begin(3, (uint64_t)1 << nvars, 1);
-        eq_stream_kernel<<<(unsigned)((size_t)1 << hi_vars), 256, 0, c->stream>>>(d_prefix, eq_vars(r + 4 * hi_vars, 3, nullptr),
-                                                                                d_low8, d_out);
+        const uint64_t* r3 = r + 4 * hi_vars;
+        bool hi4 = true;  // all three register-stage variables are 125-bit challenges [0,0,lo,hi]
+        for (int j = 0; j < 3; ++j) hi4 = hi4 && r3[4 * j] == 0 && r3[4 * j + 1] == 0;
+        const unsigned g = (unsigned)((size_t)1 << hi_vars);
+        if (hi4) eq_stream_kernel<true><<<g, 256, 0, c->stream>>>(d_prefix, eq_vars(r3, 3, nullptr), d_low8, d_out);
+        else eq_stream_kernel<false><<<g, 256, 0, c->stream>>>(d_prefix, eq_vars(r3, 3, nullptr), d_low8, d_out);
         c->timing_end(tix);
         c->launches++;
         st = c->check(cudaGetLastError(), "eq_stream_kernel launch");

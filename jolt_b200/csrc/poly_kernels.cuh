@@ -422,37 +422,36 @@ __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix, 
         if (i < cnt) st_elem(out, base_idx + i, e[i]);
 }
 
-// Streaming form for n > EQ_BLOCK_VARS: out[(b << 11) | (k << 8) | t] = prefix[b] * eq3[k] * low8[t]
-// where eq3 is the table over the block's first 3 variables and low8 the (unscaled, block-independent)
-// table over its last 8, built once by eq_expand_kernel. Each thread owns one low8 entry and emits 8
-// products; every store instruction writes 32 consecutive elements per warp (1 KiB, fully coalesced).
-// 1 Montgomery product and 32 B of HBM write per output element, no reads beyond the 8 KiB low8 table.
+// Streaming form for n > EQ_BLOCK_VARS: out[(b << 11) | (k << 8) | t] = prefix[b] * low8[t] * eq3[k]
+// where low8 is the (unscaled, block-independent) table over the block's last 8 variables, built once
+// by eq_expand_kernel, and eq3 the table over its first 3. Each thread forms v = prefix[b] * low8[t]
+// (one full product) and expands the three leading variables in registers with the reference's
+// doubling step hi = v * r_j, lo = v - hi (eq.rs:308-312) - products by the POINT, so a 125-bit
+// challenge point (Montgomery limbs [0,0,lo,hi]) takes the 4-row product: 1 + 7/2 full-product
+// equivalents per 8 outputs instead of 8. Every store instruction writes 32 consecutive elements per
+// warp (1 KiB, fully coalesced); 32 B of HBM write per output, no reads beyond the 8 KiB low8 table.
+// One Montgomery product per output is inherent to an eq table (2^n - 1 products for 2^n leaves), so
+// with a full 254-bit point this kernel is bound by the integer pipe (66.8 G mul/s x 32 B = 2.1 TB/s),
+// not by HBM.
+template <bool HI4>
 __global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, const __grid_constant__ EqVars ev,
                                                         const uint64_t* low8, uint64_t* out) {
-    __shared__ uint32_t c8[8 * 8];
     const int tid = threadIdx.x;
-    if (tid < 8) {
-        // c[tid] = prefix[b] * prod_i (bit_i(tid) ? r3[i] : 1 - r3[i]), bit 2 of tid <-> r3[0] (MSB first)
-        Fr v = ld_elem_rw<Fr>(prefix, blockIdx.x);
+    Fr e[8];
+    e[0] = fp_mul(ld_elem_rw<Fr>(prefix, blockIdx.x), ld_elem_rw<Fr>(low8, tid));
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            Fr ri = eq_var(ev, i);
-            Fr hi = fp_mul(v, ri);
-            v = ((tid >> (2 - i)) & 1) ? hi : fp_sub(v, hi);
+    for (int j = 0; j < 3; ++j) {
+        const Fr rj = eq_var(ev, j);
+#pragma unroll
+        for (int i = (1 << j) - 1; i >= 0; --i) {
+            Fr hi = HI4 ? fp_mul_hi4(e[i], rj.v + 4) : fp_mul(e[i], rj);
+            e[2 * i] = fp_sub(e[i], hi);
+            e[2 * i + 1] = hi;
         }
-#pragma unroll
-        for (int w = 0; w < 8; ++w) c8[w * 8 + tid] = v.v[w];
     }
-    __syncthreads();
-    const Fr t = ld_elem_rw<Fr>(low8, tid);
     const size_t base = ((size_t)blockIdx.x << EQ_BLOCK_VARS) + tid;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        Fr c;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) c.v[w] = c8[w * 8 + k];
-        st_elem(out, base + ((size_t)k << 8), fp_mul(c, t));
-    }
+    for (int k = 0; k < 8; ++k) st_elem(out, base + ((size_t)k << 8), e[k]);
 }
 
 // ---- element-wise helpers (tests + host glue) --------------------------------------------------

@@ -50,9 +50,18 @@ def test_eq_aligned_block_is_slice(sess):
         assert (got == full[start:start + size]).all()
 
 
-def test_eq_2pow22(sess):
+@pytest.mark.parametrize("kind", ["full254", "challenge125", "mixed"])
+def test_eq_2pow22(sess, kind):
+    """BASELINE size; the point as full elements, as 125-bit challenges [0,0,lo,hi] (the 4-row product
+    path, mod.rs:172-184), and mixed."""
     n = 22
     r = rand_limbs(0xE0, n)
+    if kind != "full254":
+        r[:, 0] = 0
+        r[:, 1] = 0
+        r[:, 3] &= np.uint64((1 << 61) - 1)
+    if kind == "mixed":
+        r[12] = rand_limbs(5, 1)[0]
     got = EqPolynomial.evals(sess, r).evals()
     want = C.eq_evals(r, None, threads=C.max_threads())
     assert (got == want).all()

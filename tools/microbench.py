@@ -124,8 +124,11 @@ for lg in ([22, 24] if quick else [20, 22, 24, 26]):
         del bufs
 
 # --- eq ---------------------------------------------------------------------------------------
-for lg in ([22] if quick else [17, 20, 22, 24, 26]):
+for lg, kind in [(l, k) for l in ([22] if quick else [20, 22, 24, 26]) for k in ("c125", "f254")]:
     r = np.ascontiguousarray(rand_table(lg, 7).cpu().numpy().view(np.uint64))
+    if kind == "c125":
+        r[:, 0] = 0
+        r[:, 1] = 0
     def one():
         EqPolynomial.evals(sess, r).free()
     sess.timing_enable(True, 1 << 12)
@@ -134,7 +137,7 @@ for lg in ([22] if quick else [17, 20, 22, 24, 26]):
     sess.timing_enable(False)
     kms = sorted(ks)[len(ks) // 2] if ks else float("nan")
     bytes_ = 32 << lg
-    emit(kind="eq", log_n=lg, call_ms=round(med, 4), kernel_ms=round(kms, 4), gbs_call=round(bytes_ / med / 1e6, 1),
+    emit(kind="eq", log_n=lg, point=kind, call_ms=round(med, 4), kernel_ms=round(kms, 4), gbs_call=round(bytes_ / med / 1e6, 1),
          gbs_kernel=round(bytes_ / kms / 1e6, 1), frac_kernel=round(bytes_ / kms / 1e6 / PEAK, 3))
 
 with open(OUT / "microbench.jsonl", "w") as f:
