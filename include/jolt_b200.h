@@ -181,6 +181,23 @@ int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars,
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
 
+/* Same with a raw device pointer to n Montgomery scalars (32-byte aligned). */
+int jb_msm_g1_device(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* device_scalars, size_t n,
+                     uint64_t out_xyz[12]);
+
+/* ---- HyperKZG prover side: HyperKZGScheme::open (crates/jolt-hyperkzg/src/scheme.rs:122-158) with
+ *      fold_polynomials (scheme.rs:88-114) and kzg_open_batch (kzg.rs:69-126) on the device. commit is
+ *      jb_msm_g1_table(srs, 0, evals, 2^ell) (kzg.rs:15-27). `point` = ell elements; evals = 2^ell
+ *      entries; the SRS must hold >= 2^ell bases. The transcript stays with the caller:
+ *        challenge_r(user, com, ell-1, r_out)  after the ell-1 intermediate commitments (Jacobian, 12 limbs each)
+ *        challenge_q(user, v, ell, q_out)      after the evaluations v[t][j] = f_j(u_t), u = [r, -r, r^2]
+ *      Outputs: com[(ell-1)][12], w[3][12] (Jacobian representatives), v[3][ell][4]. --------------------- */
+typedef int (*jb_hkzg_challenge_r_fn)(void* user, const uint64_t* com_xyz, size_t ncom, uint64_t r_out[4]);
+typedef int (*jb_hkzg_challenge_q_fn)(void* user, const uint64_t* v, size_t ell, uint64_t q_out[4]);
+int jb_hyperkzg_open(jb_ctx* ctx, jb_srs srs, jb_table evals, const uint64_t* point, size_t ell,
+                     jb_hkzg_challenge_r_fn challenge_r, jb_hkzg_challenge_q_fn challenge_q, void* user,
+                     uint64_t* out_com, uint64_t* out_w, uint64_t* out_v);
+
 /* ---- raw element-wise ops (parity harness for bn254_differential.rs:75-99) -----------------
  * field: 0 = Fr, 1 = Fq; op: 0 add, 1 sub, 2 mul, 3 mul-by-[0,0,lo,hi]. Host buffers. */
 int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

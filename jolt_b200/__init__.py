@@ -15,6 +15,8 @@ from .api import (  # noqa: F401
     BatchMember,
     EqPolynomial,
     G1Bases,
+    HyperKZG,
+    HyperKZGProof,
     Polynomial,
     ProductMember,
     ProvedBatch,

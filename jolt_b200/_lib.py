@@ -70,6 +70,9 @@ SIGNATURES = {
                                              ctypes.POINTER(ctypes.c_double), c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_diag_mul_throughput": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_double)]),
+    "jb_msm_g1_device": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_void_p, c_size_t, c_u64p]),
+    "jb_hyperkzg_open": (ctypes.c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_u64p, c_size_t, c_void_p, c_void_p,
+                                        c_void_p, c_u64p, c_u64p, c_u64p]),
     "jb_vec_op": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_u64p, c_u64p, c_u64p, c_size_t]),
 }
 
@@ -88,6 +91,8 @@ class BatchMemberC(ctypes.Structure):
                 ("rounds", c_size_t), ("offset", c_size_t)]
 
 
+HKZG_R_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_void_p, c_u64p, c_size_t, c_u64p)
+HKZG_Q_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_void_p, c_u64p, c_size_t, c_u64p)
 ABSORB_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_void_p, c_size_t, c_u64p, c_size_t, c_u64p)
 
 _lib = None

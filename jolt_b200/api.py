@@ -522,3 +522,55 @@ def msm(session: Session, bases_xy_limbs: np.ndarray, scalars_limbs: np.ndarray)
         return g.msm(s)
     finally:
         g.free()
+
+
+# ---- HyperKZG prover side ------------------------------------------------------------------------
+@dataclass
+class HyperKZGProof:
+    """jolt_hyperkzg::HyperKZGProof (types.rs): com = ell-1 intermediate commitments, w = 3 witness
+    commitments (12 Jacobian limbs each), v[t][j] = f_j(u_t) as ints."""
+    com: np.ndarray
+    w: np.ndarray
+    v: list[list[int]]
+
+
+class HyperKZG:
+    """HyperKZGScheme prover side (crates/jolt-hyperkzg/src/scheme.rs:275-338) over device-resident
+    SRS powers (`G1Bases`) and polynomials."""
+
+    @staticmethod
+    def commit(bases: G1Bases, poly: Polynomial) -> np.ndarray:
+        """CommitmentScheme::commit -> kzg_commit (kzg.rs:15-27): one MSM over g1_powers[..len]."""
+        return bases.msm(poly)
+
+    @staticmethod
+    def open(bases: G1Bases, poly: Polynomial, point_limbs, challenge_r, challenge_q) -> HyperKZGProof:
+        """HyperKZGScheme::open (scheme.rs:122-158). challenge_r(com (ell-1, 12) limbs) -> r and
+        challenge_q(v [3][ell] ints) -> q stand in for the transcript (ints mod r)."""
+        s = bases.s
+        lib = s.lib
+        pt = np.ascontiguousarray(point_limbs, dtype=np.uint64).reshape(-1, 4)
+        ell = pt.shape[0]
+        com = np.zeros((max(ell - 1, 1), 12), dtype=np.uint64)
+        w = np.zeros((3, 12), dtype=np.uint64)
+        v = np.zeros((3, max(ell, 1), 4), dtype=np.uint64)
+
+        def _r(_user, com_ptr, ncom, out):
+            arr = np.array([com_ptr[i] for i in range(ncom * 12)], dtype=np.uint64).reshape(ncom, 12)
+            limbs = F.to_limbs(challenge_r(arr))
+            for i in range(4):
+                out[i] = int(limbs[i])
+            return 0
+
+        def _q(_user, v_ptr, n_ell, out):
+            vals = [[F.from_limbs([v_ptr[(t * n_ell + j) * 4 + i] for i in range(4)]) for j in range(n_ell)] for t in range(3)]
+            limbs = F.to_limbs(challenge_q(vals))
+            for i in range(4):
+                out[i] = int(limbs[i])
+            return 0
+
+        cb_r, cb_q = _lib.HKZG_R_FN(_r), _lib.HKZG_Q_FN(_q)
+        s.check(lib.jb_hyperkzg_open(s.h, bases.handle, poly.handle, _p(pt) if ell else None, ell,
+                                     ctypes.cast(cb_r, ctypes.c_void_p), ctypes.cast(cb_q, ctypes.c_void_p), None,
+                                     _p(com), _p(w), _p(v)))
+        return HyperKZGProof(com[: max(ell - 1, 0)], w, [F.limbs_to_ints(v[t, :ell]) for t in range(3)])

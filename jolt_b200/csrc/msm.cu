@@ -564,6 +564,20 @@ int jb_msm_g1(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_
     return st;
 }
 
+int jb_msm_g1_device(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
+    if (!c || !out_xyz || (n && !d_scalars)) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    if (offset + n > it->second.n) return c->fail(JB_ERR_LENGTH, "msm: bases/scalars length mismatch");
+    if (n == 0) {
+        identity_xyz(out_xyz);
+        return JB_OK;
+    }
+    if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+    return msm_device(c, it->second.xy + 8 * offset, d_scalars, n, out_xyz);
+}
+
 int jb_msm_g1_table(jb_ctx* c, jb_srs h, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]) {
     if (!c || !out_xyz) return JB_ERR_INVALID;
     Guard g(c);

@@ -362,7 +362,7 @@ __device__ __forceinline__ Fr eq_var(const EqVars& v, int j) {
     return x;
 }
 
-__global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix,  // gridDim.x prefix values (or null: scale)
+static __global__ void __launch_bounds__(256) eq_expand_kernel(const uint64_t* prefix,  // gridDim.x prefix values (or null: scale)
                                                         const __grid_constant__ EqVars ev, int nv, uint64_t* out) {
     __shared__ uint32_t tab[8 * 256];  // word-major: tab[w*256 + idx] (conflict-free)
     const int tid = threadIdx.x;
