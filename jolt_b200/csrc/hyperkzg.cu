@@ -269,8 +269,10 @@ extern "C" {
 int jb_hyperkzg_open(jb_ctx* c, jb_srs srs, jb_table evals, const uint64_t* point, size_t ell,
                      jb_hkzg_challenge_r_fn challenge_r, jb_hkzg_challenge_q_fn challenge_q, void* user,
                      uint64_t* out_com, uint64_t* out_w, uint64_t* out_v) {
-    if (!c || !point || !challenge_r || !challenge_q || !out_w || !out_v || (ell > 1 && !out_com)) return JB_ERR_INVALID;
+    if (!c) return JB_ERR_INVALID;
     if (ell == 0) return c->fail(JB_ERR_INVALID, "HyperKZGError::EmptyPoint");
+    if (!point || !challenge_r || !challenge_q || !out_w || !out_v || (ell > 1 && !out_com))
+        return c->fail(JB_ERR_INVALID, "hyperkzg: null argument");
     if (ell > 33) return c->fail(JB_ERR_UNSUPPORTED, "hyperkzg: ell must be <= 33");
     const size_t n = (size_t)1 << ell;
     const uint64_t* d_evals = nullptr;
