@@ -38,12 +38,7 @@ struct MsmPlan {
     int T;        // segments per window
 };
 
-MsmPlan plan_for(size_t n) {
-    int lg = 0;
-    while (((size_t)1 << (lg + 1)) <= n) ++lg;
-    int c = lg - 4;  // ~ 2^5 points per bucket
-    if (c < 4) c = 4;
-    if (c > 16) c = 16;
+MsmPlan plan_with(int c) {
     MsmPlan p;
     p.c = c;
     p.W = (254 + c - 1) / c;
@@ -51,6 +46,33 @@ MsmPlan plan_for(size_t n) {
     p.B = 1 << (c - 1);
     p.T = (p.B + MSM_SEG - 1) / MSM_SEG;
     return p;
+}
+
+// Window size by a small cost model (in mixed-add equivalents): W*n bucket additions, 2.8 per bucket for
+// the running-sum reduction, and the serial tail of the sparsely populated top window (254 mod c bits):
+// its buckets hold n / 2^(bits-1) points each and are cut into at most 64 chunks, so one thread walks
+// max(64, cnt/64) points while the rest of the machine (~5 G adds/s vs ~7 M adds/s per thread) waits.
+MsmPlan plan_for(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) ++lg;
+    int c0 = lg - 4;  // ~ 2^5 points per bucket
+    double best = 0;
+    int best_c = 0;
+    for (int c = c0 - 2; c <= c0 + 2; ++c) {
+        if (c < 4 || c > 16) continue;
+        MsmPlan p = plan_with(c);
+        int top_bits = 254 - (p.W - 1) * c;
+        if (top_bits < 1) top_bits = 1;
+        double cnt_top = (double)n / (double)((size_t)1 << (top_bits - 1));
+        double chunk = cnt_top / 64.0 < 64.0 ? 64.0 : cnt_top / 64.0;
+        double cost = (double)p.W * (double)n + 2.8 * (double)p.W * (double)p.B + 750.0 * chunk;
+        if (best_c == 0 || cost < best) {
+            best = cost;
+            best_c = c;
+        }
+    }
+    if (best_c == 0) best_c = c0 < 4 ? 4 : 16;
+    return plan_with(best_c);
 }
 
 // ---- 1. digits ----------------------------------------------------------------------------------
