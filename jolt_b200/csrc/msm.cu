@@ -7,7 +7,7 @@
 // Pipeline (all on the context's stream, integer pipes only - there is no dense contraction here):
 //   1. digits     : scalar -> canonical (one Montgomery product) -> signed base-2^c digits
 //                   d_w in [-2^(c-1), 2^(c-1)], + per-(window, bucket) histogram (global REDs)
-//   2. scan       : exclusive prefix of the histogram -> bucket offsets
+//   2. scan       : exclusive prefix of the histogram -> bucket offsets and task offsets (3 small kernels)
 //   3. scatter    : point indices (with the digit's sign) into bucket order (one atomic each)
 //   4. accumulate : one thread per task (a <= max(64, cnt/64)-point chunk of one bucket): XYZZ += +-P
 //                   (mixed add, 8M + 2S) - the hot kernel; split buckets are folded by a combine pass
@@ -125,43 +125,100 @@ __device__ __forceinline__ unsigned chunk_count(unsigned cnt) {
     return cnt ? (cnt + chunk_len(cnt) - 1) / chunk_len(cnt) : 0;
 }
 
-__global__ void __launch_bounds__(1024) msm_scan_kernel(unsigned int* hist, unsigned int* offsets, unsigned int* toff,
-                                                        size_t total) {
-    __shared__ unsigned int sums[1024];
-    __shared__ unsigned int tsums[1024];
-    const size_t per = (total + 1023) / 1024;
-    const size_t lo = (size_t)threadIdx.x * per;
-    const size_t hi = lo + per < total ? lo + per : total;
-    unsigned int s = 0, ts = 0;
-    for (size_t k = lo; k < hi; ++k) {
-        s += hist[k];
-        ts += chunk_count(hist[k]);
+// Three-kernel exclusive scan of (cnt, chunk_count(cnt)) with coalesced access: (a) each block of 1024
+// threads scans 4096 counters (4 per thread, one 128-bit load) and emits its two totals, (b) one block
+// scans the block totals, (c) the block bases are added. The histogram is zeroed on the way (it becomes
+// the scatter cursor).
+constexpr int SCAN_PER_BLOCK = 4096;
+
+__device__ __forceinline__ void block_exclusive_scan2(unsigned int& a, unsigned int& b, unsigned int* sm_a, unsigned int* sm_b,
+                                                      unsigned int& total_a, unsigned int& total_b) {
+    // a, b: per-thread sums in; exclusive prefix over the block's threads out
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int ia = a, ib = b;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned int ta = __shfl_up_sync(0xffffffffu, ia, off), tb = __shfl_up_sync(0xffffffffu, ib, off);
+        if (lane >= off) { ia += ta; ib += tb; }
     }
-    sums[threadIdx.x] = s;
-    tsums[threadIdx.x] = ts;
+    if (lane == 31) { sm_a[warp] = ia; sm_b[warp] = ib; }
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan over the 1024 partials
-        unsigned int v = threadIdx.x >= d ? sums[threadIdx.x - d] : 0;
-        unsigned int tv = threadIdx.x >= d ? tsums[threadIdx.x - d] : 0;
-        __syncthreads();
-        sums[threadIdx.x] += v;
-        tsums[threadIdx.x] += tv;
-        __syncthreads();
+    if (warp == 0) {
+        unsigned int wa = sm_a[lane], wb = sm_b[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned int ta = __shfl_up_sync(0xffffffffu, wa, off), tb = __shfl_up_sync(0xffffffffu, wb, off);
+            if (lane >= off) { wa += ta; wb += tb; }
+        }
+        sm_a[lane] = wa;
+        sm_b[lane] = wb;
     }
-    unsigned int run = threadIdx.x ? sums[threadIdx.x - 1] : 0;
-    unsigned int trun = threadIdx.x ? tsums[threadIdx.x - 1] : 0;
-    for (size_t k = lo; k < hi; ++k) {
-        unsigned int cnt = hist[k];
-        offsets[k] = run;
-        toff[k] = trun;
-        run += cnt;
-        trun += chunk_count(cnt);
-        hist[k] = 0;  // reused as the scatter cursor
+    __syncthreads();
+    total_a = sm_a[31];
+    total_b = sm_b[31];
+    unsigned int base_a = warp ? sm_a[warp - 1] : 0, base_b = warp ? sm_b[warp - 1] : 0;
+    a = base_a + ia - a;  // exclusive
+    b = base_b + ib - b;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) msm_scan_local_kernel(unsigned int* hist, unsigned int* offsets, unsigned int* toff,
+                                                              size_t total, unsigned int* block_sums) {
+    __shared__ unsigned int sm_a[32], sm_b[32];
+    const size_t base = (size_t)blockIdx.x * SCAN_PER_BLOCK + (size_t)threadIdx.x * 4;
+    unsigned int c[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < total) c[k] = hist[base + k];
+    unsigned int q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = chunk_count(c[k]);
+    unsigned int sa = c[0] + c[1] + c[2] + c[3], sb = q[0] + q[1] + q[2] + q[3], ta, tb;
+    block_exclusive_scan2(sa, sb, sm_a, sm_b, ta, tb);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < total) {
+            offsets[base + k] = sa;
+            toff[base + k] = sb;
+            hist[base + k] = 0;
+        }
+        sa += c[k];
+        sb += q[k];
     }
-    if (threadIdx.x == 1023) {
-        offsets[total] = sums[1023];
-        toff[total] = tsums[1023];
+    if (threadIdx.x == 0) {
+        block_sums[2 * blockIdx.x] = ta;
+        block_sums[2 * blockIdx.x + 1] = tb;
     }
+}
+
+// nblocks <= 1024 (total <= 4 Mi counters)
+__global__ void __launch_bounds__(1024) msm_scan_blocks_kernel(unsigned int* block_sums, int nblocks, unsigned int* offsets,
+                                                               unsigned int* toff, size_t total) {
+    __shared__ unsigned int sm_a[32], sm_b[32];
+    unsigned int a = threadIdx.x < nblocks ? block_sums[2 * threadIdx.x] : 0;
+    unsigned int b = threadIdx.x < nblocks ? block_sums[2 * threadIdx.x + 1] : 0;
+    unsigned int ta, tb;
+    block_exclusive_scan2(a, b, sm_a, sm_b, ta, tb);
+    if (threadIdx.x < nblocks) {
+        block_sums[2 * threadIdx.x] = a;
+        block_sums[2 * threadIdx.x + 1] = b;
+    }
+    if (threadIdx.x == 0) {
+        offsets[total] = ta;
+        toff[total] = tb;
+    }
+}
+
+__global__ void __launch_bounds__(1024) msm_scan_apply_kernel(unsigned int* offsets, unsigned int* toff, size_t total,
+                                                              const unsigned int* block_sums) {
+    const unsigned int ba = block_sums[2 * blockIdx.x], bb = block_sums[2 * blockIdx.x + 1];
+    const size_t base = (size_t)blockIdx.x * SCAN_PER_BLOCK + (size_t)threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < total) {
+            offsets[base + k] += ba;
+            toff[base + k] += bb;
+        }
 }
 
 // task -> bucket map (a bucket writes its <= 64 task slots)
@@ -394,13 +451,15 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
     const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
     uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr;
-    unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr;
+    unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr, *block_sums = nullptr;
+    const unsigned scan_blocks = (unsigned)((nb + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);  // <= 136 for c <= 16
     uint64_t *buckets = nullptr, *partial = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
     int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&hist, nb * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&offsets, (nb + 1) * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&toff, (nb + 1) * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&block_sums, 2 * 1024 * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&task_bucket, max_tasks * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&buckets, nb * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&partial, max_tasks * 128);
@@ -411,7 +470,9 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
         msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, digits, hist);
-        msm_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets, toff, nb);
+        msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums);
+        msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
+        msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
         msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, offsets, hist, sorted);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
@@ -422,7 +483,7 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
         msm_segment_kernel<<<(unsigned)(((size_t)p.W * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, p.W, p.B, p.T, seg);
         msm_window_kernel<<<p.W, 256, 0, c->stream>>>(seg, p.T, p.c, win);
         msm_final_kernel<<<1, 32, 0, c->stream>>>(win, p.W, d_out);
-        c->launches += 9;
+        c->launches += 11;
         st = c->check(cudaGetLastError(), "msm kernels");
     }
     if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
@@ -434,6 +495,7 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     c->dev_free(hist);
     c->dev_free(offsets);
     c->dev_free(toff);
+    c->dev_free(block_sums);
     c->dev_free(buckets);
     c->dev_free(partial);
     c->dev_free(seg);
