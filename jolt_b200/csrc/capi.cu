@@ -258,6 +258,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
     if (const char* mb = std::getenv("JB_FUSED_MINB")) c->fused_minb = std::atoi(mb);  // tuning knob (2 or 3)
+    if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
     // keep freed blocks in the pool (ProofSession "device memory pools")
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -494,6 +495,13 @@ struct jb_member {
     bool sharded = false;
     size_t gather_len = 0;
     jb_member* tail = nullptr;
+    // persistent tail kernel (poly_kernels.cuh, tail_rounds_kernel): serves the short rounds from a mailbox
+    bool pt_active = false;
+    TailMailbox* pt_host = nullptr;
+    TailMailbox* pt_dev = nullptr;
+    cudaStream_t pt_stream = nullptr;
+    cudaEvent_t pt_event = nullptr;
+    uint64_t pt_seq = 0;
 };
 
 int jb_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, jb_member** out) {
@@ -613,6 +621,91 @@ static int wait_round_result(jb_ctx* c) {
     return JB_OK;
 }
 
+// ---- persistent tail -----------------------------------------------------------------------------------
+extern "C++" {
+template <int M>
+static void launch_tail(jb_member* mem, const TailTables& tt) {
+    const long long timeout = 20000000000LL;  // ~10 s of SM clocks without a command: give the SM back
+    if (mem->order == JB_HIGH_TO_LOW)
+        tail_rounds_kernel<M, ORDER_HIGH_TO_LOW><<<1, 512, 0, mem->pt_stream>>>(tt, mem->pt_dev, timeout);
+    else
+        tail_rounds_kernel<M, ORDER_LOW_TO_HIGH><<<1, 512, 0, mem->pt_stream>>>(tt, mem->pt_dev, timeout);
+}
+}  // extern "C++"
+
+static int tail_start(jb_member* mem) {
+    jb_ctx* c = mem->ctx;
+    if (!mem->pt_host) {
+        if (cudaHostAlloc((void**)&mem->pt_host, sizeof(TailMailbox), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&mem->pt_dev, mem->pt_host, 0) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&mem->pt_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&mem->pt_event, cudaEventDisableTiming) != cudaSuccess)
+            return c->fail(JB_ERR_OOM, "tail: mailbox / stream allocation failed");
+    }
+    std::memset(mem->pt_host, 0, sizeof(TailMailbox));
+    mem->pt_seq = 0;
+    TailTables tt;
+    std::memset(&tt, 0, sizeof tt);
+    tt.len = mem->len;
+    for (int j = 0; j < mem->m; ++j) {
+        Table& t = mem->tables[j];
+        if (mem->order == JB_LOW_TO_HIGH) {
+            int st = c->ensure_alt(t, mem->len / 2 ? mem->len / 2 : 1);
+            if (st != JB_OK) return st;
+        }
+        tt.buf[j] = t.buf;
+        tt.alt[j] = t.alt;
+    }
+    // the tail kernel starts after everything already queued on the context's stream
+    cudaEventRecord(mem->pt_event, c->stream);
+    cudaStreamWaitEvent(mem->pt_stream, mem->pt_event, 0);
+    switch (mem->m) {
+        case 1: launch_tail<1>(mem, tt); break;
+        case 2: launch_tail<2>(mem, tt); break;
+        case 3: launch_tail<3>(mem, tt); break;
+        default: launch_tail<4>(mem, tt); break;
+    }
+    c->launches++;
+    int st = c->check(cudaGetLastError(), "tail_rounds_kernel launch");
+    if (st == JB_OK) mem->pt_active = true;
+    return st;
+}
+
+// Posts one command and spins until the kernel has answered it.
+static int tail_post(jb_member* mem, uint64_t cmd, const uint64_t* challenge, bool skip1) {
+    jb_ctx* c = mem->ctx;
+    TailMailbox* mb = mem->pt_host;
+    mb->cmd = cmd | ((uint64_t)(skip1 ? 1 : 0) << 8);
+    if (challenge) std::memcpy((void*)mb->challenge, challenge, 32);
+    const uint64_t seq = ++mem->pt_seq;
+    __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
+    uint64_t spins = 0;
+    while (__atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+        if ((++spins & 0x3fffff) == 0) {
+            cudaError_t e = cudaStreamQuery(mem->pt_stream);
+            if (e != cudaErrorNotReady && __atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+                mem->pt_active = false;
+                return c->check(e == cudaSuccess ? cudaErrorUnknown : e, "tail kernel exited without answering");
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (mb->status != 0) {
+        mem->pt_active = false;
+        return c->fail(JB_ERR_CUDA, "tail kernel aborted (timeout)");
+    }
+    return JB_OK;
+}
+
+// The kernel has exited (final bind or abort): later work on the context's stream waits for it.
+static void tail_finish(jb_member* mem) {
+    cudaEventRecord(mem->pt_event, mem->pt_stream);
+    cudaStreamWaitEvent(mem->ctx->stream, mem->pt_event, 0);
+    mem->pt_active = false;
+}
+
 static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
                                uint64_t* out_evals);
 
@@ -668,7 +761,22 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
     // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
     const bool skip1 = claim != nullptr && !c->verify_rounds;
-    int st = member_round(mem, bind, skip1, nullptr);
+    int st;
+    if (c->use_tail && mem->len <= TAIL_MAX_LEN && mem->len >= (bind ? 4u : 2u)) {
+        // latency path: the persistent tail kernel serves this and every later round of the member
+        if (bind && !canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
+        if (!mem->pt_active && (st = tail_start(mem)) != JB_OK) return st;
+        st = tail_post(mem, bind ? TAIL_CMD_BIND_ROUND : TAIL_CMD_EVAL_ROUND, bind, skip1);
+        if (st != JB_OK) return st;
+        if (bind) {
+            mem->len /= 2;
+            for (auto& t : mem->tables) t.len = mem->len;
+        }
+        st = assemble_evals(c, mem->m, skip1, (const uint64_t*)mem->pt_host->result, claim, round, out_evals);
+        if (st == JB_OK) mem->rounds_done++;
+        return st;
+    }
+    st = member_round(mem, bind, skip1, nullptr);
     if (st != JB_OK) return st;
     st = wait_round_result(c);
     if (st != JB_OK) return st;
@@ -842,6 +950,15 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     }
     Guard g(c);
     if (mem->len < 2) return c->fail(JB_ERR_INVALID, "finish_rounds: member already fully bound");
+    if (mem->pt_active) {
+        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
+        int st = tail_post(mem, TAIL_CMD_FINAL_BIND, bind, false);
+        tail_finish(mem);
+        if (st != JB_OK) return st;
+        mem->len /= 2;
+        for (auto& t : mem->tables) t.len = mem->len;
+        return JB_OK;
+    }
     for (int j = 0; j < mem->m; ++j) {
         int st = bind_table(c, mem->tables[j], bind, mem->order);
         if (st != JB_OK) return st;
@@ -879,6 +996,17 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out) {
 void jb_member_destroy(jb_member* mem) {
     if (!mem) return;
     if (mem->tail) jb_member_destroy(mem->tail);
+    if (mem->pt_active) {
+        Guard g(mem->ctx);
+        tail_post(mem, TAIL_CMD_ABORT, nullptr, false);
+        tail_finish(mem);
+    }
+    if (mem->pt_stream) {
+        cudaStreamSynchronize(mem->pt_stream);
+        cudaStreamDestroy(mem->pt_stream);
+    }
+    if (mem->pt_event) cudaEventDestroy(mem->pt_event);
+    if (mem->pt_host) cudaFreeHost(mem->pt_host);
     {
         Guard g(mem->ctx);
         for (auto& t : mem->tables) mem->ctx->release(t);

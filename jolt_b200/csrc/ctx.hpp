@@ -58,6 +58,7 @@ struct jb_ctx {
     uint64_t launches = 0;
     uint64_t* d_partial = nullptr;  // per-block partial sums of the running fused pass
     size_t partial_cap = 0;         // in elements
+    bool use_tail = true;           // persistent tail kernel for short rounds
     int fused_minb = 2;             // min resident blocks/SM requested for the m <= 2 fused kernels
     bool verify_rounds = false;     // compute s(1) and check s(0)+s(1)==claim instead of deriving s(1)
     uint64_t* d_small = nullptr;    // device staging
