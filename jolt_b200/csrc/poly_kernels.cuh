@@ -347,13 +347,18 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
 // the K round values and raises `res_seq`. The Fiat-Shamir round trip becomes two PCIe hops and a few
 // microseconds of arithmetic. One block, 512 threads, its own stream (other members' launches are not
 // queued behind it). Values are identical to the streaming kernel's (same evaluation set, exact sums).
-struct TailMailbox {
-    volatile uint64_t cmd_seq;   // host -> device: sequence number of the posted command
+struct alignas(64) TailMailbox {
+    // line 0 (64 B), host -> device. The host writes cmd/challenge first and cmd_seq last; the device
+    // reads the whole line with ONE coalesced 64-byte request (a single PCIe read, a coherent snapshot
+    // of the cache line), so a snapshot that shows the new sequence number also shows its payload.
+    volatile uint64_t cmd_seq;   // sequence number of the posted command
     uint64_t cmd;                // TAIL_CMD_* | (skip1 << 8)
     uint64_t challenge[4];       // Montgomery limbs of the bind scalar
     uint64_t pad0[2];
-    volatile uint64_t res_seq;   // device -> host: sequence number of the completed command
+    // line 1.., device -> host
+    volatile uint64_t res_seq;   // sequence number of the completed command
     uint64_t status;             // 0 ok, 1 timeout/abort
+    uint64_t pad1[6];
     uint64_t result[8 * 4];      // K canonical elements
 };
 enum : uint64_t { TAIL_CMD_BIND_ROUND = 1, TAIL_CMD_EVAL_ROUND = 2, TAIL_CMD_FINAL_BIND = 3, TAIL_CMD_ABORT = 4 };
@@ -381,25 +386,27 @@ __global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMai
     size_t len = tt.len;
     uint64_t seq = 0;
     while (true) {
-        if (tid == 0) {
+        if (tid < 32) {  // warp 0 polls the command line
             const long long t0 = clock64();
-            uint64_t cmd = TAIL_CMD_ABORT;
+            const volatile uint64_t* line = reinterpret_cast<const volatile uint64_t*>(mb);
+            uint64_t v = 0;
+            bool got = false;
             while (true) {
-                if (mb->cmd_seq == seq + 1) {
-                    __threadfence_system();
-                    cmd = *(volatile uint64_t*)&mb->cmd;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        uint64_t v = *(volatile uint64_t*)&mb->challenge[w];
-                        s_ch[2 * w] = (uint32_t)v;
-                        s_ch[2 * w + 1] = (uint32_t)(v >> 32);
-                    }
+                if (tid < 8) v = line[tid];
+                const uint64_t sq = __shfl_sync(0xffffffffu, v, 0);
+                if (sq == seq + 1) {
+                    got = true;
                     break;
                 }
-                if (clock64() - t0 > timeout_cycles) break;  // host went away: give the SM back
-                __nanosleep(64);
+                const int expired = __shfl_sync(0xffffffffu, (int)(clock64() - t0 > timeout_cycles), 0);
+                if (expired) break;  // host went away: give the SM back
+                __nanosleep(32);
             }
-            s_cmd = cmd;
+            if (tid == 1) s_cmd = got ? v : (uint64_t)TAIL_CMD_ABORT;
+            if (got && tid >= 2 && tid < 6) {
+                s_ch[2 * (tid - 2)] = (uint32_t)v;
+                s_ch[2 * (tid - 2) + 1] = (uint32_t)(v >> 32);
+            }
         }
         __syncthreads();
         ++seq;
@@ -416,6 +423,12 @@ __global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMai
         Fr sv;
 #pragma unroll
         for (int i = 0; i < 8; ++i) sv.v[i] = s_ch[i];
+        const bool hi4 = (sv.v[0] | sv.v[1] | sv.v[2] | sv.v[3]) == 0;  // 125-bit challenge [0,0,lo,hi]: 4-row product
+        auto bind1 = [&](const Fr& lo_, const Fr& hi_) {
+            Fr d = fp_sub_lazy(hi_, lo_);
+            Fr m = hi4 ? fp_mul_hi4(d, sv.v + 4) : fp_mul(d, sv);
+            return fp_add(lo_, m);
+        };
         if (cmd == TAIL_CMD_FINAL_BIND) {
             const size_t half = len / 2;
             for (size_t i = tid; i < half; i += blockDim.x) {
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMai
                 for (int j = 0; j < M; ++j) {
                     Fr lo = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? i : 2 * i);
                     Fr hi = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? i + half : 2 * i + 1);
-                    Fr out = fp_add(lo, fp_mul(fp_sub(hi, lo), sv));
+                    Fr out = bind1(lo, hi);
                     st_elem(ORDER == ORDER_HIGH_TO_LOW ? cur[j] : oth[j], i, out);
                 }
             }
@@ -463,15 +476,15 @@ __global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMai
                     if (ORDER == ORDER_HIGH_TO_LOW) {
                         Fr a = ld_elem_rw<Fr>(cur[j], y), c = ld_elem_rw<Fr>(cur[j], y + 2 * pairs);
                         Fr b = ld_elem_rw<Fr>(cur[j], y + pairs), d = ld_elem_rw<Fr>(cur[j], y + 3 * pairs);
-                        lo[j] = fp_add(a, fp_mul(fp_sub(c, a), sv));
-                        hi[j] = fp_add(b, fp_mul(fp_sub(d, b), sv));
+                        lo[j] = bind1(a, c);
+                        hi[j] = bind1(b, d);
                         st_elem(cur[j], y, lo[j]);
                         st_elem(cur[j], y + pairs, hi[j]);
                     } else {
                         Fr a = ld_elem_rw<Fr>(cur[j], 4 * y), b = ld_elem_rw<Fr>(cur[j], 4 * y + 1);
                         Fr c = ld_elem_rw<Fr>(cur[j], 4 * y + 2), d = ld_elem_rw<Fr>(cur[j], 4 * y + 3);
-                        lo[j] = fp_add(a, fp_mul(fp_sub(b, a), sv));
-                        hi[j] = fp_add(c, fp_mul(fp_sub(d, c), sv));
+                        lo[j] = bind1(a, b);
+                        hi[j] = bind1(c, d);
                         st_elem(oth[j], 2 * y, lo[j]);
                         st_elem(oth[j], 2 * y + 1, hi[j]);
                     }
