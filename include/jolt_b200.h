@@ -206,6 +206,8 @@ int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t*
  * timing): when enabled, launches of the streaming kernels over >= min_items items are bracketed
  * by CUDA events on the context's stream. collect() synchronises and drains them.
  * kind: 0 fused bind+eval, 1 bind, 2 eval-only, 3 eq, 4 msm bucket accumulation. */
+/* out[0] = ns the host spent waiting for round results since the last call, out[1] = number of waits. */
+int jb_ctx_diag(jb_ctx* ctx, double out[4]);
 int jb_ctx_timing_enable(jb_ctx* ctx, int on, uint64_t min_items);
 int jb_ctx_timing_collect(jb_ctx* ctx, int* kinds, uint64_t* items, int* m, double* ms, size_t cap, size_t* count);
 

@@ -294,10 +294,10 @@ class ProductMember:
     def finish_rounds(self, bind) -> None:
         self.s.check(self.s.lib.jb_member_finish_rounds(self.h, _p(_limbs(bind))))
 
-    def final_evals(self) -> list[int]:
+    def final_evals(self, raw: bool = False):
         out = np.empty((self.m, 4), dtype=np.uint64)
         self.s.check(self.s.lib.jb_member_final_evals(self.h, _p(out)))
-        return F.limbs_to_ints(out)
+        return out if raw else F.limbs_to_ints(out)
 
     def close(self):
         if self.h:
@@ -386,7 +386,7 @@ def prove_batch(members_desc: list[BatchMember], members: list, max_num_vars: in
 
 def prove_batch_native(members_desc: list[BatchMember], members: list[ProductMember], max_num_vars: int,
                        max_degree: int, claimed_sum: int, absorb_round=None, seed: int = 0,
-                       check_member_rounds: bool = True) -> ProvedBatch:
+                       check_member_rounds: bool = True, raw: bool = False):
     """The same engine run by the C++ host layer (jolt_b200/csrc/sumcheck_host.cu) in one ABI call:
     no Python in the round loop. absorb_round=None uses the built-in SplitMix stand-in transcript
     (jb_absorb_round_splitmix125, seeded with `seed`)."""
@@ -428,6 +428,8 @@ def prove_batch_native(members_desc: list[BatchMember], members: list[ProductMem
         if st == _lib.JB_ERR_ROUND_CHECK:
             raise SumcheckError("RoundCheckFailed: " + detail)
         raise JoltB200Error(st, detail)
+    if raw:  # the limb arrays as the ABI returned them (no big-int conversion on the caller's critical path)
+        return ch, fin, mc, rp
     polys = [UnivariatePoly(F.limbs_to_ints(rp[r, : lens[r]])) for r in range(max_num_vars)]
     return ProvedBatch(F.limbs_to_ints(ch), F.from_limbs(fin), F.limbs_to_ints(mc), polys)
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -20,12 +21,18 @@
 
 using namespace jb;
 
+static inline uint64_t now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
 namespace {
 
 struct Guard {
     jb_ctx* c;
     std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* ctx) : c(ctx), lk(ctx->mu) { cudaSetDevice(ctx->device); }
+    explicit Guard(jb_ctx* ctx) : c(ctx), lk(ctx->mu) { ctx->make_current(); }
 };
 
 BindScalar make_scalar(const uint64_t r[4], bool* hi4) {
@@ -292,6 +299,12 @@ void jb_ctx_destroy(jb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& kv : c->tables) c->release(kv.second);
     c->tables.clear();
+    for (auto& r : c->tail_pool) {
+        if (r.stream) { cudaStreamSynchronize(r.stream); cudaStreamDestroy(r.stream); }
+        if (r.event) cudaEventDestroy(r.event);
+        if (r.mb_host) cudaFreeHost(r.mb_host);
+    }
+    c->tail_pool.clear();
     for (auto& kv : c->srs) {
         if (kv.second.xy) cudaFree(kv.second.xy);
     }
@@ -316,6 +329,16 @@ int jb_ctx_synchronize(jb_ctx* c) {
 }
 
 uint64_t jb_ctx_launch_count(jb_ctx* c) { return c ? c->launches : 0; }
+
+int jb_ctx_diag(jb_ctx* c, double out[4]) {
+    if (!c || !out) return JB_ERR_INVALID;
+    out[0] = (double)c->diag_wait_ns;
+    out[1] = (double)c->diag_waits;
+    out[2] = out[3] = 0;
+    c->diag_wait_ns = 0;
+    c->diag_waits = 0;
+    return JB_OK;
+}
 
 int jb_ctx_timing_enable(jb_ctx* c, int on, uint64_t min_items) {
     if (!c) return JB_ERR_INVALID;
@@ -497,6 +520,8 @@ struct jb_member {
     jb_member* tail = nullptr;
     // persistent tail kernel (poly_kernels.cuh, tail_rounds_kernel): serves the short rounds from a mailbox
     bool pt_active = false;
+    bool has_final = false;
+    uint64_t final_vals[4 * 4];
     TailMailbox* pt_host = nullptr;
     TailMailbox* pt_dev = nullptr;
     cudaStream_t pt_stream = nullptr;
@@ -604,6 +629,7 @@ static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* 
 
 // Spin until the last block of the round's launch has published `seq` (results are then visible).
 static int wait_round_result(jb_ctx* c) {
+    struct Acc { jb_ctx* c; uint64_t t0; ~Acc() { c->diag_wait_ns += now_ns() - t0; c->diag_waits++; } } acc_{c, now_ns()};
     volatile uint64_t* flag = c->h_result + 64;
     const uint64_t want = c->result_seq;
     uint64_t spins = 0;
@@ -636,11 +662,20 @@ static void launch_tail(jb_member* mem, const TailTables& tt) {
 static int tail_start(jb_member* mem) {
     jb_ctx* c = mem->ctx;
     if (!mem->pt_host) {
-        if (cudaHostAlloc((void**)&mem->pt_host, sizeof(TailMailbox), cudaHostAllocMapped) != cudaSuccess ||
-            cudaHostGetDevicePointer((void**)&mem->pt_dev, mem->pt_host, 0) != cudaSuccess ||
-            cudaStreamCreateWithFlags(&mem->pt_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&mem->pt_event, cudaEventDisableTiming) != cudaSuccess)
+        TailRes r;
+        if (!c->tail_pool.empty()) {
+            r = c->tail_pool.back();
+            c->tail_pool.pop_back();
+        } else if (cudaHostAlloc(&r.mb_host, sizeof(TailMailbox), cudaHostAllocMapped) != cudaSuccess ||
+                   cudaHostGetDevicePointer(&r.mb_dev, r.mb_host, 0) != cudaSuccess ||
+                   cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                   cudaEventCreateWithFlags(&r.event, cudaEventDisableTiming) != cudaSuccess) {
             return c->fail(JB_ERR_OOM, "tail: mailbox / stream allocation failed");
+        }
+        mem->pt_host = (TailMailbox*)r.mb_host;
+        mem->pt_dev = (TailMailbox*)r.mb_dev;
+        mem->pt_stream = r.stream;
+        mem->pt_event = r.event;
     }
     std::memset(mem->pt_host, 0, sizeof(TailMailbox));
     mem->pt_seq = 0;
@@ -674,6 +709,8 @@ static int tail_start(jb_member* mem) {
 // Posts one command and spins until the kernel has answered it.
 static int tail_post(jb_member* mem, uint64_t cmd, const uint64_t* challenge, bool skip1) {
     jb_ctx* c = mem->ctx;
+    const uint64_t t_begin = now_ns();
+    struct Acc { jb_ctx* c; uint64_t t0; ~Acc() { c->diag_wait_ns += now_ns() - t0; c->diag_waits++; } } acc_{c, t_begin};
     TailMailbox* mb = mem->pt_host;
     mb->cmd = cmd | ((uint64_t)(skip1 ? 1 : 0) << 8);
     if (challenge) std::memcpy((void*)mb->challenge, challenge, 32);
@@ -957,6 +994,10 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
         if (st != JB_OK) return st;
         mem->len /= 2;
         for (auto& t : mem->tables) t.len = mem->len;
+        if (mem->len == 1) {  // the kernel also returned the fully bound values: no device read-back later
+            std::memcpy(mem->final_vals, (const void*)mem->pt_host->result, (size_t)mem->m * 32);
+            mem->has_final = true;
+        }
         return JB_OK;
     }
     for (int j = 0; j < mem->m; ++j) {
@@ -975,6 +1016,10 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out) {
         return jb_member_final_evals(mem->tail, out);
     }
     Guard g(c);
+    if (mem->has_final) {
+        std::memcpy(out, mem->final_vals, (size_t)mem->m * 32);
+        return JB_OK;
+    }
     if (mem->len != 1) {
         char buf[96];
         size_t remaining = 0;
@@ -1001,12 +1046,15 @@ void jb_member_destroy(jb_member* mem) {
         tail_post(mem, TAIL_CMD_ABORT, nullptr, false);
         tail_finish(mem);
     }
-    if (mem->pt_stream) {
-        cudaStreamSynchronize(mem->pt_stream);
-        cudaStreamDestroy(mem->pt_stream);
+    if (mem->pt_host) {  // back to the context's pool (the kernel has exited: tail_finish ran)
+        Guard g(mem->ctx);
+        TailRes r;
+        r.mb_host = mem->pt_host;
+        r.mb_dev = mem->pt_dev;
+        r.stream = mem->pt_stream;
+        r.event = mem->pt_event;
+        mem->ctx->tail_pool.push_back(r);
     }
-    if (mem->pt_event) cudaEventDestroy(mem->pt_event);
-    if (mem->pt_host) cudaFreeHost(mem->pt_host);
     {
         Guard g(mem->ctx);
         for (auto& t : mem->tables) mem->ctx->release(t);

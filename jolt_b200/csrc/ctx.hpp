@@ -36,6 +36,15 @@ struct Srs {
 
 struct MsmWorkspace;  // msm.cu
 
+// Host-mapped mailbox + private stream + event for one persistent tail kernel; pooled per context so a
+// member entering its tail pays no allocation (cudaHostAlloc / stream creation cost tens of microseconds).
+struct TailRes {
+    void* mb_host = nullptr;
+    void* mb_dev = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t event = nullptr;
+};
+
 // Optional per-launch CUDA-event timing of the dominant kernels (bench.py's roofline figure is
 // measured live, on this stream, inside the timed region).
 struct TimedLaunch {
@@ -58,6 +67,8 @@ struct jb_ctx {
     uint64_t launches = 0;
     uint64_t* d_partial = nullptr;  // per-block partial sums of the running fused pass
     size_t partial_cap = 0;         // in elements
+    std::vector<TailRes> tail_pool;
+    uint64_t diag_wait_ns = 0, diag_waits = 0;  // host time spent waiting for round results
     bool use_tail = true;           // persistent tail kernel for short rounds
     int fused_minb = 2;             // min resident blocks/SM requested for the m <= 2 fused kernels
     bool verify_rounds = false;     // compute s(1) and check s(0)+s(1)==claim instead of deriving s(1)
@@ -94,6 +105,12 @@ struct jb_ctx {
         if (idx >= 0) cudaEventRecord(timed[idx].e1, stream);
     }
 
+    // cudaSetDevice is not free (a runtime lock + context check per call): skip it when this thread is
+    // already on the context's device - it sits on the per-round latency path.
+    void make_current() {
+        int current = -1;
+        if (cudaGetDevice(&current) != cudaSuccess || current != device) cudaSetDevice(device);
+    }
     int fail(int status, const char* what) {
         err = what;
         return status;

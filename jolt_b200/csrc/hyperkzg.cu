@@ -240,7 +240,7 @@ HornerParams horner_params(const HostFr u[HZ_POINTS], int L) {
 
 struct Guard {
     std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+    explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
 };
 
 // chunk length so that a polynomial of `len` coefficients needs <= 1024 blocks of 256 chunks

@@ -442,7 +442,7 @@ bool canonical_q(const uint64_t* a) {
 
 struct Guard {
     std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* c) : lk(c->mu) { cudaSetDevice(c->device); }
+    explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
 };
 
 int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {

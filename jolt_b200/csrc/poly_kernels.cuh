@@ -455,6 +455,15 @@ __global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMai
             }
             __syncthreads();
             if (tid == 0) {
+                if (half == 1) {  // fully bound: hand the M final values back with the acknowledgement
+#pragma unroll
+                    for (int j = 0; j < M; ++j) {
+                        Fr v = ld_elem_rw<Fr>(tt.buf[j], 0);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            mb->result[j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
+                    }
+                }
                 mb->status = 0;
                 __threadfence_system();
                 mb->res_seq = seq;

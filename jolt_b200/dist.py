@@ -100,12 +100,13 @@ def sharded_claim(sess: Session, polys: list[Polynomial], dist) -> int:
     return (ev[0] + ev[1]) % F.R_MOD
 
 
-def prove_sharded(sess: Session, polys: list[Polynomial], claim: int, seed: int, gather_log: int = GATHER_LOG):
+def prove_sharded(sess: Session, polys: list[Polynomial], claim: int, seed: int, gather_log: int = GATHER_LOG,
+                  raw: bool = False):
     """One index-sharded product sumcheck through the C++ engine (jb_prove_batch): no Python in the
     round loop. Returns (ProvedBatch, final_evals); identical on every rank."""
     mem = ShardedProductMember(sess, polys, gather_log)
     rounds = mem.num_rounds()
-    res = prove_batch_native([BatchMember(claim, 1, rounds, 0)], [mem], rounds, mem.m, claim, seed=seed)
-    fe = mem.final_evals()
+    res = prove_batch_native([BatchMember(claim, 1, rounds, 0)], [mem], rounds, mem.m, claim, seed=seed, raw=raw)
+    fe = mem.final_evals(raw=raw)
     mem.close()
     return res, fe

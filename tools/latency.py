@@ -18,15 +18,21 @@ for lg in (2, 6, 10, 14, 18):
         claim = (ev[0] + ev[1]) % F.R_MOD
         probe.close()
         best = 1e9
+        import ctypes
+        d = (ctypes.c_double * 4)()
         for rep in range(6):
             mem = ProductMember(sess, [p.clone() for p in polys0], order)
             sess.synchronize()
+            sess.lib.jb_ctx_diag(sess.h, d)
             t0 = time.perf_counter()
             jolt_b200.prove_batch_native([BatchMember(claim, 1, lg, 0)], [mem], lg, 2, claim, seed=3)
             dt = time.perf_counter() - t0
-            best = min(best, dt)
+            sess.lib.jb_ctx_diag(sess.h, d)
+            if dt < best:
+                best, wait_us, waits = dt, d[0] / 1e3, d[1]
             mem.close()
-        print(f"log_n={lg} order={order} total={best*1e6:.1f}us per_round={best*1e6/lg:.1f}us", flush=True)
+        print(f"log_n={lg} order={order} total={best*1e6:.1f}us per_round={best*1e6/lg:.1f}us "
+              f"device_wait={wait_us:.1f}us over {waits:.0f} waits ({wait_us/max(waits,1):.1f}us each)", flush=True)
     for p in polys0:
         p.free()
 # raw single round at tiny size through ctypes
