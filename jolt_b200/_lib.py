@@ -60,6 +60,7 @@ SIGNATURES = {
     "jb_srs_upload_affine": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p]),
     "jb_srs_upload_jacobian": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p]),
     "jb_srs_generate_multiples": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p]),
+    "jb_srs_precompute": (ctypes.c_int, [c_void_p, ctypes.c_uint64, ctypes.c_int]),
     "jb_srs_len": (ctypes.c_int, [c_void_p, ctypes.c_uint64, ctypes.POINTER(c_size_t)]),
     "jb_srs_download_affine": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_u64p, c_size_t]),
     "jb_srs_free": (ctypes.c_int, [c_void_p, ctypes.c_uint64]),

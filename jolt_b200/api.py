@@ -485,6 +485,12 @@ class G1Bases:
         session.check(session.lib.jb_srs_generate_multiples(session.h, _p(b), n, ctypes.byref(h)))
         return cls(session, h.value, n)
 
+    def precompute(self, window_bits: int = 0) -> "G1Bases":
+        """Builds the 2^(c w) * P_i table for a fixed SRS (jb_srs_precompute): later large MSMs over this
+        handle share one bucket set across windows. Same group values."""
+        self.s.check(self.s.lib.jb_srs_precompute(self.s.h, self.handle, window_bits))
+        return self
+
     def __len__(self):
         n = ctypes.c_size_t()
         self.s.check(self.s.lib.jb_srs_len(self.s.h, self.handle, ctypes.byref(n)))

@@ -306,7 +306,8 @@ void jb_ctx_destroy(jb_ctx* c) {
     }
     c->tail_pool.clear();
     for (auto& kv : c->srs) {
-        if (kv.second.xy) cudaFree(kv.second.xy);
+        if (kv.second.xy) cudaFreeAsync(kv.second.xy, c->stream);
+        if (kv.second.pre) cudaFreeAsync(kv.second.pre, c->stream);
     }
     c->srs.clear();
     c->msm_release();

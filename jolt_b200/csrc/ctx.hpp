@@ -32,6 +32,9 @@ struct Table {
 struct Srs {
     uint64_t* xy = nullptr;  // n affine points, 8 limbs each (x, y), identity = all zero
     size_t n = 0;
+    // optional: rows w = 0..pre_W-1 of 2^(pre_c * w) * P_i (affine), row stride n points (jb_srs_precompute)
+    uint64_t* pre = nullptr;
+    int pre_c = 0, pre_W = 0;
 };
 
 struct MsmWorkspace;  // msm.cu

@@ -48,6 +48,18 @@ MsmPlan plan_with(int c) {
     return p;
 }
 
+// Shared-bucket plan for an SRS with precomputed 2^(c w) P_i: one bucket set for all windows, so the
+// window can be much wider (fewer windows = fewer bucket additions) and the 2^(c w) doubling chains and
+// per-window reductions disappear. c is fixed when the table is built.
+int shared_window_for(size_t srs_len) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= srs_len) ++lg;
+    int c = lg - 2;
+    if (c < 12) c = 12;
+    if (c > 22) c = 22;
+    return c;
+}
+
 // Window size by a small cost model (in mixed-add equivalents): W*n bucket additions, 2.8 per bucket for
 // the running-sum reduction, and the serial tail of the sparsely populated top window (254 mod c bits):
 // its buckets hold n / 2^(bits-1) points each and are cut into at most 64 chunks, so one thread walks
@@ -77,7 +89,7 @@ MsmPlan plan_for(size_t n) {
 
 // ---- 1. digits ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars, const uint64_t* bases, size_t n, int c,
-                                                         int W, int B, uint32_t* digits, unsigned int* hist) {
+                                                         int W, int B, int shared, uint32_t* digits, unsigned int* hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr k = fp_from_mont(ld_elem<Fr>(scalars, i));  // canonical integer limbs
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars
         }
         if (skip) enc = 0;
         digits[(size_t)w * n + i] = enc;
-        if (enc) atomicAdd(&hist[(size_t)w * B + ((enc & 0x7fffffffu) - 1)], 1u);
+        if (enc) atomicAdd(&hist[(shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1)], 1u);
     }
 }
 
@@ -229,17 +241,19 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* toff
 }
 
 // ---- 3. scatter -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B,
-                                                          const unsigned int* offsets, unsigned int* cursor,
+// `shared`: all windows feed one bucket set and the entry addresses the precomputed table row of its
+// window (w * stride + i); otherwise one bucket set per window and the entry is the point index.
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B, int shared,
+                                                          size_t stride, const unsigned int* offsets, unsigned int* cursor,
                                                           uint32_t* sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int w = 0; w < W; ++w) {
         uint32_t enc = digits[(size_t)w * n + i];
         if (!enc) continue;
-        size_t slot = (size_t)w * B + ((enc & 0x7fffffffu) - 1);
+        size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
         unsigned int pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
-        sorted[pos] = (uint32_t)i | (enc & 0x80000000u);
+        sorted[pos] = (uint32_t)(shared ? (size_t)w * stride + i : i) | (enc & 0x80000000u);
     }
 }
 
@@ -432,6 +446,34 @@ __global__ void __launch_bounds__(128) gen_multiples_kernel(const uint64_t* base
     }
 }
 
+// table[w * n + i] = 2^(c w) * P_i (affine), w < W. One thread per base: c doublings per window in XYZZ,
+// one Fermat inversion per emitted point (one-off SRS work, like the reference's setup).
+__global__ void __launch_bounds__(128) precompute_windows_kernel(const uint64_t* xy, size_t n, int c, int W, uint64_t* table) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq px = ld_elem<Fq>(xy, 2 * i), py = ld_elem<Fq>(xy, 2 * i + 1);
+    st_elem(table, 2 * i, px);
+    st_elem(table, 2 * i + 1, py);
+    const bool inf = px.is_zero() && py.is_zero();
+    XYZZ acc;
+    acc.x = px;
+    acc.y = py;
+    acc.zz = inf ? Fq::zero() : Fq::one();
+    acc.zzz = acc.zz;
+    for (int w = 1; w < W; ++w) {
+        for (int k = 0; k < c; ++k) xyzz_double(acc);
+        Fq x = Fq::zero(), y = Fq::zero();
+        if (!acc.is_inf()) {
+            Fq i3 = fq_inverse(acc.zzz);
+            Fq tz = fp_mul(acc.zz, i3);
+            x = fp_mul(acc.x, fp_sqr(tz));
+            y = fp_mul(acc.y, i3);
+        }
+        st_elem(table, 2 * ((size_t)w * n + i), x);
+        st_elem(table, 2 * ((size_t)w * n + i) + 1, y);
+    }
+}
+
 bool canonical_q(const uint64_t* a) {
     static const uint64_t Q[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL,
                                   0x30644e72e131a029ULL};
@@ -445,14 +487,21 @@ struct Guard {
     explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
 };
 
-int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
-    const MsmPlan p = plan_for(n);
-    const size_t nb = (size_t)p.W * p.B;
+// `srs`: the resident bases; terms are bases[offset .. offset + n).
+int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
+    // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
+    // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
+    const bool shared = srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
+    const MsmPlan p = shared ? plan_with(srs.pre_c) : plan_for(n);
+    const uint64_t* d_bases = srs.xy + 8 * offset;                          // digits: identity test, per-window path: gather
+    const uint64_t* d_gather = shared ? srs.pre + 8 * offset : d_bases;     // accumulate: row w starts at w * srs.n
+    const int Weff = shared ? 1 : p.W;  // bucket sets
+    const size_t nb = (size_t)Weff * p.B;
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
     const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
     uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr;
     unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr, *block_sums = nullptr;
-    const unsigned scan_blocks = (unsigned)((nb + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);  // <= 136 for c <= 16
+    const unsigned scan_blocks = (unsigned)((nb + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);  // <= 512 (c <= 22)
     uint64_t *buckets = nullptr, *partial = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
     int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
@@ -463,26 +512,26 @@ int msm_device(jb_ctx* c, const uint64_t* d_bases, const uint64_t* d_scalars, si
     if (st == JB_OK) st = c->dev_alloc((void**)&task_bucket, max_tasks * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&buckets, nb * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&partial, max_tasks * 128);
-    if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)p.W * p.T * 128);
-    if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)p.W * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)Weff * p.T * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)Weff * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
     if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
-        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, digits, hist);
+        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
-        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, offsets, hist, sorted);
+        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, srs.n, offsets, hist, sorted);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
-        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_bases, sorted, offsets, toff,
+        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
                                                                                       task_bucket, nb, buckets, partial);
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
-        msm_segment_kernel<<<(unsigned)(((size_t)p.W * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, p.W, p.B, p.T, seg);
-        msm_window_kernel<<<p.W, 256, 0, c->stream>>>(seg, p.T, p.c, win);
-        msm_final_kernel<<<1, 32, 0, c->stream>>>(win, p.W, d_out);
+        msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, seg);
+        msm_window_kernel<<<Weff, 256, 0, c->stream>>>(seg, p.T, p.c, win);  // block w doubles c*w times: none when shared
+        msm_final_kernel<<<1, 32, 0, c->stream>>>(win, Weff, d_out);
         c->launches += 11;
         st = c->check(cudaGetLastError(), "msm kernels");
     }
@@ -598,6 +647,34 @@ int jb_srs_generate_multiples(jb_ctx* c, const uint64_t base_xy[8], size_t n, jb
     return JB_OK;
 }
 
+int jb_srs_precompute(jb_ctx* c, jb_srs h, int window_bits) {
+    if (!c) return JB_ERR_INVALID;
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    Srs& s = it->second;
+    if (s.pre) return JB_OK;
+    if (s.n == 0) return c->fail(JB_ERR_INVALID, "srs precompute: empty srs");
+    const int cbits = window_bits > 0 ? window_bits : shared_window_for(s.n);
+    if (cbits < 8 || cbits > 24) return c->fail(JB_ERR_INVALID, "srs precompute: window bits must be in 8..24");
+    const MsmPlan p = plan_with(cbits);
+    if ((size_t)p.W * s.n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "srs precompute: windows * bases must be < 2^31");
+    int st = c->dev_alloc((void**)&s.pre, (size_t)p.W * s.n * 64);
+    if (st != JB_OK) return st;  // JB_ERR_OOM: the caller keeps the plain per-window path
+    precompute_windows_kernel<<<(unsigned)((s.n + 127) / 128), 128, 0, c->stream>>>(s.xy, s.n, p.c, p.W, s.pre);
+    c->launches++;
+    st = c->check(cudaGetLastError(), "precompute_windows launch");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "precompute sync");
+    if (st != JB_OK) {
+        c->dev_free(s.pre);
+        s.pre = nullptr;
+        return st;
+    }
+    s.pre_c = p.c;
+    s.pre_W = p.W;
+    return JB_OK;
+}
+
 int jb_srs_len(jb_ctx* c, jb_srs h, size_t* n) {
     if (!c || !n) return JB_ERR_INVALID;
     Guard g(c);
@@ -624,6 +701,7 @@ int jb_srs_free(jb_ctx* c, jb_srs h) {
     auto it = c->srs.find(h);
     if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
     c->dev_free(it->second.xy);
+    if (it->second.pre) c->dev_free(it->second.pre);
     c->srs.erase(it);
     return JB_OK;
 }
@@ -643,7 +721,7 @@ int jb_msm_g1(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_
     int st = c->dev_alloc((void**)&d_s, n * 32);
     if (st != JB_OK) return st;
     st = c->check(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, c->stream), "msm scalars H2D");
-    if (st == JB_OK) st = msm_device(c, it->second.xy + 8 * offset, d_s, n, out_xyz);
+    if (st == JB_OK) st = msm_device(c, it->second, offset, d_s, n, out_xyz);
     c->dev_free(d_s);
     return st;
 }
@@ -659,7 +737,7 @@ int jb_msm_g1_device(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* d_scala
         return JB_OK;
     }
     if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
-    return msm_device(c, it->second.xy + 8 * offset, d_scalars, n, out_xyz);
+    return msm_device(c, it->second, offset, d_scalars, n, out_xyz);
 }
 
 int jb_msm_g1_table(jb_ctx* c, jb_srs h, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]) {
@@ -675,7 +753,7 @@ int jb_msm_g1_table(jb_ctx* c, jb_srs h, size_t offset, jb_table scalars, size_t
         return JB_OK;
     }
     if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
-    return msm_device(c, it->second.xy + 8 * offset, t->buf, n, out_xyz);
+    return msm_device(c, it->second, offset, t->buf, n, out_xyz);
 }
 
 }  // extern "C"

@@ -173,3 +173,37 @@ def test_msm_skewed_digits(sess):
     sc = C.ints_to_mont([int(b) for b in bits])
     got = g1_jacobian_to_affine(bases.msm(sc))
     assert got == O.g1_scalar_mul(O.G1_GEN, int(sum(i + 1 for i in range(n) if bits[i])))
+
+
+@pytest.mark.parametrize("window_bits", [0, 10, 13])
+def test_msm_precomputed_windows_same_value(sess, srs_bases, window_bits):
+    """jb_srs_precompute: shared-bucket MSM over 2^(c w) P_i == per-window MSM == oracle."""
+    n = 1 << 14
+    sc = rand_limbs(0x5CA1A2 + 99, n)
+    want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+    plain = G1Bases.from_affine(sess, srs_bases[:n])
+    pre = G1Bases.from_affine(sess, srs_bases[:n]).precompute(window_bits)
+    assert g1_jacobian_to_affine(plain.msm(sc)) == want
+    assert g1_jacobian_to_affine(pre.msm(sc)) == want
+    half = n // 2          # offset window of the SRS, still on the shared path
+    want2 = oracle_affine(*C.g1_msm_pippenger(srs_bases[half:n], sc[:half], 0, C.max_threads()))
+    assert g1_jacobian_to_affine(pre.msm(sc[:half], offset=half)) == want2
+    small = rand_limbs(5, 16)   # a small MSM over the same handle takes the plain path
+    assert g1_jacobian_to_affine(pre.msm(small)) == oracle_affine(*C.g1_msm_naive(srs_bases[:16], small))
+
+
+def test_msm_precomputed_edge_cases(sess):
+    pts = [O.g1_scalar_mul(O.G1_GEN, k) for k in (1, 2, 3, 5, 7, 11, 13, 17)] * 64
+    pts[6] = None
+    sc = ([0, 1, 1, 12345, 12345, O.R_MOD - 1, 999, (1 << 253) + 7] * 64)
+    pts[4] = O.g1_neg(pts[3])
+    bases = G1Bases.from_affine(sess, g1_affine_limbs(pts)).precompute(9)
+    want = O.g1_msm_naive(pts, sc)
+    assert g1_jacobian_to_affine(bases.msm(C.ints_to_mont(sc))) == want
+
+
+def test_msm_precomputed_closed_form_2pow20(sess):
+    n = 1 << 20
+    bases = G1Bases.generate_multiples(sess, G, n).precompute()
+    sc = rand_limbs(0x5CA1A2, n)
+    assert g1_jacobian_to_affine(bases.msm(sc)) == O.g1_scalar_mul(O.G1_GEN, _weighted_sum(sc))

@@ -21,6 +21,11 @@ for lg in sizes:
     t0 = time.perf_counter()
     bases = G1Bases.generate_multiples(sess, G, n)
     gen_s = time.perf_counter() - t0
+    pre_s = 0.0
+    if "--pre" in sys.argv:
+        t0 = time.perf_counter()
+        bases.precompute()
+        pre_s = time.perf_counter() - t0
     sc = C.rand_limbs(0x5CA1A2, n)
     tab = Polynomial.new(sess, sc)
     sess.synchronize()
@@ -39,7 +44,7 @@ for lg in sizes:
     bases.msm(sc)                   # host scalars: + H2D of 32 B/term
     e2e = time.perf_counter() - t0
     rec = dict(kind="msm", log_n=lg, ok=bool(ok), ms=round(min(ts) * 1e3, 3), mterms_per_s=round(n / min(ts) / 1e6, 1),
-               accumulate_ms=round(sum(acc) / max(len(acc), 1), 3), e2e_ms=round(e2e * 1e3, 3), srs_generate_s=round(gen_s, 2))
+               accumulate_ms=round(sum(acc) / max(len(acc), 1), 3), e2e_ms=round(e2e * 1e3, 3), srs_generate_s=round(gen_s, 2), precompute_s=round(pre_s, 2))
     if cpu and lg <= 20:
         xy = bases.affine()
         t0 = time.perf_counter()
