@@ -54,10 +54,13 @@ MsmPlan plan_with(int c) {
 int shared_window_for(size_t srs_len) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= srs_len) ++lg;
-    int c = lg - 2;
-    if (c < 12) c = 12;
-    if (c > 22) c = 22;
-    return c;
+    // only windows whose top digit is well populated (254 mod c large): 15 -> 14 bits, 16 -> 14, 17 -> 16,
+    // 20 -> 14, 22 -> 12; a near-empty top window would pile n/4 points into each of four buckets
+    if (lg >= 24) return 22;
+    if (lg >= 20) return 20;
+    if (lg >= 18) return 17;
+    if (lg >= 16) return 16;
+    return 15;
 }
 
 // Window size by a small cost model (in mixed-add equivalents): W*n bucket additions, 2.8 per bucket for
@@ -309,10 +312,10 @@ __global__ void __launch_bounds__(128) msm_segment_kernel(const uint64_t* bucket
         xyzz_add(run, bk);
         xyzz_add(acc, run);
     }
-    // acc = sum (b - lo + 1) B_b ; add lo * run (double-and-add, lo < 2^15)
+    // acc = sum (b - lo + 1) B_b ; add lo * run (double-and-add, lo < 2^23)
     if (lo && !run.is_inf()) {
         XYZZ m = XYZZ::inf();
-        for (int bit = 15; bit >= 0; --bit) {
+        for (int bit = 23; bit >= 0; --bit) {
             xyzz_double(m);
             if ((lo >> bit) & 1) xyzz_add(m, run);
         }
