@@ -275,11 +275,23 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bas
     unsigned int lo = base + j * len;
     unsigned int hi = lo + len < base + cnt ? lo + len : base + cnt;
     XYZZ acc = XYZZ::inf();
+    // The gather is a dependent random 64-byte read per addition: fetch point k+1 while adding point k
+    // (the addresses come from the index list, not from the running sum).
+    uint32_t e_next = 0;
+    Fq nx = Fq::zero(), ny = Fq::zero();
+    if (lo < hi) {
+        e_next = sorted[lo];
+        nx = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu));
+        ny = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu) + 1);
+    }
     for (unsigned int k = lo; k < hi; ++k) {
-        uint32_t e = sorted[k];
-        size_t idx = e & 0x7fffffffu;
-        Fq px = ld_elem<Fq>(bases, 2 * idx);
-        Fq py = ld_elem<Fq>(bases, 2 * idx + 1);
+        const uint32_t e = e_next;
+        const Fq px = nx, py = ny;
+        if (k + 1 < hi) {
+            e_next = sorted[k + 1];
+            nx = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu));
+            ny = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu) + 1);
+        }
         xyzz_add_affine(acc, px, py, (e >> 31) != 0);
     }
     if (toff[b + 1] - toff[b] == 1) st_xyzz(buckets, b, acc);
