@@ -132,12 +132,16 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars
 constexpr unsigned MSM_CHUNK = 64;
 constexpr unsigned MSM_MAX_CHUNKS = 64;
 
-__device__ __forceinline__ unsigned chunk_len(unsigned cnt) {
-    unsigned l = (cnt + MSM_MAX_CHUNKS - 1) / MSM_MAX_CHUNKS;
-    return l < MSM_CHUNK ? MSM_CHUNK : l;
-}
+// q = min(64, ceil(cnt / 64)) chunks of ceil(cnt / q) points: equal-sized chunks keep the lanes of a warp
+// in step (a 96-point bucket is 2 x 48, not 64 + 32).
 __device__ __forceinline__ unsigned chunk_count(unsigned cnt) {
-    return cnt ? (cnt + chunk_len(cnt) - 1) / chunk_len(cnt) : 0;
+    if (!cnt) return 0;
+    unsigned q = (cnt + MSM_CHUNK - 1) / MSM_CHUNK;
+    return q > MSM_MAX_CHUNKS ? MSM_MAX_CHUNKS : q;
+}
+__device__ __forceinline__ unsigned chunk_len(unsigned cnt) {
+    unsigned q = chunk_count(cnt);
+    return q ? (cnt + q - 1) / q : 1;
 }
 
 // Three-kernel exclusive scan of (cnt, chunk_count(cnt)) with coalesced access: (a) each block of 1024
@@ -358,12 +362,15 @@ __device__ __forceinline__ XYZZ smem_get(const uint32_t* sm, int tid) {
     return p;
 }
 
-// ---- 6. per-window sum of the T segment points, then 2^(c w) -----------------------------------------
-__global__ void __launch_bounds__(256) msm_window_kernel(const uint64_t* seg, int T, int c, uint64_t* win_out) {
+// ---- 6. per-window sum of the segment points: a multi-block tree (each block folds 2048 points of one
+//         window into one), repeated until one point per window is left; then the 2^(c w) doublings ----
+// in: [W][count] points, out: [W][gridDim.x] points
+__global__ void __launch_bounds__(256) msm_tree_sum_kernel(const uint64_t* in, int count, uint64_t* out) {
     __shared__ uint32_t sm[32 * 256];
-    const int w = blockIdx.x, tid = threadIdx.x;
+    const int w = blockIdx.y, tid = threadIdx.x;
+    const size_t base = (size_t)w * count;
     XYZZ acc = XYZZ::inf();
-    for (int k = tid; k < T; k += 256) xyzz_add(acc, ld_xyzz(seg, (size_t)w * T + k));
+    for (int k = blockIdx.x * 2048 + tid; k < count && k < (blockIdx.x + 1) * 2048; k += 256) xyzz_add(acc, ld_xyzz(in, base + k));
     smem_put(sm, tid, acc);
     __syncthreads();
     for (int half = 128; half > 0; half >>= 1) {
@@ -374,10 +381,16 @@ __global__ void __launch_bounds__(256) msm_window_kernel(const uint64_t* seg, in
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        for (int k = 0; k < c * w; ++k) xyzz_double(acc);
-        st_xyzz(win_out, w, acc);
-    }
+    if (tid == 0) st_xyzz(out, (size_t)w * gridDim.x + blockIdx.x, acc);
+}
+
+// win[w] *= 2^(c w)   (one thread per window; absent on the shared-bucket path)
+__global__ void __launch_bounds__(32) msm_window_shift_kernel(uint64_t* win, int W, int c) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W || w == 0) return;
+    XYZZ acc = ld_xyzz(win, w);
+    for (int k = 0; k < c * w; ++k) xyzz_double(acc);
+    st_xyzz(win, w, acc);
 }
 
 // ---- 7. final: sum of the W window points -> Jacobian (X Z'^2-scaled): Z = ZZ*ZZZ ------------------------
@@ -518,6 +531,8 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
     unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr, *block_sums = nullptr;
     const unsigned scan_blocks = (unsigned)((nb + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);  // <= 512 (c <= 22)
     uint64_t *buckets = nullptr, *partial = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
+    uint64_t *tree_a = nullptr, *tree_b = nullptr;
+    const size_t tree_pts = (size_t)Weff * ((p.T + 2047) / 2048) + 1;
     int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&hist, nb * 4);
@@ -529,6 +544,8 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
     if (st == JB_OK) st = c->dev_alloc((void**)&partial, max_tasks * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)Weff * p.T * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)Weff * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&tree_a, tree_pts * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&tree_b, tree_pts * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
     if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
     if (st == JB_OK) {
@@ -545,9 +562,26 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
         msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, seg);
-        msm_window_kernel<<<Weff, 256, 0, c->stream>>>(seg, p.T, p.c, win);  // block w doubles c*w times: none when shared
+        {   // tree-sum the T segment points of every bucket set, ping-ponging between two scratch buffers
+            const uint64_t* src = seg;
+            int count = p.T;
+            uint64_t* dst = count > 2048 ? tree_a : win;
+            while (true) {
+                const int blocks = (count + 2047) / 2048;
+                msm_tree_sum_kernel<<<dim3(blocks, Weff), 256, 0, c->stream>>>(src, count, blocks == 1 ? win : dst);
+                c->launches++;
+                if (blocks == 1) break;
+                src = dst;
+                count = blocks;
+                dst = (dst == tree_a) ? tree_b : tree_a;
+            }
+            if (!shared) {
+                msm_window_shift_kernel<<<(Weff + 31) / 32, 32, 0, c->stream>>>(win, Weff, p.c);
+                c->launches++;
+            }
+        }
         msm_final_kernel<<<1, 32, 0, c->stream>>>(win, Weff, d_out);
-        c->launches += 11;
+        c->launches += 10;
         st = c->check(cudaGetLastError(), "msm kernels");
     }
     if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
@@ -564,6 +598,8 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
     c->dev_free(partial);
     c->dev_free(seg);
     c->dev_free(win);
+    c->dev_free(tree_a);
+    c->dev_free(tree_b);
     c->dev_free(d_out);
     return st;
 }
