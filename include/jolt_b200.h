@@ -187,6 +187,10 @@ int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars,
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
 
+/* Multi-GPU MSM: this rank's share of the terms (its own srs handle and host scalars); one
+ * all-gather of the G partial points (96 B each) and a local sum give every rank the same total.
+ * Needs jb_comm_init. */
+int jb_msm_g1_sharded(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
 /* Same with a raw device pointer to n Montgomery scalars (32-byte aligned). */
 int jb_msm_g1_device(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* device_scalars, size_t n,
                      uint64_t out_xyz[12]);

@@ -513,6 +513,13 @@ class G1Bases:
             self.s.check(self.s.lib.jb_msm_g1(self.s.h, self.handle, offset, _p(a) if a.shape[0] else None, a.shape[0], _p(out)))
         return out
 
+    def msm_sharded(self, scalars, offset: int = 0) -> np.ndarray:
+        """This rank's share of a term-partitioned MSM; every rank gets the same total (jb_msm_g1_sharded)."""
+        out = np.zeros(12, dtype=np.uint64)
+        a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+        self.s.check(self.s.lib.jb_msm_g1_sharded(self.s.h, self.handle, offset, _p(a) if a.shape[0] else None, a.shape[0], _p(out)))
+        return out
+
     def free(self):
         if self.handle:
             self.s.check(self.s.lib.jb_srs_free(self.s.h, self.handle))

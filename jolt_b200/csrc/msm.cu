@@ -502,6 +502,45 @@ __global__ void __launch_bounds__(128) precompute_windows_kernel(const uint64_t*
     }
 }
 
+// out = sum of `count` Jacobian points (X, Y, Z; Z == 0 is the identity) -> Jacobian. One warp.
+__global__ void __launch_bounds__(32) jacobian_sum_kernel(const uint64_t* pts, int count, uint64_t* out_xyz) {
+    __shared__ uint32_t sm[32 * 256];
+    const int tid = threadIdx.x;
+    XYZZ acc = XYZZ::inf();
+    for (int k = tid; k < count; k += 32) {
+        Fq X = ld_elem_rw<Fq>(pts, 3 * (size_t)k), Y = ld_elem_rw<Fq>(pts, 3 * (size_t)k + 1), Z = ld_elem_rw<Fq>(pts, 3 * (size_t)k + 2);
+        if (Z.is_zero()) continue;
+        XYZZ p;  // (X, Y, Z) Jacobian == (X, Y, Z^2, Z^3) XYZZ
+        p.x = X;
+        p.y = Y;
+        p.zz = fp_sqr(Z);
+        p.zzz = fp_mul(p.zz, Z);
+        xyzz_add(acc, p);
+    }
+    smem_put(sm, tid, acc);
+    __syncwarp();
+    for (int half = 16; half > 0; half >>= 1) {
+        if (tid < half) {
+            XYZZ o = smem_get(sm, tid + half);
+            xyzz_add(acc, o);
+            smem_put(sm, tid, acc);
+        }
+        __syncwarp();
+    }
+    if (tid == 0) {
+        Fq X = Fq::one(), Y = Fq::one(), Z = Fq::zero();
+        if (!acc.is_inf()) {
+            Fq zzz2 = fp_sqr(acc.zzz), zz2 = fp_sqr(acc.zz);
+            X = fp_mul(fp_mul(acc.x, acc.zz), zzz2);
+            Y = fp_mul(fp_mul(acc.y, fp_mul(zz2, acc.zz)), zzz2);
+            Z = fp_mul(acc.zz, acc.zzz);
+        }
+        st_elem(out_xyz, 0, X);
+        st_elem(out_xyz, 1, Y);
+        st_elem(out_xyz, 2, Z);
+    }
+}
+
 bool canonical_q(const uint64_t* a) {
     static const uint64_t Q[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL,
                                   0x30644e72e131a029ULL};
@@ -789,6 +828,37 @@ int jb_msm_g1_device(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* d_scala
     }
     if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
     return msm_device(c, it->second, offset, d_scalars, n, out_xyz);
+}
+
+// Multi-GPU MSM: the terms are partitioned across ranks (each rank holds its own bases and
+// scalars), every rank runs a full Pippenger on its share, ONE all-gather moves the G partial points
+// (96 B each - EC addition is not an NCCL reduction) and every rank adds them. Same value on all ranks.
+int jb_msm_g1_sharded(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]) {
+    if (!c || !out_xyz) return JB_ERR_INVALID;
+    if (!c->nccl_comm) return c->fail(JB_ERR_INVALID, "sharded msm: no communicator (jb_comm_init)");
+    uint64_t local[12];
+    int st = jb_msm_g1(c, h, offset, scalars, n, local);
+    if (st != JB_OK) return st;
+    Guard g(c);
+    uint64_t *d_mine = nullptr, *d_all = nullptr, *d_out = nullptr;
+    st = c->dev_alloc((void**)&d_mine, 96);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_all, 96 * (size_t)c->world);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
+    std::memcpy(c->h_small, local, 96);
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_mine, c->h_small, 96, cudaMemcpyHostToDevice, c->stream), "sharded msm H2D");
+    if (st == JB_OK) st = c->comm_allgather(d_mine, d_all, 12);
+    if (st == JB_OK) {
+        jacobian_sum_kernel<<<1, 32, 0, c->stream>>>(d_all, c->world, d_out);
+        c->launches++;
+        st = c->check(cudaGetLastError(), "jacobian_sum launch");
+    }
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "sharded msm D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "sharded msm sync");
+    if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
+    c->dev_free(d_mine);
+    c->dev_free(d_all);
+    c->dev_free(d_out);
+    return st;
 }
 
 int jb_msm_g1_table(jb_ctx* c, jb_srs h, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]) {

@@ -34,7 +34,16 @@ def _worker(rank, world, port, log_n_local, m, q):
     polys = [Polynomial.new(sess, s) for s in shard]
     claim = sharded_claim(sess, polys, dist)
     res, fe = prove_sharded(sess, polys, claim, seed=11, gather_log=6)
-    q.put((rank, res.challenges, res.final_claim, fe, [p.coefficients for p in res.round_polynomials]))
+    # term-sharded MSM: rank g holds bases (g*n + i + 1) * G and its slice of the scalars
+    from jolt_b200 import G1Bases, g1_jacobian_to_affine
+    from oracle import bn254 as O
+    G = np.array(O.to_mont_limbs(1, O.Q_MOD) + O.to_mont_limbs(2, O.Q_MOD), dtype=np.uint64)
+    nm = 1 << 12
+    allb = G1Bases.generate_multiples(sess, G, nm * world).affine()
+    mine = G1Bases.from_affine(sess, allb[rank * nm:(rank + 1) * nm])
+    sc = rand_limbs(4242, nm * world)
+    msm_pt = g1_jacobian_to_affine(mine.msm_sharded(sc[rank * nm:(rank + 1) * nm]))
+    q.put((rank, res.challenges, res.final_claim, fe, [p.coefficients for p in res.round_polynomials], msm_pt))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,3 +83,10 @@ def test_sharded_equals_single_gpu(log_n_local, m):
     assert outs[0][1] == one.challenges and outs[0][2] == one.final_claim
     assert outs[0][3] == mem.final_evals()
     assert outs[0][4] == [p.coefficients for p in one.round_polynomials]
+    # sharded MSM == single-GPU MSM over all terms
+    from jolt_b200 import G1Bases, g1_jacobian_to_affine
+    from oracle import bn254 as O
+    G = np.array(O.to_mont_limbs(1, O.Q_MOD) + O.to_mont_limbs(2, O.Q_MOD), dtype=np.uint64)
+    nm = 1 << 12
+    full = G1Bases.generate_multiples(sess, G, nm * world)
+    assert outs[0][5] == g1_jacobian_to_affine(full.msm(rand_limbs(4242, nm * world)))
