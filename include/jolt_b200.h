@@ -129,6 +129,13 @@ void jb_member_destroy(jb_member* mem);
 int jb_comm_unique_id(uint8_t out[128], const char* libnccl_path_or_null);
 int jb_comm_init(jb_ctx* ctx, int nranks, int rank, const uint8_t id[128], const char* libnccl_path_or_null);
 int jb_comm_destroy(jb_ctx* ctx);
+/* Optional, after jb_comm_init: peer-memory exchange buffers (CUDA IPC over NVLink). Each rank exports
+ * the 64-byte handle of its buffer, the caller all-gathers them (rank order) and every rank opens them.
+ * Sharded members then perform the per-round all-reduce INSIDE the round kernel (the finishing thread
+ * stores its lanes into every peer's buffer, waits for the others' and sums) - no NCCL launch per round.
+ * If opening fails the NCCL path remains in force. */
+int jb_comm_p2p_handle(jb_ctx* ctx, uint8_t out[64]);
+int jb_comm_p2p_open(jb_ctx* ctx, const uint8_t* handles_world_x_64);
 /* An index-sharded ProveRounds member: this rank's m tables are the contiguous block `rank` of the
  * global tables (LowToHigh binding keeps every pair local). It reports log2(local len) + log2(nranks)
  * rounds and is driven by the same jb_member_prove_round / jb_prove_batch as a local member: each early

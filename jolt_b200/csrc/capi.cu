@@ -576,6 +576,8 @@ int jb_member_degree(jb_member* mem, size_t* degree) {
 
 // Runs the fused pass; on return d_small[0..m] holds the m+1 sums (canonical) or, if lanes_out,
 // lanes_out holds them widened to one 32-bit limb per u64.
+static void* const JB_LANES_EXCHANGE = (void*)(uintptr_t)1;  // sentinel: all-reduce in the kernel epilogue
+
 static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* lanes_out) {
     jb_ctx* c = mem->ctx;
     bool do_bind = bind != nullptr;
@@ -608,8 +610,22 @@ static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* 
     ro.partial = nullptr;  // set by launch_fused
     ro.counter = c->d_counter;
     ro.lanes = lanes_out ? 1 : 0;
+    ro.world = 1;
+    ro.rank = 0;
+    ro.xseq = 0;
+    ro.timeout_cycles = 0;
+    for (int g2 = 0; g2 < 16; ++g2) ro.peer[g2] = nullptr;
     ro.seq = ++c->result_seq;
-    if (lanes_out) {
+    if (lanes_out == JB_LANES_EXCHANGE) {  // fused all-reduce over peer memory, totals (lanes) to the host
+        ro.lanes = 2;
+        ro.result = c->d_result_alias;
+        ro.flag = c->d_result_alias + 64;
+        for (int g2 = 0; g2 < 16; ++g2) ro.peer[g2] = c->xch_peer[g2];
+        ro.world = c->world;
+        ro.rank = c->rank;
+        ro.xseq = ++c->xch_seq;
+        ro.timeout_cycles = 20000000000LL;
+    } else if (lanes_out) {
         ro.result = (uint64_t*)lanes_out;
         ro.flag = nullptr;
     } else {
@@ -861,11 +877,19 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
                 // a sharded round: local fused pass -> lanes -> ONE all-reduce -> publish -> host fold
                 const bool skip1 = claim != nullptr && !c->verify_rounds;
                 const int K = skip1 ? mem->m : mem->m + 1;
-                int st = member_round(mem, bind, skip1, c->d_lanes);
-                if (st == JB_OK) st = c->comm_allreduce_lanes(c->d_lanes, (size_t)K * 8);
-                if (st == JB_OK) st = c->publish_lanes(c->d_lanes, K * 8);
+                int st;
+                if (c->xch_ready) {
+                    // the all-reduce rides in the round kernel's epilogue over NVLink peer memory
+                    st = member_round(mem, bind, skip1, JB_LANES_EXCHANGE);
+                } else {
+                    st = member_round(mem, bind, skip1, c->d_lanes);
+                    if (st == JB_OK) st = c->comm_allreduce_lanes(c->d_lanes, (size_t)K * 8);
+                    if (st == JB_OK) st = c->publish_lanes(c->d_lanes, K * 8);
+                }
                 if (st == JB_OK) st = wait_round_result(c);
                 if (st != JB_OK) return st;
+                if (c->h_result[0] == ~0ull && c->h_result[1] == ~0ull)
+                    return c->fail(JB_ERR_CUDA, "peer exchange timed out (a rank did not arrive)");
                 uint64_t vals[JB_MAX_EVALS * 4];
                 st = jb_lanes_reduce_host(c->h_result, (size_t)K, vals);
                 if (st != JB_OK) return st;

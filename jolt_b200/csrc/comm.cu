@@ -131,6 +131,52 @@ int jb_comm_init(jb_ctx* c, int nranks, int rank, const uint8_t id_bytes[128], c
     return JB_OK;
 }
 
+// ---- peer-memory exchange buffers (CUDA IPC): the handle of this rank's buffer goes out through the
+// caller's rendezvous, the peers' handles come back and are opened here.
+int jb_comm_p2p_handle(jb_ctx* c, uint8_t out[64]) {
+    if (!c || !out) return JB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!c->xch_peer[c->rank]) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, 65536) != cudaSuccess) return c->fail(JB_ERR_OOM, "p2p: exchange buffer");
+        cudaMemset(p, 0, 65536);
+        cudaDeviceSynchronize();
+        c->xch_peer[c->rank] = (uint64_t*)p;
+    }
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, c->xch_peer[c->rank]);
+    if (e != cudaSuccess) return c->check(e, "cudaIpcGetMemHandle");
+    std::memcpy(out, &h, 64);
+    return JB_OK;
+}
+
+int jb_comm_p2p_open(jb_ctx* c, const uint8_t* handles) {
+    if (!c) return JB_ERR_INVALID;
+    if (!handles) {  // NULL: switch the exchange off (the NCCL all-reduce path stays)
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->xch_ready = false;
+        return JB_OK;
+    }
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaSetDevice(c->device);
+    if (c->world > 16) return c->fail(JB_ERR_UNSUPPORTED, "p2p: at most 16 ranks");
+    if (!c->xch_peer[c->rank]) return c->fail(JB_ERR_INVALID, "p2p: call jb_comm_p2p_handle first");
+    for (int g = 0; g < c->world; ++g) {
+        if (g == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * g, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return c->check(e, "cudaIpcOpenMemHandle (peer exchange unavailable; NCCL path stays)");
+        c->xch_peer[g] = (uint64_t*)p;
+    }
+    c->xch_ready = true;
+    c->xch_seq = 0;
+    return JB_OK;
+}
+
 int jb_comm_destroy(jb_ctx* c) {
     if (!c) return JB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -140,6 +186,17 @@ int jb_comm_destroy(jb_ctx* c) {
         const NcclApi* a = nccl_api(nullptr, nullptr);
         if (a) a->CommDestroy((ncclComm_t)c->nccl_comm);
         c->nccl_comm = nullptr;
+    }
+    if (c->xch_ready || c->xch_peer[c->rank]) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        for (int g = 0; g < 16; ++g) {
+            if (!c->xch_peer[g]) continue;
+            if (g == c->rank) cudaFree(c->xch_peer[g]);
+            else cudaIpcCloseMemHandle(c->xch_peer[g]);
+            c->xch_peer[g] = nullptr;
+        }
+        c->xch_ready = false;
     }
     c->world = 1;
     c->rank = 0;

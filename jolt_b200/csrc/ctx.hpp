@@ -87,6 +87,10 @@ struct jb_ctx {
     void* nccl_comm = nullptr;
     int world = 1, rank = 0;
     uint64_t* d_lanes = nullptr;
+    // peer-memory exchange (fused all-reduce in the round kernel's epilogue): every rank's buffer mapped here
+    uint64_t* xch_peer[16] = {nullptr};
+    bool xch_ready = false;
+    uint64_t xch_seq = 0;
     int comm_allreduce_lanes(uint64_t* d_lanes_buf, size_t n_u64);
     int comm_allgather(const uint64_t* d_send, uint64_t* d_recv, size_t n_u64_per_rank);
     int publish_lanes(const uint64_t* d_lanes_buf, int n_u64);

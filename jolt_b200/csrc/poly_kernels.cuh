@@ -114,8 +114,22 @@ struct RoundOut {
     uint64_t* result;     // lanes == 0: K canonical elements (host-mapped); lanes == 1: K*8 u64 device lanes
     volatile uint64_t* flag;  // host-mapped; set to `seq` after the results are visible (may be null)
     uint64_t seq;
-    int lanes;
+    int lanes;            // 0: canonical to `result`; 1: device lanes to `result`; 2: peer exchange (below)
+    // lanes == 2: the all-reduce is done HERE, over NVLink peer memory. The finishing thread stores this
+    // rank's K*8 lanes straight into every peer's exchange buffer (slot [parity][rank]) and raises a
+    // per-source sequence flag there, waits until all `world` sources have landed in its own buffer, sums
+    // them and publishes the totals (as lanes) to the host-mapped `result` + `flag`. No NCCL launch, no
+    // extra kernel: the collective costs one NVLink store/flag round trip inside the round's own launch.
+    // Double buffering by the parity of the exchange sequence number `xseq` makes slot reuse safe: a rank
+    // can only be one exchange ahead of a peer.
+    uint64_t* peer[16];   // exchange buffer of every rank as mapped in THIS process (peer[rank] = own)
+    int world, rank;
+    uint64_t xseq;
+    long long timeout_cycles;
 };
+constexpr int XCH_SLOT_U64 = 64;                 // u64 lanes per (parity, source) slot
+constexpr int XCH_FLAG_BASE = 2 * 16 * XCH_SLOT_U64;  // flags[parity][source] follow the slots
+constexpr size_t XCH_BYTES = (size_t)(XCH_FLAG_BASE + 2 * 16) * 8;
 
 template <class F>
 __device__ __forceinline__ F ld_elem_cg(const uint64_t* base, size_t idx) {
@@ -131,6 +145,44 @@ __device__ __forceinline__ F ld_elem_cg(const uint64_t* base, size_t idx) {
 // Thread 0 of the finishing block: write the K totals, then (host-mapped mode) raise the flag.
 template <int K>
 __device__ __forceinline__ void publish_round(const Fr (&tot)[K], const RoundOut& out) {
+    if (out.lanes == 2) {
+        const int par = (int)(out.xseq & 1);
+        const int slot = (par * 16 + out.rank) * XCH_SLOT_U64;
+        for (int g = 0; g < out.world; ++g) {
+            uint64_t* dst = out.peer[g] + slot;
+#pragma unroll
+            for (int t = 0; t < K; ++t)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) dst[t * 8 + w] = tot[t].v[w];
+        }
+        __threadfence_system();
+        for (int g = 0; g < out.world; ++g)
+            *(volatile uint64_t*)(out.peer[g] + XCH_FLAG_BASE + par * 16 + out.rank) = out.xseq;
+        // wait for every source's lanes of this exchange to land in OUR buffer
+        uint64_t* mine = out.peer[out.rank];
+        const long long t0 = clock64();
+        bool ok = true;
+        for (int src = 0; src < out.world && ok; ++src) {
+            while (*(volatile uint64_t*)(mine + XCH_FLAG_BASE + par * 16 + src) != out.xseq) {
+                if (clock64() - t0 > out.timeout_cycles) {
+                    ok = false;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        for (int i = 0; i < K * 8; ++i) {
+            uint64_t sum = 0;
+            for (int src = 0; src < out.world; ++src)
+                sum += *(volatile uint64_t*)(mine + (par * 16 + src) * XCH_SLOT_U64 + i);
+            out.result[i] = ok ? sum : ~0ull;
+        }
+        if (out.flag) {
+            __threadfence_system();
+            *out.flag = out.seq;
+        }
+        return;
+    }
 #pragma unroll
     for (int t = 0; t < K; ++t) {
         if (out.lanes) {

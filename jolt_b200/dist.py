@@ -53,7 +53,7 @@ def splitmix_challenge(seed: int, poly: UnivariatePoly) -> int:
     return F.from_limbs(out)
 
 
-def init_comm(sess: Session, dist) -> None:
+def init_comm(sess: Session, dist, p2p: bool = True) -> None:
     """Creates the context's NCCL communicator: rank 0 draws the unique id, torch.distributed (the
     rendezvous the launcher already set up) broadcasts it, every rank joins. Per-round collectives are
     then issued by the C++ side directly on the context's stream."""
@@ -69,6 +69,25 @@ def init_comm(sess: Session, dist) -> None:
     host = t.cpu().numpy().tobytes()
     buf = (ctypes.c_uint8 * 128).from_buffer_copy(host)
     sess.check(lib.jb_comm_init(sess.h, dist.get_world_size(), dist.get_rank(), buf, None))
+    if p2p and dist.get_world_size() > 1:
+        # peer-memory exchange (CUDA IPC over NVLink): the per-round all-reduce moves into the round kernel
+        world = dist.get_world_size()
+        mine = (ctypes.c_uint8 * 64)()
+        ok = lib.jb_comm_p2p_handle(sess.h, mine) == _lib.JB_OK
+        hs = torch.zeros((world, 65), dtype=torch.uint8, device="cuda")
+        row = torch.tensor(list(mine) + [1 if ok else 0], dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(hs, row)
+        hs = hs.cpu().numpy()
+        if hs[:, 64].all():
+            flat = np.ascontiguousarray(hs[:, :64]).reshape(-1)
+            arr = (ctypes.c_uint8 * flat.size).from_buffer_copy(flat.tobytes())
+            opened = lib.jb_comm_p2p_open(sess.h, arr) == _lib.JB_OK
+        else:
+            opened = False
+        agree = torch.tensor([1 if opened else 0], device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if not int(agree.item()):  # not available everywhere: every rank falls back to the NCCL all-reduce
+            lib.jb_comm_p2p_open(sess.h, None)
 
 
 class ShardedProductMember(ProductMember):

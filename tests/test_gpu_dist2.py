@@ -13,7 +13,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, log_n_local, m, q):
+def _worker(rank, world, port, log_n_local, m, q, p2p=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch
@@ -30,7 +30,7 @@ def _worker(rank, world, port, log_n_local, m, q):
     n = 1 << log_n_local
     glob = [rand_limbs(900 + j, n * world) for j in range(m)]
     shard = [g[rank * n:(rank + 1) * n] for g in glob]          # contiguous block per rank
-    init_comm(sess, dist)
+    init_comm(sess, dist, p2p=p2p)
     polys = [Polynomial.new(sess, s) for s in shard]
     claim = sharded_claim(sess, polys, dist)
     res, fe = prove_sharded(sess, polys, claim, seed=11, gather_log=6)
@@ -48,8 +48,10 @@ def _worker(rank, world, port, log_n_local, m, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("log_n_local,m", [(10, 2), (9, 3)])
-def test_sharded_equals_single_gpu(log_n_local, m):
+@pytest.mark.parametrize("log_n_local,m,p2p", [(10, 2, True), (9, 3, True), (10, 2, False)])
+def test_sharded_equals_single_gpu(log_n_local, m, p2p):
+    """p2p=True: the per-round all-reduce runs inside the round kernel over NVLink peer memory;
+    p2p=False: ncclAllReduce. Both must reproduce the single-GPU proof exactly."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -62,7 +64,7 @@ def test_sharded_equals_single_gpu(log_n_local, m):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, log_n_local, m, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, log_n_local, m, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=300) for _ in procs])
