@@ -331,6 +331,13 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": len(big),
                 "traffic": None}
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+            tr = json.load(open(ROOT / "profiles" / "r01_final_traffic.json"))
+            if args.log_n == 22 and m == 2 and args.order == "l2h":
+                roof["traffic"] = tr["fused_round_kernel m=2 l2h 2^22"]["traffic"]
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         kernel_ms = sum(t["ms"] for t in timed) / K
         roof["timed_kernels_share_of_step"] = kernel_ms / ms_per_step
 

@@ -266,6 +266,16 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     c->sm_count = prop.multiProcessorCount;
     if (const char* mb = std::getenv("JB_FUSED_MINB")) c->fused_minb = std::atoi(mb);  // tuning knob (2 or 3)
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
+    // A kernel-replaying profiler (ncu) or a serialising tool (compute-sanitizer, nsys CUDA trace) cannot
+    // run a kernel that waits for host commands; under CUDA injection keep one launch per round.
+    {
+        extern char** environ;
+        for (char** e = environ; e && *e; ++e) {
+            if (!std::strncmp(*e, "CUDA_INJECTION64_PATH=", 22) || !std::strncmp(*e, "NV_NSIGHT_INJECTION", 19) ||
+                !std::strncmp(*e, "NV_COMPUTE_PROFILER", 19) || !std::strncmp(*e, "NSYS_PROFILING_SESSION_ID=", 26))
+                c->use_tail = false;
+        }
+    }
     // keep freed blocks in the pool (ProofSession "device memory pools")
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
