@@ -95,18 +95,18 @@ int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
     return st;
 }
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int MINB>
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB>
 int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
-    auto kernel = fused_round_kernel<M, ORDER, BIND, HI4, SKIP1, MINB>;
-    constexpr size_t smem = FusedShape<M, SKIP1>::SMEM_BYTES;
+    auto kernel = fused_round_kernel<M, ORDER, BIND, HI4, SKIP1, BLOCK, MINB>;
+    constexpr size_t smem = FusedShape<M, SKIP1>::smem_bytes(BLOCK);
     static int per_sm = [&] {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK, smem) != cudaSuccess || nb < 1) nb = 1;
         return nb;
     }();
     // grid-stride over whole waves of resident blocks; tiny rounds take one (small) block
-    size_t need = (pairs + 255) / 256;
+    size_t need = (pairs + BLOCK - 1) / BLOCK;
     size_t resident = (size_t)c->sm_count * per_sm;
     size_t grid = need < resident ? need : resident;
     if (grid < 1) grid = 1;
@@ -116,7 +116,7 @@ int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScal
     out.partial = c->d_partial;
     int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
     // latency path: a round of <= 32 pairs runs as one warp (no barriers, no shared-memory stage)
-    const unsigned block = pairs <= 32 ? 32u : 256u;
+    const unsigned block = pairs <= 32 ? 32u : (unsigned)BLOCK;
     kernel<<<(unsigned)grid, block, smem, c->stream>>>(tp, pairs, s, out);
     c->timing_end(tix);
     c->launches++;
@@ -125,13 +125,12 @@ int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScal
 
 template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
 int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, const RoundOut& out) {
-    // register budget: 3 blocks/SM (<= 85 registers) for the common shapes, 2 where the sweep is wide
-    if constexpr (M <= 2) {
-        if (c->fused_minb == 2) return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 2>(c, tp, pairs, s, out);
-        return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 3>(c, tp, pairs, s, out);
-    } else {
-        return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 2>(c, tp, pairs, s, out);
+    // occupancy shapes (tuning knob JB_FUSED_SHAPE): 0 = 256 threads x 2 blocks (128 registers),
+    // 1 = 128 threads x 5 blocks (<= 102 registers, 20 warps/SM)
+    if constexpr (M == 2) {
+        if (c->fused_shape == 1) return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 128, 5>(c, tp, pairs, s, out);
     }
+    return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 256, 2>(c, tp, pairs, s, out);
 }
 
 template <int M, int ORDER, bool SKIP1>
@@ -264,7 +263,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->sm_count = prop.multiProcessorCount;
-    if (const char* mb = std::getenv("JB_FUSED_MINB")) c->fused_minb = std::atoi(mb);  // tuning knob (2 or 3)
+    if (const char* sh = std::getenv("JB_FUSED_SHAPE")) c->fused_shape = std::atoi(sh);  // tuning knob
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
     // A kernel-replaying profiler (ncu) or a serialising tool (compute-sanitizer, nsys CUDA trace) cannot
     // run a kernel that waits for host commands; under CUDA injection keep one launch per round.

@@ -262,16 +262,17 @@ template <int M, bool SKIP1>
 struct FusedShape {
     static constexpr int K = SKIP1 ? M : M + 1;  // number of values produced
     // dynamic shared memory: K accumulators x 17 words x 256 threads (M > 1) + the block-sum scratch
-    static constexpr size_t ACC_WORDS = (M == 1) ? 0 : (size_t)K * 17 * 256;
-    static constexpr size_t SMEM_BYTES = (ACC_WORDS + 8 * K * 8) * 4;
+    __host__ __device__ static constexpr size_t acc_words(int block) { return (M == 1) ? 0 : (size_t)K * 17 * block; }
+    __host__ __device__ static constexpr size_t smem_bytes(int block) { return (acc_words(block) + 8 * K * 8) * 4; }
 };
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int MINB>
-__global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
+// BLOCK threads per block (256 or 128), MINB = resident blocks per SM requested from ptxas.
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
     constexpr int K = FusedShape<M, SKIP1>::K;
     extern __shared__ uint32_t dsm[];
-    uint32_t* wacc = dsm;                                   // [e][word][tid]
-    uint32_t* red = dsm + FusedShape<M, SKIP1>::ACC_WORDS;  // block_sum scratch
+    uint32_t* wacc = dsm;                                          // [e][word][tid]
+    uint32_t* red = dsm + FusedShape<M, SKIP1>::acc_words(BLOCK);  // block_sum scratch
     const int tid = threadIdx.x;
     Fr sum1[M == 1 ? K : 1];
     if (M == 1) {
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
 #pragma unroll
         for (int e = 0; e < K; ++e)
 #pragma unroll
-            for (int w = 0; w < 17; ++w) wacc[(e * 17 + w) * 256 + tid] = 0;
+            for (int w = 0; w < 17; ++w) wacc[(e * 17 + w) * BLOCK + tid] = 0;
     }
 
     size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -346,14 +347,14 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
                 Fr prod = lo[0];
 #pragma unroll
                 for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, lo[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, lo[M - 1].v);
+                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, lo[M - 1].v);
                 ++e;
             }
             if (!SKIP1) {  // t = 1: lo + D = hi
                 Fr prod = hi[0];
 #pragma unroll
                 for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, hi[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, hi[M - 1].v);
+                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, hi[M - 1].v);
                 ++e;
             }
             Fr dlt[M];
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
                     Fr prod = cur[0];
 #pragma unroll
                     for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, cur[j]);
-                    mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, cur[M - 1].v);
+                    mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, cur[M - 1].v);
                     ++e;
                 }
             }
@@ -378,14 +379,14 @@ __global__ void __launch_bounds__(256, MINB) fused_round_kernel(TablePtrs tp, si
                 Fr prod = dlt[0];
 #pragma unroll
                 for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, dlt[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * 256 + tid, 256, prod.v, dlt[M - 1].v);
+                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, dlt[M - 1].v);
             }
         }
     }
     Fr acc[K];
 #pragma unroll
     for (int e = 0; e < K; ++e)
-        acc[e] = (M == 1) ? sum1[e] : reduce_wide17<FrParams>(wacc + (e * 17) * 256 + tid, 256);
+        acc[e] = (M == 1) ? sum1[e] : reduce_wide17<FrParams>(wacc + (e * 17) * BLOCK + tid, BLOCK);
     block_sum<K>(acc, red);
     __syncthreads();  // scratch is reused by the last block's fold
     round_epilogue<K>(acc, red, out);
