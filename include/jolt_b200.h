@@ -110,6 +110,17 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind_or_null, size_t r
 int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]);
 /* The m fully bound table values (SumcheckKernel::output_claims, kernel.rs:72-126). */
 int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
+/* Split-eq member: ProveRounds for sum_x eq(w, x) * prod_j f_j(x), degree m + 1, without
+ * ever materialising or binding the eq table - GruenSplitEqPolynomial / TensorEqTable
+ * (crates/jolt-poly/src/split_eq.rs:10-447): each round's sweep is weighted by E_out (x) E_in over the
+ * not-yet-current variables (two ~sqrt(N) tables), the current variable's linear factor and the hint
+ * s(0)+s(1) = previous_claim complete the round polynomial on the host (gruen_poly_from_evals, :404-437).
+ * w = nvars elements, w[0] <-> most significant index bit; LowToHigh binding; m in 1..3; the running claim
+ * is mandatory in prove_round. Round polynomials equal those of the (m+1)-table product member over the
+ * materialised eq table. jb_eq_member_scalar returns scale * eq(w, r) after the rounds. */
+int jb_eq_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, const uint64_t* w, size_t nvars,
+                        const uint64_t* scale_or_null, int order, jb_member** out);
+int jb_eq_member_scalar(jb_member* mem, uint64_t out[4]);
 /* Multi-GPU: like prove_round but leaves this rank's partial sums - s(0..degree), or with skip_t1
  * s(0), s(2), .., s(degree) - on the device as count x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32
  * ranks); the caller all-reduces that buffer and calls jb_partials_finalize. No round check. */

@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     LOW_TO_HIGH,
     BatchMember,
     EqPolynomial,
+    EqProductMember,
     G1Bases,
     HyperKZG,
     HyperKZGProof,

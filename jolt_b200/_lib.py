@@ -43,6 +43,9 @@ SIGNATURES = {
     "jb_member_prove_round": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p, c_u64p]),
     "jb_member_finish_rounds": (ctypes.c_int, [c_void_p, c_u64p]),
     "jb_member_final_evals": (ctypes.c_int, [c_void_p, c_u64p]),
+    "jb_eq_member_create": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p, c_size_t, c_u64p, ctypes.c_int,
+                                           ctypes.POINTER(c_void_p)]),
+    "jb_eq_member_scalar": (ctypes.c_int, [c_void_p, c_u64p]),
     "jb_member_prove_round_partials": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.c_int, c_void_p]),
     "jb_ctx_set_verify_rounds": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "jb_partials_finalize": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_u64p]),

@@ -311,6 +311,41 @@ class ProductMember:
             pass
 
 
+class EqProductMember(ProductMember):
+    """ProveRounds member for sum_x eq(w, x) * prod_j f_j(x) (degree m + 1) with the eq polynomial kept
+    split (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): no eq table is materialised,
+    bound or streamed. `w_limbs`: n elements, w[0] <-> MSB; LowToHigh binding."""
+
+    def __init__(self, session: Session, polys: list[Polynomial], w_limbs, scale=None):
+        self.s = session
+        handles = np.array([p.handle for p in polys], dtype=np.uint64)
+        w = np.ascontiguousarray(w_limbs, dtype=np.uint64).reshape(-1, 4)
+        sc = None if scale is None else _limbs(scale)
+        h = ctypes.c_void_p()
+        session.check(session.lib.jb_eq_member_create(session.h, _p(handles), len(polys), _p(w), w.shape[0],
+                                                      _p(sc) if sc is not None else None, LOW_TO_HIGH, ctypes.byref(h)))
+        for p in polys:
+            p.handle = 0
+        self.h = h
+        self.m = len(polys)
+
+    def degree(self) -> int:
+        return self.m + 1
+
+    def prove_round_evals(self, bind, rnd: int, previous_claim=None) -> list[int]:
+        b = None if bind is None else _limbs(bind)
+        c = None if previous_claim is None else _limbs(previous_claim)
+        out = np.empty((self.m + 2, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_member_prove_round(self.h, _p(b) if b is not None else None, rnd,
+                                                      _p(c) if c is not None else None, _p(out)))
+        return F.limbs_to_ints(out)
+
+    def eq_scalar(self) -> int:
+        out = np.empty(4, dtype=np.uint64)
+        self.s.check(self.s.lib.jb_eq_member_scalar(self.h, _p(out)))
+        return F.from_limbs(out)
+
+
 @dataclass
 class BatchMember:
     """jolt_sumcheck::BatchMember (batch.rs:24-71)."""

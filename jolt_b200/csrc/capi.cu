@@ -18,6 +18,7 @@
 #include "ctx.hpp"
 #include "host_fr.hpp"
 #include "poly_kernels.cuh"
+#include "sumcheck_host.hpp"
 
 using namespace jb;
 
@@ -131,6 +132,49 @@ int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar&
         if (c->fused_shape == 1) return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 128, 5>(c, tp, pairs, s, out);
     }
     return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 256, 2>(c, tp, pairs, s, out);
+}
+
+// weighted (split-eq) passes: LowToHigh, s(1) from the claim, 256 x 2
+template <int M, bool BIND, bool HI4>
+int launch_weighted(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
+    auto kernel = fused_round_kernel<M, ORDER_LOW_TO_HIGH, BIND, HI4, true, 256, 2, true>;
+    constexpr size_t smem = FusedShape<M, true>::smem_bytes(256);
+    static int per_sm = [&] {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+        return nb;
+    }();
+    size_t need = (pairs + 255) / 256;
+    size_t resident = (size_t)c->sm_count * per_sm;
+    size_t grid = need < resident ? need : resident;
+    if (grid < 1) grid = 1;
+    int st = c->ensure_partial(grid * M);
+    if (st != JB_OK) return st;
+    out.partial = c->d_partial;
+    int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
+    const unsigned block = pairs <= 32 ? 32u : 256u;
+    kernel<<<(unsigned)grid, block, smem, c->stream>>>(tp, pairs, s, out);
+    c->timing_end(tix);
+    c->launches++;
+    return c->check(cudaGetLastError(), "fused_round_kernel (weighted) launch");
+}
+
+template <int M>
+int dispatch_weighted1(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
+                       const RoundOut& out) {
+    if (!bind) return launch_weighted<M, false, false>(c, tp, pairs, s, out);
+    return hi4 ? launch_weighted<M, true, true>(c, tp, pairs, s, out) : launch_weighted<M, true, false>(c, tp, pairs, s, out);
+}
+
+int dispatch_weighted(jb_ctx* c, int m, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
+                      const RoundOut& out) {
+    switch (m) {
+        case 1: return dispatch_weighted1<1>(c, tp, pairs, bind, hi4, s, out);
+        case 2: return dispatch_weighted1<2>(c, tp, pairs, bind, hi4, s, out);
+        case 3: return dispatch_weighted1<3>(c, tp, pairs, bind, hi4, s, out);
+        default: return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
+    }
 }
 
 template <int M, int ORDER, bool SKIP1>
@@ -528,6 +572,16 @@ struct jb_member {
     bool sharded = false;
     size_t gather_len = 0;
     jb_member* tail = nullptr;
+    // split-eq member (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): the relation is
+    // sum_x eq(w, x) prod_j f_j(x); eq is never materialised - per round the sweep is weighted by
+    // E_out (x) E_in over the not-yet-current variables and the current variable's linear factor
+    // l(t) = scalar * ((1 - w_cur) + t (2 w_cur - 1)) is multiplied in on the host.
+    bool eq = false;
+    size_t eq_n = 0, eq_split = 0;
+    std::vector<uint64_t> eq_w;        // n elements, w[0] <-> most significant index bit
+    uint64_t eq_scalar[4] = {0, 0, 0, 0};
+    uint64_t* eq_tabs = nullptr;       // prefix tables Eo[k] (k <= split) then Ei[k] (k <= n-1-split), table k at 2^k - 1
+    size_t eq_in_base = 0;             // element offset of the Ei family
     // persistent tail kernel (poly_kernels.cuh, tail_rounds_kernel): serves the short rounds from a mailbox
     bool pt_active = false;
     bool has_final = false;
@@ -579,7 +633,7 @@ int jb_member_num_rounds(jb_member* mem, size_t* rounds) {
 
 int jb_member_degree(jb_member* mem, size_t* degree) {
     if (!mem || !degree) return JB_ERR_INVALID;
-    *degree = (size_t)mem->m;
+    *degree = (size_t)mem->m + (mem->eq ? 1 : 0);
     return JB_OK;
 }
 
@@ -587,7 +641,13 @@ int jb_member_degree(jb_member* mem, size_t* degree) {
 // lanes_out holds them widened to one 32-bit limb per u64.
 static void* const JB_LANES_EXCHANGE = (void*)(uintptr_t)1;  // sentinel: all-reduce in the kernel epilogue
 
-static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* lanes_out) {
+struct EqRound {
+    const uint64_t* e_out;
+    const uint64_t* e_in;
+    int in_bits;
+};
+
+static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* lanes_out, const EqRound* eqr = nullptr) {
     jb_ctx* c = mem->ctx;
     bool do_bind = bind != nullptr;
     bool hi4 = false;
@@ -641,7 +701,15 @@ static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* 
         ro.result = c->d_result_alias;
         ro.flag = c->d_result_alias + 64;
     }
-    int st = dispatch_fused(c, mem->m, mem->order, skip1, tp, pairs, do_bind, hi4, s, ro);
+    int st;
+    if (eqr) {
+        tp.e_out = eqr->e_out;
+        tp.e_in = eqr->e_in;
+        tp.in_bits = eqr->in_bits;
+        st = dispatch_weighted(c, mem->m, tp, pairs, do_bind, hi4, s, ro);
+    } else {
+        st = dispatch_fused(c, mem->m, mem->order, skip1, tp, pairs, do_bind, hi4, s, ro);
+    }
     if (st != JB_OK) return st;
     if (do_bind) {
         for (int j = 0; j < mem->m; ++j) {
@@ -772,6 +840,8 @@ static void tail_finish(jb_member* mem) {
 static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
                                uint64_t* out_evals);
 
+static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals);
+
 // Assembles s(0..M) from the K published values. Kernel order: s(0), [s(1)], s(2..M-1), s(inf) for
 // M >= 2 (s(0), [s(1)] for M == 1); with skip1, s(1) = claim - s(0). s(M) is rebuilt from the leading
 // coefficient: q(t) = s(t) - s(inf) t^M has degree < M, so q(M) = sum_{i<M} (-1)^(M-1-i) C(M,i) q(i).
@@ -820,6 +890,11 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
     if ((mem->rounds_done == 0) != (bind == nullptr))
         return c->fail(JB_ERR_INVALID, "prove_round: bind must be absent exactly on the first round");
+    if (mem->eq) {
+        int st = eq_prove_round(mem, bind, round, claim, out_evals);
+        if (st == JB_OK) mem->rounds_done++;
+        return st;
+    }
     // With a claim and round verification off (the default, = the reference's optimized tier) the
     // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
     // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
@@ -846,6 +921,109 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     st = assemble_evals(c, mem->m, skip1, c->h_result, claim, round, out_evals);
     if (st == JB_OK) mem->rounds_done++;
     return st;
+}
+
+// ---- split-eq member: one round ------------------------------------------------------------------------
+// scalar <- scalar * eq(w_v, r) for the variable v just bound (GruenSplitEqPolynomial::bind, split_eq.rs:347-352)
+static void eq_absorb_bind(jb_member* mem, size_t var, const uint64_t* r) {
+    HostFr wv = HostFr::from_limbs(mem->eq_w.data() + 4 * var), rr = HostFr::from_limbs(r);
+    HostFr prod = wv * rr;
+    HostFr f = HostFr::one() - wv - rr + prod + prod;
+    (HostFr::from_limbs(mem->eq_scalar) * f).store(mem->eq_scalar);
+}
+
+static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals) {
+    jb_ctx* c = mem->ctx;
+    if (!claim) return c->fail(JB_ERR_INVALID, "eq member: the running claim is required (Gruen hint s(0)+s(1))");
+    const size_t n = mem->eq_n, M = (size_t)mem->m;
+    if (round >= n) return c->fail(JB_ERR_INVALID, "prove_round: member is fully bound");
+    if (bind) {
+        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
+        eq_absorb_bind(mem, n - round, bind);  // the previous round's variable
+    }
+    const size_t cur = n - round;  // unbound variables including the current one (index cur - 1, LowToHigh)
+    const size_t head = cur - 1;
+    const size_t out_bits = head < mem->eq_split ? head : mem->eq_split;
+    const size_t in_bits = head - out_bits;
+    EqRound er;
+    er.e_out = mem->eq_tabs + 4 * (((size_t)1 << out_bits) - 1);
+    er.e_in = mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << in_bits) - 1);
+    er.in_bits = (int)in_bits;
+    int st = member_round(mem, bind, true, nullptr, &er);
+    if (st == JB_OK) st = wait_round_result(c);
+    if (st != JB_OK) return st;
+    // kernel order: q(0), q(2), .., q(M-1), q(inf)   (M values; q(0) only for M == 1)
+    const HostFr scalar = HostFr::from_limbs(mem->eq_scalar);
+    const HostFr wc = HostFr::from_limbs(mem->eq_w.data() + 4 * (cur - 1));
+    const HostFr l1 = scalar * wc, l0 = scalar - l1;
+    if (l1.is_zero()) return c->fail(JB_ERR_INVALID, "eq member: current eq evaluation at one must be invertible");
+    const HostFr q0 = HostFr::from_limbs(c->h_result);
+    const HostFr q1 = (HostFr::from_limbs(claim) - l0 * q0) * l1.inverse();
+    uint64_t vals[JB_MAX_EVALS * 4], qe[JB_MAX_EVALS * 4];
+    q0.store(vals);
+    q1.store(vals + 4);
+    if (M > 1) std::memcpy(vals + 8, c->h_result + 4, (M - 1) * 32);
+    st = assemble_evals(c, (int)M, false, vals, nullptr, round, qe);  // q(0..M)
+    if (st != JB_OK) return st;
+    // q(M+1) by extrapolation (degree M), then s(t) = l(t) q(t), t = 0..M+1
+    std::vector<HostFr> qv(M + 1);
+    for (size_t t = 0; t <= M; ++t) qv[t] = HostFr::from_limbs(qe + 4 * t);
+    jb::UnivariatePoly qp = jb::UnivariatePoly::from_evals(qv);
+    const HostFr dl = l1 - l0;
+    HostFr lt = l0;
+    for (size_t t = 0; t <= M + 1; ++t) {
+        HostFr qt = t <= M ? qv[t] : qp.evaluate(HostFr::from_u64(t));
+        (lt * qt).store(out_evals + 4 * t);
+        lt = lt + dl;
+    }
+    return JB_OK;
+}
+
+int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint64_t* w, size_t nvars,
+                        const uint64_t* scale_or_null, int order, jb_member** out) {
+    if (!c || !handles || !w || !out) return JB_ERR_INVALID;
+    if (order != JB_LOW_TO_HIGH) return c->fail(JB_ERR_UNSUPPORTED, "eq member: LowToHigh binding only");
+    if (m < 1 || m > 3) return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
+    for (size_t i = 0; i < nvars; ++i)
+        if (!canonical_fr(w + 4 * i)) return c->fail(JB_ERR_INVALID, "eq member: point limbs not canonical");
+    if (scale_or_null && !canonical_fr(scale_or_null)) return c->fail(JB_ERR_INVALID, "eq member: scale not canonical");
+    int st = jb_member_create(c, handles, m, order, out);
+    if (st != JB_OK) return st;
+    jb_member* mem = *out;
+    if (mem->rounds != nvars || nvars == 0) {
+        jb_member_destroy(mem);
+        *out = nullptr;
+        return c->fail(JB_ERR_INVALID, "eq member: point length must equal log2(table length) >= 1");
+    }
+    Guard g(c);
+    mem->eq = true;
+    mem->eq_n = nvars;
+    mem->eq_split = nvars / 2;
+    mem->eq_w.assign(w, w + 4 * nvars);
+    HostFr sc = scale_or_null ? HostFr::from_limbs(scale_or_null) : HostFr::one();
+    sc.store(mem->eq_scalar);
+    // prefix tables (EqPolynomial::evals_cached, eq.rs:322-340): Eo[k] over w[0..k), Ei[k] over w[split..split+k)
+    const size_t split = mem->eq_split, nin = nvars - 1 - (split < nvars - 1 ? split : nvars - 1);
+    const size_t out_max = split < nvars - 1 ? split : nvars - 1;
+    mem->eq_in_base = ((size_t)2 << out_max) - 1;
+    const size_t total = mem->eq_in_base + ((size_t)2 << nin) - 1;
+    st = c->dev_alloc((void**)&mem->eq_tabs, total * 32);
+    for (size_t k = 0; k <= out_max && st == JB_OK; ++k)
+        st = eq_build(c, w, k, nullptr, mem->eq_tabs + 4 * (((size_t)1 << k) - 1));
+    for (size_t k = 0; k <= nin && st == JB_OK; ++k)
+        st = eq_build(c, w + 4 * split, k, nullptr, mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << k) - 1));
+    if (st != JB_OK) {
+        jb_member_destroy(mem);
+        *out = nullptr;
+    }
+    return st;
+}
+
+// eq(w, r) * scale after all rounds (the member's eq factor of the final claim)
+int jb_eq_member_scalar(jb_member* mem, uint64_t out[4]) {
+    if (!mem || !out || !mem->eq) return JB_ERR_INVALID;
+    std::memcpy(out, mem->eq_scalar, 32);
+    return JB_OK;
 }
 
 // ---- index-sharded member ----------------------------------------------------------------------
@@ -1021,6 +1199,12 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     }
     Guard g(c);
     if (mem->len < 2) return c->fail(JB_ERR_INVALID, "finish_rounds: member already fully bound");
+    if (mem->eq) {
+        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
+        size_t var = 0;
+        for (size_t l = mem->len; l > 2; l >>= 1) ++var;  // index of the variable being bound (LowToHigh)
+        eq_absorb_bind(mem, var, bind);
+    }
     if (mem->pt_active) {
         if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
         int st = tail_post(mem, TAIL_CMD_FINAL_BIND, bind, false);
@@ -1079,6 +1263,10 @@ void jb_member_destroy(jb_member* mem) {
         Guard g(mem->ctx);
         tail_post(mem, TAIL_CMD_ABORT, nullptr, false);
         tail_finish(mem);
+    }
+    if (mem->eq_tabs) {
+        Guard g(mem->ctx);
+        mem->ctx->dev_free(mem->eq_tabs);
     }
     if (mem->pt_host) {  // back to the context's pool (the kernel has exited: tail_finish ran)
         Guard g(mem->ctx);

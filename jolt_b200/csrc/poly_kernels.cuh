@@ -235,6 +235,11 @@ __device__ __forceinline__ void round_epilogue(Fr (&acc)[K], uint32_t* smem, con
 struct TablePtrs {
     const uint64_t* in[4];
     uint64_t* out[4];
+    // WEIGHTED passes (split-eq members): the pair y carries the weight e_out[y >> in_bits] * e_in[y & mask]
+    // (TensorEqTable::evaluate_index, crates/jolt-poly/src/split_eq.rs:52-56); both tables are ~sqrt(N) long.
+    const uint64_t* e_out;
+    const uint64_t* e_in;
+    int in_bits;
 };
 
 // Fused pass for a product-of-M member:
@@ -267,7 +272,11 @@ struct FusedShape {
 };
 
 // BLOCK threads per block (256 or 128), MINB = resident blocks per SM requested from ptxas.
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB>
+// WEIGHTED: the sweep is sum_y E(y) prod_j(...) with the split-eq weight E(y) = e_out * e_in folded into
+// table 0's pair AFTER the bound values are stored (GruenSplitEqPolynomial, split_eq.rs:159-447: the eq
+// polynomial is never materialised or bound as a table; its current variable is a linear factor the host
+// multiplies in).
+template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB, bool WEIGHTED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
     constexpr int K = FusedShape<M, SKIP1>::K;
     extern __shared__ uint32_t dsm[];
@@ -337,6 +346,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
                     hi[j] = ld_elem<Fr>(tp.in[j], 2 * y + 1);
                 }
             }
+        }
+        if (WEIGHTED) {
+            const size_t mask = ((size_t)1 << tp.in_bits) - 1;
+            Fr wgt = fp_mul(ld_elem<Fr>(tp.e_out, y >> tp.in_bits), ld_elem<Fr>(tp.e_in, y & mask));
+            lo[0] = fp_mul(lo[0], wgt);
+            hi[0] = fp_mul(hi[0], wgt);
         }
         if (M == 1) {
             sum1[0] = fp_add(sum1[0], lo[0]);
