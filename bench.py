@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--m", type=int, default=2, help="tables in the product (degree)")
     ap.add_argument("--order", default="l2h", choices=["l2h", "h2l"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msm", action="store_true", help="skip the secondary G1 MSM measurement")
+    ap.add_argument("--msm-log-n", type=int, default=20)
     return ap.parse_args()
 
 
@@ -182,6 +184,59 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def msm_section(sess, log_n: int, with_cpu: bool):
+    """Secondary metric of BASELINE.json: BN254 G1 MSM terms/s (config 3). Synthetic bases (i+1)*G generated
+    on the device, uniform 253-bit scalars resident in HBM; every result is checked against the closed form
+    msm(s) = (sum_i s_i (i+1)) * G. Reported with the SRS as uploaded and with jb_srs_precompute."""
+    import numpy as np
+    from jolt_b200 import G1Bases, Polynomial, g1_jacobian_to_affine
+    from jolt_b200 import field as F
+    n = 1 << log_n
+    G = np.concatenate([F.to_limbs(1, F.Q_MOD), F.to_limbs(2, F.Q_MOD)])
+    rng = np.random.Generator(np.random.PCG64(0x5CA1A2))
+    sc = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] &= np.uint64(((1 << 64) - 1) >> 3)
+    tab = Polynomial.new(sess, sc)
+    # closed form, computed on the host with big ints (O(n) word products)
+    wts = np.arange(1, n + 1, dtype=object)
+    tot = 0
+    for limb in range(4):
+        for half in range(2):
+            words = ((sc[:, limb] >> np.uint64(32 * half)) & np.uint64(0xFFFFFFFF)).astype(object)
+            tot += int((words * wts).sum()) << (64 * limb + 32 * half)
+    k = tot * pow(1 << 256, -1, F.R_MOD) % F.R_MOD
+    out = {"log_n": log_n, "unit": "terms/s", "data": "synthetic: bases (i+1)*G, uniform 253-bit scalars"}
+    for label, pre in (("plain_srs", False), ("precomputed_srs", True)):
+        bases = G1Bases.generate_multiples(sess, G, n)
+        if pre:
+            bases.precompute()
+        res = bases.msm(tab)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            res = bases.msm(tab)
+            ts.append(time.perf_counter() - t0)
+        out[label] = {"ms": min(ts) * 1e3, "terms_per_s": n / min(ts)}
+        if label == "plain_srs":
+            out["_pt"] = g1_jacobian_to_affine(res)
+            xy = bases.affine() if with_cpu else None
+        else:
+            out["results_agree"] = out.pop("_pt") == g1_jacobian_to_affine(res)
+        bases.free()
+    if with_cpu:
+        from oracle import coracle as C
+        from oracle import bn254 as O
+        t0 = time.perf_counter()
+        cpu_xy, cpu_inf = C.g1_msm_pippenger(xy, sc, 0, C.max_threads())
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"ms": dt * 1e3, "terms_per_s": n / dt, "cores": C.max_threads(), "kind": "port",
+                               "sample": "one Pippenger MSM (arkworks window heuristic) with the C restatement, OpenMP over windows"}
+        out["matches_closed_form"] = (not cpu_inf) and O.g1_scalar_mul(O.G1_GEN, k) == (
+            O.from_mont_limbs(cpu_xy[:4], O.Q_MOD), O.from_mont_limbs(cpu_xy[4:], O.Q_MOD))
+    tab.free()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -355,6 +410,8 @@ def run_ours(args):
         "all_field_ops_per_s": all_ops(args.log_n, m) * world / (ms_per_step * 1e-3),
         "wall_ms_per_step": wall / K * 1e3,
     }
+    if world == 1 and not args.no_msm:
+        line["msm"] = msm_section(sess, args.msm_log_n, not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import coracle as C
         threads = C.max_threads()

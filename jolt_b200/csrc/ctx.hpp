@@ -74,7 +74,6 @@ struct jb_ctx {
     uint64_t diag_wait_ns = 0, diag_waits = 0;  // host time spent waiting for round results
     bool use_tail = true;           // persistent tail kernel for short rounds
     int fused_shape = 0;            // fused-kernel occupancy shape (see launch_fused)
-    int fused_minb = 2;             // min resident blocks/SM requested for the m <= 2 fused kernels
     bool verify_rounds = false;     // compute s(1) and check s(0)+s(1)==claim instead of deriving s(1)
     uint64_t* d_small = nullptr;    // device staging
     uint64_t* h_small = nullptr;    // pinned host staging

@@ -346,10 +346,10 @@ __device__ __forceinline__ Fp<PR> fp_to_mont(const Fp<PR>& a) {
 }
 
 // ---- deferred-reduction accumulation (the GPU counterpart of the reference's WideAccumulator,
-// crates/jolt-field/src/bn254/mont.rs:565-602): acc (16 x u32, < 2^512) += a * b as a plain 512-bit
-// integer product of the Montgomery limbs; ONE Montgomery reduction at the end turns the sum of
-// products into the field sum. Operands canonical (< p < 2^254) => each product < 2^508, so an
-// accumulator holds at least 8 products before it must be reduced.
+// crates/jolt-field/src/bn254/mont.rs:565-602): acc += a * b as a plain 512-bit integer product of the
+// Montgomery limbs, E collecting the lo/hi pairs that start at even limb positions and O (weight
+// shifted by one limb) those that start at odd positions - every row is two 4-pair carry chains; ONE
+// Montgomery reduction at the end turns the sum of products into the field sum.
 
 // r[0..7] += (a0,a1,a2,a3) * b as four adjacent lo/hi pairs in one carry chain; the carry out is
 // added into `top` (the word above r[7]).
@@ -367,81 +367,6 @@ __device__ __forceinline__ void chain8_top(uint32_t* r, uint32_t& top, uint32_t 
         : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(top)
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
 }
-// same without a carry out (the chain ends at the top of the product)
-__device__ __forceinline__ void chain8_end(uint32_t* r, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                           uint32_t b) {
-    asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\t"
-        "madc.hi.cc.u32 %1, %8, %12, %1;\n\t"
-        "madc.lo.cc.u32 %2, %9, %12, %2;\n\t"
-        "madc.hi.cc.u32 %3, %9, %12, %3;\n\t"
-        "madc.lo.cc.u32 %4, %10, %12, %4;\n\t"
-        "madc.hi.cc.u32 %5, %10, %12, %5;\n\t"
-        "madc.lo.cc.u32 %6, %11, %12, %6;\n\t"
-        "madc.hi.u32 %7, %11, %12, %7;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
-}
-
-// acc += a * b  (512-bit integer). E collects the pairs starting at even positions, O (weight
-// shifted by one limb) those starting at odd positions; every row is two 4-pair carry chains.
-__device__ __forceinline__ void mul_wide_acc(uint32_t* acc, const uint32_t* a, const uint32_t* b) {
-    uint32_t E[17], O[17];
-#pragma unroll
-    for (int k = 0; k < 17; ++k) E[k] = O[k] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-        // row i (even): even j -> E[i..i+7]; odd j -> positions i+1..i+8 = O[i..i+7]
-        chain8_top(E + i, E[i + 8], a[0], a[2], a[4], a[6], b[i]);
-        chain8_top(O + i, O[i + 8], a[1], a[3], a[5], a[7], b[i]);
-        // row i+1 (odd): even j -> positions i+1..i+8 = O[i..i+7]; odd j -> E[i+2..i+9]
-        chain8_top(O + i, O[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
-        if (i + 2 + 8 <= 16) chain8_top(E + i + 2, E[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
-        else chain8_end(E + i + 2, a[1], a[3], a[5], a[7], b[i + 1]);
-    }
-    // acc += E + (O << 32)
-    asm("add.cc.u32 %0, %0, %16;\n\t"
-        "addc.cc.u32 %1, %1, %17;\n\t"
-        "addc.cc.u32 %2, %2, %18;\n\t"
-        "addc.cc.u32 %3, %3, %19;\n\t"
-        "addc.cc.u32 %4, %4, %20;\n\t"
-        "addc.cc.u32 %5, %5, %21;\n\t"
-        "addc.cc.u32 %6, %6, %22;\n\t"
-        "addc.cc.u32 %7, %7, %23;\n\t"
-        "addc.cc.u32 %8, %8, %24;\n\t"
-        "addc.cc.u32 %9, %9, %25;\n\t"
-        "addc.cc.u32 %10, %10, %26;\n\t"
-        "addc.cc.u32 %11, %11, %27;\n\t"
-        "addc.cc.u32 %12, %12, %28;\n\t"
-        "addc.cc.u32 %13, %13, %29;\n\t"
-        "addc.cc.u32 %14, %14, %30;\n\t"
-        "addc.u32 %15, %15, %31;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
-          "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]),
-          "+r"(acc[14]), "+r"(acc[15])
-        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
-          "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]));
-    asm("add.cc.u32 %0, %0, %15;\n\t"
-        "addc.cc.u32 %1, %1, %16;\n\t"
-        "addc.cc.u32 %2, %2, %17;\n\t"
-        "addc.cc.u32 %3, %3, %18;\n\t"
-        "addc.cc.u32 %4, %4, %19;\n\t"
-        "addc.cc.u32 %5, %5, %20;\n\t"
-        "addc.cc.u32 %6, %6, %21;\n\t"
-        "addc.cc.u32 %7, %7, %22;\n\t"
-        "addc.cc.u32 %8, %8, %23;\n\t"
-        "addc.cc.u32 %9, %9, %24;\n\t"
-        "addc.cc.u32 %10, %10, %25;\n\t"
-        "addc.cc.u32 %11, %11, %26;\n\t"
-        "addc.cc.u32 %12, %12, %27;\n\t"
-        "addc.cc.u32 %13, %13, %28;\n\t"
-        "addc.u32 %14, %14, %29;"
-        : "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
-          "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(acc[12]), "+r"(acc[13]), "+r"(acc[14]),
-          "+r"(acc[15])
-        : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
-          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
-}
-
 // Shared-memory form: the 544-bit accumulator lives at acc[k * stride] (k = 0..16; one column per
 // thread, so accesses are conflict-free) and is only in registers while a product is merged - this
 // is what lets the fused round kernel run at three blocks per SM. Operands may be lazy (< 2p):
@@ -572,40 +497,6 @@ __device__ __forceinline__ Fp<PR> reduce_wide17(const uint32_t* acc, int stride)
 #pragma unroll
     for (int k = 0; k < 8; ++k) out.v[k] = r[k];
     return out;
-}
-
-// Montgomery-reduce a 512-bit accumulator (< 2^511) to the canonical element acc * R^-1 mod p.
-// Runs once per thread per kernel, so it is written for clarity, not for the multiplier pipe.
-template <class PR>
-__device__ __forceinline__ Fp<PR> reduce_wide(const uint32_t* acc) {
-    uint32_t T[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) T[k] = acc[k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t m = T[k] * PR::INV;
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint64_t t = (uint64_t)m * PR::P(j) + T[k + j] + carry;
-            T[k + j] = (uint32_t)t;
-            carry = t >> 32;
-        }
-#pragma unroll
-        for (int l = k + 8; l < 16; ++l) {
-            uint64_t t = (uint64_t)T[l] + carry;
-            T[l] = (uint32_t)t;
-            carry = t >> 32;
-        }
-    }
-    Fp<PR> r;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = T[8 + k];
-    // acc/R + p < 2^255 + p < 4p: at most three subtractions
-    cond_sub_p<PR>(r.v);
-    cond_sub_p<PR>(r.v);
-    cond_sub_p<PR>(r.v);
-    return r;
 }
 
 using Fr = Fp<FrParams>;
