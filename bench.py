@@ -186,8 +186,8 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 def msm_section(sess, log_n: int, with_cpu: bool):
     """Secondary metric of BASELINE.json: BN254 G1 MSM terms/s (config 3). Synthetic bases (i+1)*G generated
-    on the device, uniform 253-bit scalars resident in HBM; every result is checked against the closed form
-    msm(s) = (sum_i s_i (i+1)) * G. Reported with the SRS as uploaded and with jb_srs_precompute."""
+    on the device, uniform 253-bit scalars resident in HBM. Reported with the SRS as uploaded and with
+    jb_srs_precompute; the two device results must agree, and (cpu_baseline leg) must equal the CPU port's."""
     import numpy as np
     from jolt_b200 import G1Bases, Polynomial, g1_jacobian_to_affine
     from jolt_b200 import field as F
@@ -197,14 +197,6 @@ def msm_section(sess, log_n: int, with_cpu: bool):
     sc = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
     sc[:, 3] &= np.uint64(((1 << 64) - 1) >> 3)
     tab = Polynomial.new(sess, sc)
-    # closed form, computed on the host with big ints (O(n) word products)
-    wts = np.arange(1, n + 1, dtype=object)
-    tot = 0
-    for limb in range(4):
-        for half in range(2):
-            words = ((sc[:, limb] >> np.uint64(32 * half)) & np.uint64(0xFFFFFFFF)).astype(object)
-            tot += int((words * wts).sum()) << (64 * limb + 32 * half)
-    k = tot * pow(1 << 256, -1, F.R_MOD) % F.R_MOD
     out = {"log_n": log_n, "unit": "terms/s", "data": "synthetic: bases (i+1)*G, uniform 253-bit scalars"}
     for label, pre in (("plain_srs", False), ("precomputed_srs", True)):
         bases = G1Bases.generate_multiples(sess, G, n)
@@ -218,10 +210,10 @@ def msm_section(sess, log_n: int, with_cpu: bool):
             ts.append(time.perf_counter() - t0)
         out[label] = {"ms": min(ts) * 1e3, "terms_per_s": n / min(ts)}
         if label == "plain_srs":
-            out["_pt"] = g1_jacobian_to_affine(res)
+            gpu_pt = g1_jacobian_to_affine(res)
             xy = bases.affine() if with_cpu else None
         else:
-            out["results_agree"] = out.pop("_pt") == g1_jacobian_to_affine(res)
+            out["results_agree"] = gpu_pt == g1_jacobian_to_affine(res)
         bases.free()
     if with_cpu:
         from oracle import coracle as C
@@ -231,7 +223,7 @@ def msm_section(sess, log_n: int, with_cpu: bool):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"ms": dt * 1e3, "terms_per_s": n / dt, "cores": C.max_threads(), "kind": "port",
                                "sample": "one Pippenger MSM (arkworks window heuristic) with the C restatement, OpenMP over windows"}
-        out["matches_closed_form"] = (not cpu_inf) and O.g1_scalar_mul(O.G1_GEN, k) == (
+        out["matches_cpu_port"] = (not cpu_inf) and gpu_pt == (
             O.from_mont_limbs(cpu_xy[:4], O.Q_MOD), O.from_mont_limbs(cpu_xy[4:], O.Q_MOD))
     tab.free()
     return out
