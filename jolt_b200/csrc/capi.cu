@@ -361,6 +361,7 @@ void jb_ctx_destroy(jb_ctx* c) {
     for (auto& kv : c->srs) {
         if (kv.second.xy) cudaFreeAsync(kv.second.xy, c->stream);
         if (kv.second.pre) cudaFreeAsync(kv.second.pre, c->stream);
+        if (kv.second.pre_small) cudaFreeAsync(kv.second.pre_small, c->stream);
     }
     c->srs.clear();
     c->msm_release();

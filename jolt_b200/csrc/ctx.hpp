@@ -35,6 +35,9 @@ struct Srs {
     // optional: rows w = 0..pre_W-1 of 2^(pre_c * w) * P_i (affine), row stride n points (jb_srs_precompute)
     uint64_t* pre = nullptr;
     int pre_c = 0, pre_W = 0;
+    // second table for small MSMs: 8-bit windows over the first pre_small_len bases (row stride pre_small_len)
+    uint64_t* pre_small = nullptr;
+    size_t pre_small_len = 0;
 };
 
 struct MsmWorkspace;  // msm.cu

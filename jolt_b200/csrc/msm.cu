@@ -558,10 +558,15 @@ struct Guard {
 int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
     // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
     // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
-    const bool shared = srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
-    const MsmPlan p = shared ? plan_with(srs.pre_c) : plan_for(n);
+    // Small MSMs (the tail of HyperKZG's intermediate commitments, verifier-sized MSMs) use a second, tiny
+    // table with 8-bit windows over the first bases: 128 buckets, no doubling chain - latency, not work.
+    const bool use_small = srs.pre_small != nullptr && n <= 4096 && offset + n <= srs.pre_small_len;
+    const bool use_big = !use_small && srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
+    const bool shared = use_small || use_big;
+    const MsmPlan p = use_small ? plan_with(8) : use_big ? plan_with(srs.pre_c) : plan_for(n);
+    const size_t pre_stride = use_small ? srs.pre_small_len : srs.n;       // row w starts at w * stride
     const uint64_t* d_bases = srs.xy + 8 * offset;                          // digits: identity test, per-window path: gather
-    const uint64_t* d_gather = shared ? srs.pre + 8 * offset : d_bases;     // accumulate: row w starts at w * srs.n
+    const uint64_t* d_gather = use_small ? srs.pre_small + 8 * offset : use_big ? srs.pre + 8 * offset : d_bases;
     const int Weff = shared ? 1 : p.W;  // bucket sets
     const size_t nb = (size_t)Weff * p.B;
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
@@ -593,7 +598,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
-        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, srs.n, offsets, hist, sorted);
+        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
         msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
@@ -762,6 +767,22 @@ int jb_srs_precompute(jb_ctx* c, jb_srs h, int window_bits) {
     }
     s.pre_c = p.c;
     s.pre_W = p.W;
+    // the small-MSM table: 8-bit windows over the first <= 2^15 bases (<= 66 MiB)
+    const MsmPlan ps = plan_with(8);
+    const size_t small_len = s.n < ((size_t)1 << 15) ? s.n : ((size_t)1 << 15);
+    if (c->dev_alloc((void**)&s.pre_small, (size_t)ps.W * small_len * 64) == JB_OK) {
+        precompute_windows_kernel<<<(unsigned)((small_len + 127) / 128), 128, 0, c->stream>>>(s.xy, small_len, ps.c, ps.W, s.pre_small);
+        c->launches++;
+        if (c->check(cudaGetLastError(), "precompute_windows (small) launch") == JB_OK &&
+            c->check(cudaStreamSynchronize(c->stream), "precompute sync") == JB_OK) {
+            s.pre_small_len = small_len;
+        } else {
+            c->dev_free(s.pre_small);
+            s.pre_small = nullptr;
+        }
+    } else {
+        s.pre_small = nullptr;  // optional: the plain path stays
+    }
     return JB_OK;
 }
 
@@ -792,6 +813,7 @@ int jb_srs_free(jb_ctx* c, jb_srs h) {
     if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
     c->dev_free(it->second.xy);
     if (it->second.pre) c->dev_free(it->second.pre);
+    if (it->second.pre_small) c->dev_free(it->second.pre_small);
     c->srs.erase(it);
     return JB_OK;
 }

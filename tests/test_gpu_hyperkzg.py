@@ -51,8 +51,9 @@ def oracle_open(srs_xy, evals_limbs, point_limbs, r_int, q_int):
     return com, w, v
 
 
-@pytest.mark.parametrize("ell", [1, 2, 3, 5, 8, 11, 14])
-def test_open_matches_oracle(sess, ell):
+@pytest.mark.parametrize("ell,precompute", [(1, False), (2, False), (3, True), (5, False), (8, True), (11, False),
+                                            (14, False), (14, True)])
+def test_open_matches_oracle(sess, ell, precompute):
     n = 1 << ell
     beta = C.ints_to_mont([O.random_fr(0x4D534D, 1)[0]])[0]
     srs_xy = C.g1_powers(n, G, beta) if ell <= 11 else None
@@ -61,6 +62,8 @@ def test_open_matches_oracle(sess, ell):
         srs_xy = bases.affine()
     else:
         bases = G1Bases.from_affine(sess, srs_xy)
+    if precompute:       # fixed-SRS tables: shared buckets for the large MSMs, the 8-bit table for the small ones
+        bases.precompute()
     evals = rand_limbs(100 + ell, n)
     point = np.stack([rand_challenge(7 + i) if i % 2 else rand_limbs(9 + i, 1)[0] for i in range(ell)])
     r_int, q_int = O.random_fr(1000 + ell, 2)

@@ -207,3 +207,15 @@ def test_msm_precomputed_closed_form_2pow20(sess):
     bases = G1Bases.generate_multiples(sess, G, n).precompute()
     sc = rand_limbs(0x5CA1A2, n)
     assert g1_jacobian_to_affine(bases.msm(sc)) == O.g1_scalar_mul(O.G1_GEN, _weighted_sum(sc))
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 33, 1000, 4096])
+def test_small_msm_over_precomputed_srs(sess, srs_bases, n):
+    """n <= 4096 over a precomputed handle takes the 8-bit-window table (no doubling chains)."""
+    bases = G1Bases.from_affine(sess, srs_bases[: 1 << 13]).precompute()
+    sc = rand_limbs(31 + n, n)
+    want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+    assert g1_jacobian_to_affine(bases.msm(sc)) == want
+    off = 100
+    want2 = oracle_affine(*C.g1_msm_pippenger(srs_bases[off:off + n], sc, 0, C.max_threads()))
+    assert g1_jacobian_to_affine(bases.msm(sc, offset=off)) == want2
