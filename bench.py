@@ -32,6 +32,8 @@ import pathlib
 
 ROOT = pathlib.Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+# the CPU arm's OpenMP threads must not spin at barriers when the cgroup quota is below the thread count
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 METRIC = "bn254_fr_field_ops_per_s_sumcheck_bind"
 UNIT = "field-ops/s"
@@ -128,6 +130,29 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU arm can really use: the scheduler affinity capped by the cgroup CPU quota (the GPU
+    boxes expose 128 logical CPUs under a 16-CPU quota; 128 spinning OpenMP threads on that quota are 12x
+    SLOWER than 32). Twice the quota measured best (threads that block at barriers yield their share)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = int(q) / int(period)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / period
+        except Exception:
+            pass
+    if quota:
+        n = max(1, min(n, int(2 * quota + 0.5)))
+    return n
+
+
 def cpu_sumcheck_times(log_n: int, m: int, order: int, threads: int, reps: int) -> list[float]:
     """`reps` full sumchecks of the workload on the host cores with the C restatement of the reference
     algorithm (bind pass + eval pass per round, OpenMP static chunks of >= 1024 like Rayon's PAR_THRESHOLD).
@@ -161,8 +186,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import coracle as C
-    threads = C.max_threads()
+    threads = host_threads()
     order = 1 if args.order == "l2h" else 0
     world = args.gpus
     # bounded sample: the per-GPU workload (2^log_n); warm-up and timed repetitions in ONE run so the timed
@@ -222,9 +246,9 @@ def msm_section(sess, log_n: int, with_cpu: bool):
         from oracle import coracle as C
         from oracle import bn254 as O
         t0 = time.perf_counter()
-        cpu_xy, cpu_inf = C.g1_msm_pippenger(xy, sc, 0, C.max_threads())
+        cpu_xy, cpu_inf = C.g1_msm_pippenger(xy, sc, 0, host_threads())
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"ms": dt * 1e3, "terms_per_s": n / dt, "cores": C.max_threads(), "kind": "port",
+        out["cpu_baseline"] = {"ms": dt * 1e3, "terms_per_s": n / dt, "cores": host_threads(), "kind": "port",
                                "sample": "one Pippenger MSM (arkworks window heuristic) with the C restatement, OpenMP over windows"}
         out["matches_cpu_port"] = (not cpu_inf) and gpu_pt == (
             O.from_mont_limbs(cpu_xy[:4], O.Q_MOD), O.from_mont_limbs(cpu_xy[4:], O.Q_MOD))
@@ -408,8 +432,7 @@ def run_ours(args):
     if world == 1 and not args.no_msm:
         line["msm"] = msm_section(sess, args.msm_log_n, not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import coracle as C
-        threads = C.max_threads()
+        threads = host_threads()
         reps = 2
         secs = cpu_sumcheck_sample(args.log_n, m, 1 if args.order == "l2h" else 0, threads, reps)
         line["cpu_baseline"] = {
