@@ -44,6 +44,23 @@ typedef enum jb_status {
 /* BindingOrder, crates/jolt-poly/src/lib.rs (HighToLow pairs (i, i+half); LowToHigh (2i, 2i+1)). */
 typedef enum jb_order { JB_HIGH_TO_LOW = 0, JB_LOW_TO_HIGH = 1 } jb_order;
 
+/* Element encodings. JB_SCALAR_FR = 4 x u64 Montgomery limbs. The others are the primitive integer columns
+ * the reference keeps compact - `Polynomial<T>` (crates/jolt-poly/src/dense.rs:22-142), legacy
+ * MultilinearPolynomial::{U8Scalars..I128Scalars} (crates/jolt-prover-legacy/src/msm/mod.rs:27-79) - as
+ * native little-endian arrays (u128/i128: 16 bytes, low half first; bool columns are U8 with values 0/1).
+ * Their field value is Ring::from_u64/from_i64/from_u128/from_i128
+ * (crates/jolt-field/src/bn254/mod.rs:265-298): v mod r, negatives as r - |v|. */
+typedef enum jb_scalar_kind {
+    JB_SCALAR_FR = 0,
+    JB_SCALAR_U8 = 1,
+    JB_SCALAR_U16 = 2,
+    JB_SCALAR_U32 = 3,
+    JB_SCALAR_U64 = 4,
+    JB_SCALAR_U128 = 5,
+    JB_SCALAR_I64 = 6,
+    JB_SCALAR_I128 = 7
+} jb_scalar_kind;
+
 typedef struct jb_ctx jb_ctx;       /* ~ ProofSession: device pools + stream */
 typedef struct jb_member jb_member; /* ~ Box<dyn SumcheckKernel>: a ProveRounds member on device */
 typedef uint64_t jb_table;          /* device-resident Polynomial<Fr> / DensePolynomial<Fr> */
@@ -83,6 +100,14 @@ int jb_table_free(jb_ctx* ctx, jb_table t);
  * `r` = Montgomery limbs of the challenge; limbs [0,0,lo,hi] (the 125-bit MontU128Challenge,
  * crates/jolt-prover-legacy/src/field/challenge/mont_ark_u128.rs:28-34) take the half-cost path. */
 int jb_table_bind(jb_ctx* ctx, jb_table t, const uint64_t r[4], int order);
+/* Compact tables. upload_small: a host array of `len` primitive integers (kind != JB_SCALAR_FR) becomes a
+ * field table, promoted on the device (F::from(T), dense.rs:129-142): 1-16 bytes per entry cross PCIe
+ * instead of 32. bind_small: Polynomial<T>::bind_to_field (dense.rs:129-142; the reference folds
+ * HighToLow, both orders are offered) - the compact table folded under `r` straight into a NEW field table
+ * of len/2 entries, out[i] = F(lo) + r * (F(hi) - F(lo)). Values identical to promoting then binding. */
+int jb_table_upload_small(jb_ctx* ctx, const void* values, size_t len, int kind, jb_table* out);
+int jb_table_bind_small(jb_ctx* ctx, const void* values, size_t len, int kind, const uint64_t r[4], int order,
+                        jb_table* out);
 
 /* EqPolynomial::evals(r, scaling_factor) (crates/jolt-poly/src/eq.rs:221-231): 2^nvars entries,
  * r[0] <-> most-significant index bit. scale_or_null == NULL means 1. */
@@ -202,6 +227,14 @@ int jb_srs_free(jb_ctx* ctx, jb_srs s);
  * normalisation is needed (or paid for) at the boundary. n == 0 -> identity (group_laws.rs:143-146);
  * offset + n > srs length -> JB_ERR_LENGTH (the reference panics, mod.rs:200-204). */
 int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
+/* Small-scalar MSM: VariableBaseMSM::msm_u8/u16/u32/u64/u128/i64/i128 and the U8Scalars..I64Scalars arms of
+ * VariableBaseMSM::msm (crates/jolt-prover-legacy/src/msm/mod.rs:27-150; msm_binary = JB_SCALAR_U8 with
+ * values 0/1). `scalars`: host array of n primitive integers of `kind` (not JB_SCALAR_FR). Only
+ * ceil(bits / c) windows are formed and the window is sized for the width (one 9-bit window for u8, five
+ * 13-bit windows for u64); a negative scalar flips the sign of its digits. Skewed columns (one-hot, binary:
+ * every point in one bucket) are cut into up to 16384 chunks per bucket. Same result conventions as jb_msm_g1. */
+int jb_msm_g1_small(jb_ctx* ctx, jb_srs bases, size_t offset, const void* scalars, size_t n, int kind,
+                    uint64_t out_xyz[12]);
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
 

@@ -12,6 +12,7 @@ from ._lib import JoltB200Error, load  # noqa: F401
 from .api import (  # noqa: F401
     HIGH_TO_LOW,
     LOW_TO_HIGH,
+    SCALAR_KINDS,
     BatchMember,
     EqPolynomial,
     EqProductMember,
@@ -29,6 +30,7 @@ from .api import (  # noqa: F401
     msm,
     prove_batch,
     prove_batch_native,
+    small_scalars,
 )
 
 DensePolynomial = Polynomial  # legacy name (jolt-prover-legacy/src/poly/dense_mlpoly.rs:20)

@@ -35,6 +35,9 @@ SIGNATURES = {
     "jb_table_clone": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_u64p]),
     "jb_table_free": (ctypes.c_int, [c_void_p, ctypes.c_uint64]),
     "jb_table_bind": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_u64p, ctypes.c_int]),
+    "jb_table_upload_small": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)]),
+    "jb_table_bind_small": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, ctypes.c_int, c_u64p, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_uint64)]),
     "jb_eq_evals": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p, c_u64p]),
     "jb_eq_evals_aligned_block": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_size_t, c_size_t, c_u64p]),
     "jb_member_create": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.c_int, ctypes.POINTER(c_void_p)]),
@@ -70,6 +73,7 @@ SIGNATURES = {
     "jb_srs_download_affine": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_u64p, c_size_t]),
     "jb_srs_free": (ctypes.c_int, [c_void_p, ctypes.c_uint64]),
     "jb_msm_g1": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_u64p, c_size_t, c_u64p]),
+    "jb_msm_g1_small": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_void_p, c_size_t, ctypes.c_int, c_u64p]),
     "jb_msm_g1_table": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, ctypes.c_uint64, c_size_t, c_u64p]),
     "jb_ctx_diag": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "jb_ctx_timing_enable": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_uint64]),

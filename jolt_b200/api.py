@@ -104,6 +104,37 @@ class Session:
         return out
 
 
+# jb_scalar_kind (include/jolt_b200.h): compact-table / small-scalar encodings
+SCALAR_KINDS = {"fr": 0, "u8": 1, "u16": 2, "u32": 3, "u64": 4, "u128": 5, "i64": 6, "i128": 7}
+_DTYPE_KIND = {np.dtype(np.uint8): "u8", np.dtype(np.bool_): "u8", np.dtype(np.uint16): "u16",
+               np.dtype(np.uint32): "u32", np.dtype(np.uint64): "u64", np.dtype(np.int64): "i64"}
+
+
+def small_scalars(values, kind: str | None = None) -> tuple[np.ndarray, int, int]:
+    """(contiguous byte-exact array, jb_scalar_kind, n) for a primitive integer column. `values`: a numpy
+    array of dtype bool/u8/u16/u32/u64/i64, or - for the 128-bit kinds - a sequence of Python ints with
+    `kind` = "u128" / "i128" (stored as 16 little-endian bytes each, two's complement)."""
+    if kind in ("u128", "i128"):
+        ints = [int(v) for v in values]
+        lo_hi = np.empty((len(ints), 2), dtype=np.uint64)
+        for i, v in enumerate(ints):
+            if kind == "u128" and not 0 <= v < 1 << 128:
+                raise ValueError("u128 value out of range")
+            if kind == "i128" and not -(1 << 127) <= v < 1 << 127:
+                raise ValueError("i128 value out of range")
+            w = v & ((1 << 128) - 1)
+            lo_hi[i, 0] = w & 0xFFFFFFFFFFFFFFFF
+            lo_hi[i, 1] = w >> 64
+        return lo_hi, SCALAR_KINDS[kind], len(ints)
+    a = np.ascontiguousarray(values)
+    name = _DTYPE_KIND.get(a.dtype)
+    if name is None or (kind is not None and kind != name):
+        raise ValueError(f"unsupported compact dtype {a.dtype} (kind={kind})")
+    if a.dtype == np.bool_:
+        a = a.astype(np.uint8)
+    return a.reshape(-1), SCALAR_KINDS[name], a.size
+
+
 class Polynomial:
     """Device-resident multilinear polynomial in evaluation form
     (jolt_poly::Polynomial<Fr>, dense.rs:35; legacy DensePolynomial, dense_mlpoly.rs:20)."""
@@ -125,6 +156,28 @@ class Polynomial:
     @classmethod
     def from_ints(cls, session: Session, values) -> "Polynomial":
         return cls.new(session, F.ints_to_limbs(values))
+
+    @classmethod
+    def from_small(cls, session: Session, values, kind: str | None = None) -> "Polynomial":
+        """Polynomial<T> for a primitive T (dense.rs:22-119) promoted to the field on the device
+        (jb_table_upload_small): F::from(T), i.e. v mod r with negatives as r - |v|."""
+        a, k, n = small_scalars(values, kind)
+        if n == 0 or n & (n - 1):
+            raise ValueError(f"Dense multi-linear polynomials must be made from a power of 2 (not {n})")
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_table_upload_small(session.h, a.ctypes.data_as(ctypes.c_void_p), n, k, ctypes.byref(h)))
+        return cls(session, h.value)
+
+    @classmethod
+    def bind_to_field(cls, session: Session, values, scalar, order: int = HIGH_TO_LOW, kind: str | None = None) -> "Polynomial":
+        """Polynomial<T>::bind_to_field (dense.rs:129-142): the compact table folded under `scalar` into a
+        new field polynomial of half the length (fused promote + bind, jb_table_bind_small)."""
+        a, k, n = small_scalars(values, kind)
+        r = _limbs(scalar)
+        h = ctypes.c_uint64()
+        session.check(session.lib.jb_table_bind_small(session.h, a.ctypes.data_as(ctypes.c_void_p), n, k, _p(r), order,
+                                                      ctypes.byref(h)))
+        return cls(session, h.value)
 
     @classmethod
     def wrap_device(cls, session: Session, device_ptr: int, length: int) -> "Polynomial":
@@ -546,6 +599,15 @@ class G1Bases:
         else:
             a = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
             self.s.check(self.s.lib.jb_msm_g1(self.s.h, self.handle, offset, _p(a) if a.shape[0] else None, a.shape[0], _p(out)))
+        return out
+
+    def msm_small(self, values, offset: int = 0, kind: str | None = None) -> np.ndarray:
+        """VariableBaseMSM::msm_u8 .. msm_i128 (crates/jolt-prover-legacy/src/msm/mod.rs:90-150): the
+        scalars are a primitive integer column (see small_scalars); 12 Jacobian limbs."""
+        a, k, n = small_scalars(values, kind)
+        out = np.zeros(12, dtype=np.uint64)
+        self.s.check(self.s.lib.jb_msm_g1_small(self.s.h, self.handle, offset,
+                                                a.ctypes.data_as(ctypes.c_void_p) if n else None, n, k, _p(out)))
         return out
 
     def msm_sharded(self, scalars, offset: int = 0) -> np.ndarray:

@@ -24,6 +24,7 @@
 
 #include "ctx.hpp"
 #include "ec.cuh"
+#include "small_scalar.cuh"
 
 using namespace jb;
 
@@ -38,11 +39,12 @@ struct MsmPlan {
     int T;        // segments per window
 };
 
-MsmPlan plan_with(int c) {
+// `bits`: width of the scalars' magnitudes (254 for Fr, 8..128 for the small-scalar kinds).
+MsmPlan plan_with(int c, int bits = 254) {
     MsmPlan p;
     p.c = c;
-    p.W = (254 + c - 1) / c;
-    if (254 - (p.W - 1) * c > c - 1) p.W += 1;  // top window: data < 2^(c-1), so data + carry <= 2^(c-1) = B
+    p.W = (bits + c - 1) / c;
+    if (bits - (p.W - 1) * c > c - 1) p.W += 1;  // top window: data < 2^(c-1), so data + carry <= 2^(c-1) = B
     p.B = 1 << (c - 1);
     p.T = (p.B + MSM_SEG - 1) / MSM_SEG;
     return p;
@@ -67,19 +69,23 @@ int shared_window_for(size_t srs_len) {
 // the running-sum reduction, and the serial tail of the sparsely populated top window (254 mod c bits):
 // its buckets hold n / 2^(bits-1) points each and are cut into at most 64 chunks, so one thread walks
 // max(64, cnt/64) points while the rest of the machine (~5 G adds/s vs ~7 M adds/s per thread) waits.
-MsmPlan plan_for(size_t n) {
+// Small-scalar kinds (bits < 254) search every window size: a u8 column wants ONE 9-bit window, a u64
+// column five 13-bit ones, whatever n is.
+MsmPlan plan_for(size_t n, int bits = 254) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) ++lg;
     int c0 = lg - 4;  // ~ 2^5 points per bucket
     double best = 0;
     int best_c = 0;
-    for (int c = c0 - 2; c <= c0 + 2; ++c) {
+    const bool small = bits < 254;
+    for (int c = small ? 4 : c0 - 2; c <= (small ? 16 : c0 + 2); ++c) {
         if (c < 4 || c > 16) continue;
-        MsmPlan p = plan_with(c);
-        int top_bits = 254 - (p.W - 1) * c;
+        MsmPlan p = plan_with(c, bits);
+        int top_bits = bits - (p.W - 1) * c;
         if (top_bits < 1) top_bits = 1;
         double cnt_top = (double)n / (double)((size_t)1 << (top_bits - 1));
         double chunk = cnt_top / 64.0 < 64.0 ? 64.0 : cnt_top / 64.0;
+        if (small && (double)n / (double)p.B / 64.0 > chunk) chunk = (double)n / (double)p.B / 64.0;
         double cost = (double)p.W * (double)n + 2.8 * (double)p.W * (double)p.B + 750.0 * chunk;
         if (best_c == 0 || cost < best) {
             best = cost;
@@ -87,15 +93,25 @@ MsmPlan plan_for(size_t n) {
         }
     }
     if (best_c == 0) best_c = c0 < 4 ? 4 : 16;
-    return plan_with(best_c);
+    return plan_with(best_c, bits);
 }
 
 // ---- 1. digits ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars, const uint64_t* bases, size_t n, int c,
+// `kind`: SK_FR = Montgomery Fr limbs; otherwise a primitive integer column (small_scalar.cuh) whose
+// magnitude is cut into digits and whose sign flips every digit (msm_u8 .. msm_i128 of the arkworks fork,
+// as called from crates/jolt-prover-legacy/src/msm/mod.rs:27-150).
+__global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, int kind, const uint64_t* bases, size_t n, int c,
                                                          int W, int B, int shared, uint32_t* digits, unsigned int* hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr k = fp_from_mont(ld_elem<Fr>(scalars, i));  // canonical integer limbs
+    Fr k;
+    uint32_t flip = 0;
+    if (kind == SK_FR) {
+        k = fp_from_mont(ld_elem<Fr>((const uint64_t*)scalars, i));  // canonical integer limbs
+    } else {
+        k = Fr::zero();
+        if (ld_small(scalars, i, kind, k.v)) flip = 0x80000000u;
+    }
     // identity bases contribute nothing
     bool skip = ld_elem<Fq>(bases, 2 * i).is_zero() && ld_elem<Fq>(bases, 2 * i + 1).is_zero();
     uint32_t carry = 0;
@@ -119,6 +135,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const uint64_t* scalars
             if (d) enc = d;
         }
         if (skip) enc = 0;
+        if (enc) enc ^= flip;
         digits[(size_t)w * n + i] = enc;
         if (enc) atomicAdd(&hist[(shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1)], 1u);
     }
@@ -134,13 +151,16 @@ constexpr unsigned MSM_MAX_CHUNKS = 64;
 
 // q = min(64, ceil(cnt / 64)) chunks of ceil(cnt / q) points: equal-sized chunks keep the lanes of a warp
 // in step (a 96-point bucket is 2 x 48, not 64 + 32).
-__device__ __forceinline__ unsigned chunk_count(unsigned cnt) {
+// maxq = MSM_MAX_CHUNKS for field scalars; the small-scalar kinds (a one-hot or binary column puts every
+// point into ONE bucket) raise it to MSM_MAX_CHUNKS_SMALL and fold wide buckets with a block per bucket.
+constexpr unsigned MSM_MAX_CHUNKS_SMALL = 16384;
+__device__ __forceinline__ unsigned chunk_count(unsigned cnt, unsigned maxq) {
     if (!cnt) return 0;
     unsigned q = (cnt + MSM_CHUNK - 1) / MSM_CHUNK;
-    return q > MSM_MAX_CHUNKS ? MSM_MAX_CHUNKS : q;
+    return q > maxq ? maxq : q;
 }
-__device__ __forceinline__ unsigned chunk_len(unsigned cnt) {
-    unsigned q = chunk_count(cnt);
+__device__ __forceinline__ unsigned chunk_len(unsigned cnt, unsigned maxq) {
+    unsigned q = chunk_count(cnt, maxq);
     return q ? (cnt + q - 1) / q : 1;
 }
 
@@ -182,7 +202,7 @@ __device__ __forceinline__ void block_exclusive_scan2(unsigned int& a, unsigned 
 }
 
 __global__ void __launch_bounds__(1024) msm_scan_local_kernel(unsigned int* hist, unsigned int* offsets, unsigned int* toff,
-                                                              size_t total, unsigned int* block_sums) {
+                                                              size_t total, unsigned int* block_sums, unsigned maxq) {
     __shared__ unsigned int sm_a[32], sm_b[32];
     const size_t base = (size_t)blockIdx.x * SCAN_PER_BLOCK + (size_t)threadIdx.x * 4;
     unsigned int c[4] = {0, 0, 0, 0};
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(1024) msm_scan_local_kernel(unsigned int* hist
         if (base + k < total) c[k] = hist[base + k];
     unsigned int q[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = chunk_count(c[k]);
+    for (int k = 0; k < 4; ++k) q[k] = chunk_count(c[k], maxq);
     unsigned int sa = c[0] + c[1] + c[2] + c[3], sb = q[0] + q[1] + q[2] + q[3], ta, tb;
     block_exclusive_scan2(sa, sb, sm_a, sm_b, ta, tb);
 #pragma unroll
@@ -270,12 +290,12 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bases, const uint32_t* sorted,
                                                              const unsigned int* offsets, const unsigned int* toff,
                                                              const uint32_t* task_bucket, size_t nbuckets,
-                                                             uint64_t* buckets, uint64_t* partial) {
+                                                             uint64_t* buckets, uint64_t* partial, unsigned maxq) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= toff[nbuckets]) return;
     const uint32_t b = task_bucket[t];
     const unsigned int base = offsets[b], cnt = offsets[b + 1] - base;
-    const unsigned int len = chunk_len(cnt), j = (unsigned int)t - toff[b];
+    const unsigned int len = chunk_len(cnt, maxq), j = (unsigned int)t - toff[b];
     unsigned int lo = base + j * len;
     unsigned int hi = lo + len < base + cnt ? lo + len : base + cnt;
     XYZZ acc = XYZZ::inf();
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const unsigned int* to
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nbuckets) return;
     unsigned int t0 = toff[b], t1 = toff[b + 1];
-    if (t1 - t0 == 1) return;
+    if (t1 - t0 == 1 || t1 - t0 > MSM_MAX_CHUNKS) return;  // wide buckets: msm_combine_wide_kernel
     XYZZ acc = XYZZ::inf();
     for (unsigned int t = t0; t < t1; ++t) xyzz_add(acc, ld_xyzz(partial, t));
     st_xyzz(buckets, b, acc);
@@ -360,6 +380,30 @@ __device__ __forceinline__ XYZZ smem_get(const uint32_t* sm, int tid) {
         p.zzz.v[w] = sm[(3 * 8 + w) * 256 + tid];
     }
     return p;
+}
+
+// Buckets cut into more than MSM_MAX_CHUNKS chunks (small-scalar kinds only): one block per bucket, a
+// strided pass over its partials and a shared-memory tree.
+__global__ void __launch_bounds__(256) msm_combine_wide_kernel(const unsigned int* toff, const uint64_t* partial,
+                                                               uint64_t* buckets) {
+    __shared__ uint32_t sm[32 * 256];
+    const size_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned int t0 = toff[b], t1 = toff[b + 1];
+    if (t1 - t0 <= MSM_MAX_CHUNKS) return;  // uniform over the block
+    XYZZ acc = XYZZ::inf();
+    for (unsigned int t = t0 + tid; t < t1; t += 256) xyzz_add(acc, ld_xyzz(partial, t));
+    smem_put(sm, tid, acc);
+    __syncthreads();
+    for (int half = 128; half > 0; half >>= 1) {
+        if (tid < half) {
+            XYZZ o = smem_get(sm, tid + half);
+            xyzz_add(acc, o);
+            smem_put(sm, tid, acc);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) st_xyzz(buckets, b, acc);
 }
 
 // ---- 6. per-window sum of the segment points: a multi-block tree (each block folds 2048 points of one
@@ -555,7 +599,10 @@ struct Guard {
 };
 
 // `srs`: the resident bases; terms are bases[offset .. offset + n).
-int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scalars, size_t n, uint64_t out_xyz[12]) {
+int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, size_t n, uint64_t out_xyz[12],
+               int kind = SK_FR) {
+    const int bits = small_kind_bits(kind);
+    const unsigned maxq = kind == SK_FR ? MSM_MAX_CHUNKS : MSM_MAX_CHUNKS_SMALL;
     // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
     // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
     // Small MSMs (the tail of HyperKZG's intermediate commitments, verifier-sized MSMs) use a second, tiny
@@ -563,7 +610,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
     const bool use_small = srs.pre_small != nullptr && n <= 4096 && offset + n <= srs.pre_small_len;
     const bool use_big = !use_small && srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
     const bool shared = use_small || use_big;
-    const MsmPlan p = use_small ? plan_with(8) : use_big ? plan_with(srs.pre_c) : plan_for(n);
+    const MsmPlan p = use_small ? plan_with(8, bits) : use_big ? plan_with(srs.pre_c, bits) : plan_for(n, bits);
     const size_t pre_stride = use_small ? srs.pre_small_len : srs.n;       // row w starts at w * stride
     const uint64_t* d_bases = srs.xy + 8 * offset;                          // digits: identity test, per-window path: gather
     const uint64_t* d_gather = use_small ? srs.pre_small + 8 * offset : use_big ? srs.pre + 8 * offset : d_bases;
@@ -594,17 +641,21 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const uint64_t* d_scala
     if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
-        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
-        msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums);
+        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
+        msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
         msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
         msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
-                                                                                      task_bucket, nb, buckets, partial);
+                                                                                      task_bucket, nb, buckets, partial, maxq);
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
+        if (maxq > MSM_MAX_CHUNKS) {
+            msm_combine_wide_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(toff, partial, buckets);
+            c->launches++;
+        }
         msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, seg);
         {   // tree-sum the T segment points of every bucket set, ping-ponging between two scratch buffers
             const uint64_t* src = seg;
@@ -834,6 +885,28 @@ int jb_msm_g1(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_
     if (st != JB_OK) return st;
     st = c->check(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, c->stream), "msm scalars H2D");
     if (st == JB_OK) st = msm_device(c, it->second, offset, d_s, n, out_xyz);
+    c->dev_free(d_s);
+    return st;
+}
+
+int jb_msm_g1_small(jb_ctx* c, jb_srs h, size_t offset, const void* scalars, size_t n, int kind, uint64_t out_xyz[12]) {
+    if (!c || !out_xyz || (n && !scalars)) return JB_ERR_INVALID;
+    if (kind < SK_U8 || kind > SK_I128) return c->fail(JB_ERR_INVALID, "msm_small: unknown scalar kind");
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    if (offset + n > it->second.n) return c->fail(JB_ERR_LENGTH, "msm: bases/scalars length mismatch");
+    if (n == 0) {
+        identity_xyz(out_xyz);
+        return JB_OK;
+    }
+    if (n >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm: n must be < 2^31");
+    void* d_s = nullptr;
+    const size_t bytes = n * (size_t)small_kind_bytes(kind);
+    int st = c->dev_alloc(&d_s, bytes);
+    if (st != JB_OK) return st;
+    st = c->check(cudaMemcpyAsync(d_s, scalars, bytes, cudaMemcpyHostToDevice, c->stream), "msm small scalars H2D");
+    if (st == JB_OK) st = msm_device(c, it->second, offset, d_s, n, out_xyz, kind);
     c->dev_free(d_s);
     return st;
 }

@@ -94,3 +94,23 @@ def test_engine_host_logic_matches_oracle_engine():
     assert [p.coefficients for p in got.round_polynomials] == want["round_polys"]
     with pytest.raises(jolt_b200.SumcheckError):
         jolt_b200.prove_batch([jolt_b200.BatchMember(**desc[0])], [_OracleMember(t_a)], 4, 2, total + 1, lambda r, p: 1)
+
+
+def test_small_scalar_encoding_host_side():
+    """jb_scalar_kind byte layouts (include/jolt_b200.h): dtype -> kind, 128-bit values as 16 LE bytes."""
+    import numpy as np
+    from jolt_b200 import SCALAR_KINDS, small_scalars
+
+    a, k, n = small_scalars(np.array([1, 0, 1], dtype=np.bool_))
+    assert (k, n, a.dtype) == (SCALAR_KINDS["u8"], 3, np.uint8)
+    a, k, n = small_scalars(np.array([-1, 2], dtype=np.int64))
+    assert (k, n) == (SCALAR_KINDS["i64"], 2) and a.tobytes() == (-1).to_bytes(8, "little", signed=True) + (2).to_bytes(8, "little")
+    a, k, n = small_scalars([-(1 << 127), -1, (1 << 127) - 1], "i128")
+    assert k == SCALAR_KINDS["i128"]
+    assert a.tobytes() == b"".join(v.to_bytes(16, "little", signed=True) for v in (-(1 << 127), -1, (1 << 127) - 1))
+    a, k, n = small_scalars([(1 << 128) - 1, 5], "u128")
+    assert a.tobytes() == ((1 << 128) - 1).to_bytes(16, "little") + (5).to_bytes(16, "little")
+    with pytest.raises(ValueError):
+        small_scalars([1 << 128], "u128")
+    with pytest.raises(ValueError):
+        small_scalars(np.zeros(2, dtype=np.float64))
