@@ -172,13 +172,16 @@ int jb_comm_destroy(jb_ctx* ctx);
  * If opening fails the NCCL path remains in force. */
 int jb_comm_p2p_handle(jb_ctx* ctx, uint8_t out[64]);
 int jb_comm_p2p_open(jb_ctx* ctx, const uint8_t* handles_world_x_64);
-/* An index-sharded ProveRounds member: this rank's m tables are the contiguous block `rank` of the
- * global tables (LowToHigh binding keeps every pair local). It reports log2(local len) + log2(nranks)
+/* An index-sharded ProveRounds member. `order` fixes the partition that keeps every (lo, hi) pair local
+ * (SURVEY 8e): JB_LOW_TO_HIGH pairs (2i, 2i+1) -> this rank's m tables are the CONTIGUOUS block `rank` of the
+ * global tables, local[j] = global[rank * n + j]; JB_HIGH_TO_LOW pairs (i, i + half) -> the STRIDED shard,
+ * local[j] = global[j * nranks + rank]. It reports log2(local len) + log2(nranks)
  * rounds and is driven by the same jb_member_prove_round / jb_prove_batch as a local member: each early
  * round costs ONE all-reduce of <= 40 u64; when a shard is 2^gather_log long the shards are
  * all-gathered once and every rank finishes the remaining rounds redundantly (identical results on all
  * ranks, identical to the single-GPU member over the global tables). `previous_claim` is the GLOBAL claim. */
-int jb_sharded_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, size_t gather_log, jb_member** out);
+int jb_sharded_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, int order, size_t gather_log,
+                             jb_member** out);
 
 /* ---- batched engine: jolt_sumcheck::prove_batch (crates/jolt-sumcheck/src/prover.rs:193-362) over
  *      device members, SequentialRounds traversal. BatchMember = batch.rs:24-71. The transcript stays

@@ -59,7 +59,7 @@ SIGNATURES = {
     "jb_comm_destroy": (ctypes.c_int, [c_void_p]),
     "jb_comm_p2p_handle": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint8)]),
     "jb_comm_p2p_open": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint8)]),
-    "jb_sharded_member_create": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_size_t, ctypes.POINTER(c_void_p)]),
+    "jb_sharded_member_create": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.c_int, c_size_t, ctypes.POINTER(c_void_p)]),
     "jb_member_destroy": (None, [c_void_p]),
     "jb_prove_batch": (ctypes.c_int, [ctypes.POINTER(c_void_p), c_void_p, c_size_t, c_size_t, c_size_t, c_u64p,
                                       ctypes.c_int, c_void_p, c_void_p, c_u64p, c_u64p, c_u64p, c_u64p,

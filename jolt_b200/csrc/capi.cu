@@ -1028,6 +1028,15 @@ int jb_eq_member_scalar(jb_member* mem, uint64_t out[4]) {
 }
 
 // ---- index-sharded member ----------------------------------------------------------------------
+// HighToLow shards are strided (rank g owns global[j * G + g]): gathered[g][j] -> global[j * G + g]
+static __global__ void __launch_bounds__(256) interleave_shards_kernel(const uint64_t* gathered, uint64_t* global, size_t len,
+                                                                       size_t G) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= len * G) return;
+    const size_t g = idx / len, j = idx % len;
+    st_elem(global, j * G + g, ld_elem<Fr>(gathered, idx));
+}
+
 static int gather_into_tail(jb_member* mem) {
     jb_ctx* c = mem->ctx;
     const size_t len = mem->len, G = (size_t)c->world;
@@ -1035,7 +1044,7 @@ static int gather_into_tail(jb_member* mem) {
     if (!tail) return JB_ERR_OOM;
     tail->ctx = c;
     tail->m = mem->m;
-    tail->order = JB_LOW_TO_HIGH;
+    tail->order = mem->order;
     tail->len = len * G;
     tail->rounds = 0;
     while (((size_t)1 << tail->rounds) < tail->len) ++tail->rounds;
@@ -1045,8 +1054,20 @@ static int gather_into_tail(jb_member* mem) {
         if (st != JB_OK) { delete tail; return st; }
         t.cap = t.len = tail->len;
         tail->tables.push_back(t);
-        // rank order == global order for contiguous blocks under LowToHigh binding
-        st = c->comm_allgather(mem->tables[j].buf, t.buf, len * 4);
+        if (mem->order == JB_LOW_TO_HIGH) {
+            // rank order == global order for contiguous blocks under LowToHigh binding
+            st = c->comm_allgather(mem->tables[j].buf, t.buf, len * 4);
+        } else {
+            uint64_t* tmp = nullptr;
+            st = c->dev_alloc((void**)&tmp, tail->len * 32);
+            if (st == JB_OK) st = c->comm_allgather(mem->tables[j].buf, tmp, len * 4);
+            if (st == JB_OK) {
+                interleave_shards_kernel<<<(unsigned)((tail->len + 255) / 256), 256, 0, c->stream>>>(tmp, t.buf, len, G);
+                c->launches++;
+                st = c->check(cudaGetLastError(), "interleave_shards launch");
+            }
+            c->dev_free(tmp);
+        }
         if (st != JB_OK) { delete tail; return st; }
     }
     mem->tail = tail;
@@ -1099,10 +1120,11 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
     return jb_member_prove_round(mem->tail, bind, mem->tail->rounds_done, claim, out_evals);
 }
 
-int jb_sharded_member_create(jb_ctx* c, const jb_table* handles, size_t m, size_t gather_log, jb_member** out) {
+int jb_sharded_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, size_t gather_log, jb_member** out) {
     if (!c || !out) return JB_ERR_INVALID;
     if (!c->nccl_comm) return c->fail(JB_ERR_INVALID, "sharded member: no communicator (jb_comm_init)");
-    int st = jb_member_create(c, handles, m, JB_LOW_TO_HIGH, out);
+    if (order != JB_LOW_TO_HIGH && order != JB_HIGH_TO_LOW) return c->fail(JB_ERR_INVALID, "sharded member: unknown binding order");
+    int st = jb_member_create(c, handles, m, order, out);
     if (st != JB_OK) return st;
     jb_member* mem = *out;
     size_t log_g = 0;

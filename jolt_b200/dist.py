@@ -3,7 +3,8 @@ for the plumbing) - SURVEY.md section 8e.
 
 Partitioning: LowToHigh binding pairs (2i, 2i+1) (crates/jolt-poly/src/dense.rs:236-238), so rank g
 owning the CONTIGUOUS global block [g*n, (g+1)*n) keeps every pair local while its shard is longer
-than one element. Per round each rank produces degree+1 partial sums (its fused bind+eval pass); they
+than one element; HighToLow pairs (i, i + half) (dense.rs:196-199), so rank g owns the STRIDED shard
+global[g::G] (`shard_of` below cuts either). Per round each rank produces degree+1 partial sums (its fused bind+eval pass); they
 leave the kernel as 8 x u64 lanes of 32-bit limbs, ONE integer all-reduce (ncclSum, exact) combines
 them, and the carry + mod-r fold happens on the O(degree) result. No table data crosses NVLink until
 the shards are tiny: at 2^GATHER_LOG entries per rank the bound shards are all-gathered once (rank
@@ -91,15 +92,24 @@ def init_comm(sess: Session, dist, p2p: bool = True) -> None:
             lib.jb_comm_p2p_open(sess.h, None)
 
 
+def shard_of(global_table, rank: int, world: int, order: int = LOW_TO_HIGH):
+    """This rank's share of a global table (any indexable with len and slicing) under the partition that
+    keeps `order`'s pairs local: the contiguous block for LowToHigh, the strided slice for HighToLow."""
+    n = len(global_table) // world
+    return global_table[rank * n:(rank + 1) * n] if order == LOW_TO_HIGH else global_table[rank::world]
+
+
 class ShardedProductMember(ProductMember):
-    """ProveRounds member over this rank's contiguous block of the global tables (jb_sharded_member_create).
+    """ProveRounds member over this rank's shard of the global tables (jb_sharded_member_create): the
+    contiguous block under LowToHigh, the strided slice under HighToLow.
     Reports log2(local) + log2(world) rounds; `previous_claim` is the global claim."""
 
-    def __init__(self, session: Session, polys: list[Polynomial], gather_log: int = GATHER_LOG):
+    def __init__(self, session: Session, polys: list[Polynomial], gather_log: int = GATHER_LOG, order: int = LOW_TO_HIGH):
         self.s = session
         handles = np.array([p.handle for p in polys], dtype=np.uint64)
         h = ctypes.c_void_p()
-        session.check(session.lib.jb_sharded_member_create(session.h, _p(handles), len(polys), gather_log, ctypes.byref(h)))
+        session.check(session.lib.jb_sharded_member_create(session.h, _p(handles), len(polys), order, gather_log,
+                                                           ctypes.byref(h)))
         for p in polys:
             p.handle = 0
         self.h = h
@@ -121,10 +131,10 @@ def sharded_claim(sess: Session, polys: list[Polynomial], dist) -> int:
 
 
 def prove_sharded(sess: Session, polys: list[Polynomial], claim: int, seed: int, gather_log: int = GATHER_LOG,
-                  raw: bool = False):
+                  raw: bool = False, order: int = LOW_TO_HIGH):
     """One index-sharded product sumcheck through the C++ engine (jb_prove_batch): no Python in the
     round loop. Returns (ProvedBatch, final_evals); identical on every rank."""
-    mem = ShardedProductMember(sess, polys, gather_log)
+    mem = ShardedProductMember(sess, polys, gather_log, order)
     rounds = mem.num_rounds()
     res = prove_batch_native([BatchMember(claim, 1, rounds, 0)], [mem], rounds, mem.m, claim, seed=seed, raw=raw)
     fe = mem.final_evals(raw=raw)

@@ -13,7 +13,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, log_n_local, m, q, p2p=True):
+def _worker(rank, world, port, log_n_local, m, q, p2p=True, order=1):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import torch
@@ -22,18 +22,18 @@ def _worker(rank, world, port, log_n_local, m, q, p2p=True):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     import jolt_b200
     from jolt_b200 import LOW_TO_HIGH, Polynomial, ProductMember
-    from jolt_b200.dist import init_comm, prove_sharded, sharded_claim
+    from jolt_b200.dist import init_comm, prove_sharded, shard_of, sharded_claim
     from oracle.coracle import rand_limbs
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     sess = jolt_b200.Session(rank, cuda_stream=stream.cuda_stream)
     n = 1 << log_n_local
     glob = [rand_limbs(900 + j, n * world) for j in range(m)]
-    shard = [g[rank * n:(rank + 1) * n] for g in glob]          # contiguous block per rank
+    shard = [shard_of(g, rank, world, order) for g in glob]      # contiguous block (l2h) / strided slice (h2l)
     init_comm(sess, dist, p2p=p2p)
     polys = [Polynomial.new(sess, s) for s in shard]
     claim = sharded_claim(sess, polys, dist)
-    res, fe = prove_sharded(sess, polys, claim, seed=11, gather_log=6)
+    res, fe = prove_sharded(sess, polys, claim, seed=11, gather_log=6, order=order)
     # term-sharded MSM: rank g holds bases (g*n + i + 1) * G and its slice of the scalars
     from jolt_b200 import G1Bases, g1_jacobian_to_affine
     from oracle import bn254 as O
@@ -48,10 +48,11 @@ def _worker(rank, world, port, log_n_local, m, q, p2p=True):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("log_n_local,m,p2p", [(10, 2, True), (9, 3, True), (10, 2, False)])
-def test_sharded_equals_single_gpu(log_n_local, m, p2p):
+@pytest.mark.parametrize("log_n_local,m,p2p,order", [(10, 2, True, 1), (9, 3, True, 0), (10, 2, False, 1), (10, 2, False, 0)])
+def test_sharded_equals_single_gpu(log_n_local, m, p2p, order):
     """p2p=True: the per-round all-reduce runs inside the round kernel over NVLink peer memory;
-    p2p=False: ncclAllReduce. Both must reproduce the single-GPU proof exactly."""
+    p2p=False: ncclAllReduce. order 1 = LowToHigh (contiguous blocks), 0 = HighToLow (strided shards).
+    All must reproduce the single-GPU proof of the same global polynomial exactly."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -64,7 +65,7 @@ def test_sharded_equals_single_gpu(log_n_local, m, p2p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, log_n_local, m, q, p2p)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, log_n_local, m, q, p2p, order)) for r in range(world)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=300) for _ in procs])
@@ -76,10 +77,10 @@ def test_sharded_equals_single_gpu(log_n_local, m, p2p):
     sess = jolt_b200.Session(0)
     n = (1 << log_n_local) * world
     glob = [rand_limbs(900 + j, n) for j in range(m)]
-    probe = ProductMember(sess, [Polynomial.new(sess, g) for g in glob], LOW_TO_HIGH)
+    probe = ProductMember(sess, [Polynomial.new(sess, g) for g in glob], order)
     ev = probe.prove_round_evals(None, 0)
     claim = (ev[0] + ev[1]) % F.R_MOD
-    mem = ProductMember(sess, [Polynomial.new(sess, g) for g in glob], LOW_TO_HIGH)
+    mem = ProductMember(sess, [Polynomial.new(sess, g) for g in glob], order)
     L = log_n_local + 1
     one = jolt_b200.prove_batch_native([BatchMember(claim, 1, L, 0)], [mem], L, m, claim, seed=11)
     assert outs[0][1] == one.challenges and outs[0][2] == one.final_claim
