@@ -30,7 +30,7 @@ def sess():
 @pytest.fixture(scope="module")
 def srs_bases():
     beta = C.ints_to_mont([O.random_fr(0x4D534D, 1)[0]])[0]
-    return C.g1_powers(1 << 12, G, beta)
+    return C.g1_powers(1 << 13, G, beta)
 
 
 def column(kind: str, n: int, seed: int) -> list[int]:
@@ -149,3 +149,13 @@ def test_msm_small_with_precomputed_srs_and_offsets(sess, srs_bases):
     with pytest.raises(jolt_b200.JoltB200Error, match="length mismatch"):
         bases.msm_small(np.zeros(n + 1, dtype=np.uint8))
     bases.free()
+    # n > 4096 on a precomputed handle: the shared-bucket path (one bucket set, 9-bit windows) with few windows
+    n = 1 << 13
+    big = G1Bases.from_affine(sess, srs_bases[:n]).precompute(9)
+    for kind in ("u16", "i64", "i128"):
+        vals = column(kind, n, 41)
+        a, k = as_input(kind, vals)
+        sc = C.ints_to_mont([v % O.R_MOD for v in vals])
+        want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+        assert g1_jacobian_to_affine(big.msm_small(a, kind=k)) == want, kind
+    big.free()

@@ -51,6 +51,25 @@ for lg in sizes:
         C.g1_msm_pippenger(xy, sc, 0, C.max_threads())
         rec["cpu_ms"] = round((time.perf_counter() - t0) * 1e3, 1)
         rec["cpu_cores"] = C.max_threads()
+    if "--small" in sys.argv:
+        # primitive-integer columns (legacy msm_u8 .. msm_i64): host scalars, so each time includes the H2D of
+        # 1..8 B/term; checked against the same closed form over the integers
+        rng = np.random.default_rng(lg)
+        cols = {"u8": rng.integers(0, 256, size=n, dtype=np.uint8), "binary": rng.integers(0, 2, size=n).astype(np.uint8),
+                "u16": rng.integers(0, 1 << 16, size=n, dtype=np.uint16), "u32": rng.integers(0, 1 << 32, size=n, dtype=np.uint32),
+                "u64": rng.integers(0, 1 << 64, size=n, dtype=np.uint64), "i64": rng.integers(-(1 << 63), 1 << 63, size=n, dtype=np.int64)}
+        small = {}
+        for name, col in cols.items():
+            r0 = bases.msm_small(col)
+            wsum = int((col.astype(object) * np.arange(1, n + 1, dtype=object)).sum()) % O.R_MOD if n <= (1 << 20) else None
+            good = wsum is None or g1_jacobian_to_affine(r0) == O.g1_scalar_mul(O.G1_GEN, wsum)
+            tt = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                bases.msm_small(col)
+                tt.append(time.perf_counter() - t0)
+            small[name] = dict(ms=round(min(tt) * 1e3, 3), ok=bool(good))
+        rec["small"] = small
     print(json.dumps(rec), flush=True)
     out.append(rec)
     bases.free(); tab.free()
