@@ -100,22 +100,29 @@ MsmPlan plan_for(size_t n, int bits = 254) {
 // `kind`: SK_FR = Montgomery Fr limbs; otherwise a primitive integer column (small_scalar.cuh) whose
 // magnitude is cut into digits and whose sign flips every digit (msm_u8 .. msm_i128 of the arkworks fork,
 // as called from crates/jolt-prover-legacy/src/msm/mod.rs:27-150).
+// AGG: equal slots within a warp are counted by ONE atomic (match.any) - witness columns are skewed
+// (binary, one-hot, constants: millions of points in one bucket), and same-address atomics serialise.
+template <bool AGG>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, int kind, const uint64_t* bases, size_t n, int c,
                                                          int W, int B, int shared, uint32_t* digits, unsigned int* hist) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr k;
+    const bool valid = i < n;
+    if (!AGG && !valid) return;
+    Fr k = Fr::zero();
     uint32_t flip = 0;
-    if (kind == SK_FR) {
-        k = fp_from_mont(ld_elem<Fr>((const uint64_t*)scalars, i));  // canonical integer limbs
-    } else {
-        k = Fr::zero();
-        if (ld_small(scalars, i, kind, k.v)) flip = 0x80000000u;
+    bool skip = true;
+    if (valid) {
+        if (kind == SK_FR) {
+            k = fp_from_mont(ld_elem<Fr>((const uint64_t*)scalars, i));  // canonical integer limbs
+        } else {
+            if (ld_small(scalars, i, kind, k.v)) flip = 0x80000000u;
+        }
+        // identity bases contribute nothing
+        skip = ld_elem<Fq>(bases, 2 * i).is_zero() && ld_elem<Fq>(bases, 2 * i + 1).is_zero();
     }
-    // identity bases contribute nothing
-    bool skip = ld_elem<Fq>(bases, 2 * i).is_zero() && ld_elem<Fq>(bases, 2 * i + 1).is_zero();
     uint32_t carry = 0;
     const uint32_t mask = (1u << c) - 1u;
+    const int lane = threadIdx.x & 31;
     for (int w = 0; w < W; ++w) {
         int bit = w * c;
         int word = bit >> 5, off = bit & 31;
@@ -136,8 +143,17 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, in
         }
         if (skip) enc = 0;
         if (enc) enc ^= flip;
-        digits[(size_t)w * n + i] = enc;
-        if (enc) atomicAdd(&hist[(shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1)], 1u);
+        if (valid) digits[(size_t)w * n + i] = enc;
+        const size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
+        if (AGG) {
+            const unsigned m = __ballot_sync(0xffffffffu, enc != 0);
+            if (enc) {
+                const unsigned peers = __match_any_sync(m, (unsigned)slot);
+                if (lane == __ffs(peers) - 1) atomicAdd(&hist[slot], (unsigned)__popc(peers));
+            }
+        } else {
+            if (enc) atomicAdd(&hist[slot], 1u);
+        }
     }
 }
 
@@ -270,16 +286,32 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* toff
 // ---- 3. scatter -----------------------------------------------------------------------------------
 // `shared`: all windows feed one bucket set and the entry addresses the precomputed table row of its
 // window (w * stride + i); otherwise one bucket set per window and the entry is the point index.
+template <bool AGG>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B, int shared,
                                                           size_t stride, const unsigned int* offsets, unsigned int* cursor,
                                                           uint32_t* sorted) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool valid = i < n;
+    if (!AGG && !valid) return;
+    const int lane = threadIdx.x & 31;
     for (int w = 0; w < W; ++w) {
-        uint32_t enc = digits[(size_t)w * n + i];
-        if (!enc) continue;
-        size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
-        unsigned int pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
+        uint32_t enc = valid ? digits[(size_t)w * n + i] : 0u;
+        const size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
+        unsigned int pos;
+        if (AGG) {
+            // one atomic per distinct slot in the warp; lanes take consecutive positions in lane order
+            const unsigned m = __ballot_sync(0xffffffffu, enc != 0);
+            if (!enc) continue;
+            const unsigned peers = __match_any_sync(m, (unsigned)slot);
+            const int leader = __ffs(peers) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[slot], (unsigned)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            pos = offsets[slot] + base + (unsigned)__popc(peers & ((1u << lane) - 1u));
+        } else {
+            if (!enc) continue;
+            pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
+        }
         sorted[pos] = (uint32_t)(shared ? (size_t)w * stride + i : i) | (enc & 0x80000000u);
     }
 }
@@ -641,11 +673,18 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
-        msm_digits_kernel<<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
+        const bool agg = kind != SK_FR;
+        if (agg)
+            msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
+        else
+            msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
-        msm_scatter_kernel<<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
+        if (agg)
+            msm_scatter_kernel<true><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
+        else
+            msm_scatter_kernel<false><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
         int tix = c->timing_begin(4, n, p.c);
         msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
