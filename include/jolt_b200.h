@@ -263,7 +263,8 @@ int jb_hyperkzg_open(jb_ctx* ctx, jb_srs srs, jb_table evals, const uint64_t* po
                      uint64_t* out_com, uint64_t* out_w, uint64_t* out_v);
 
 /* ---- raw element-wise ops (parity harness for bn254_differential.rs:75-99) -----------------
- * field: 0 = Fr, 1 = Fq; op: 0 add, 1 sub, 2 mul, 3 mul-by-[0,0,lo,hi]. Host buffers. */
+ * field: 0 = Fr, 1 = Fq; op: 0 add, 1 sub, 2 mul, 3 mul-by-[0,0,lo,hi], 4 neg(a), 5 square(a) (b ignored
+ * for 4 and 5 but must be a valid buffer). Host buffers. */
 int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 
 /* ---- observability (specs/clean-slate-prover.md:585-587 asks device backends for device-event

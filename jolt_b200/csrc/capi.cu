@@ -1309,7 +1309,7 @@ void jb_member_destroy(jb_member* mem) {
 
 // ---- element-wise parity harness ---------------------------------------------------------------
 int jb_vec_op(jb_ctx* c, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
-    if (!c || !a || !b || !out || op < 0 || op > 3 || (field != 0 && field != 1)) return JB_ERR_INVALID;
+    if (!c || !a || !b || !out || op < 0 || op > 5 || (field != 0 && field != 1)) return JB_ERR_INVALID;
     if (n == 0) return JB_OK;
     Guard g(c);
     uint64_t *da = nullptr, *db = nullptr, *dd = nullptr;

@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(256) eq_stream_kernel(const uint64_t* prefix, 
 }
 
 // ---- element-wise helpers (tests + host glue) --------------------------------------------------
-// op: 0 add, 1 sub, 2 mul (Montgomery), 3 mul with b's 4 low words zero (hi4 path)
+// op: 0 add, 1 sub, 2 mul (Montgomery), 3 mul with b's 4 low words zero (hi4 path), 4 neg(a), 5 square(a)
 template <class F>
 __global__ void vec_op_kernel(const uint64_t* a, const uint64_t* b, uint64_t* o, size_t n, int op) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -760,7 +760,9 @@ __global__ void vec_op_kernel(const uint64_t* a, const uint64_t* b, uint64_t* o,
     if (op == 0) z = fp_add(x, y);
     else if (op == 1) z = fp_sub(x, y);
     else if (op == 2) z = fp_mul(x, y);
-    else z = fp_mul_hi4(x, y.v + 4);
+    else if (op == 3) z = fp_mul_hi4(x, y.v + 4);
+    else if (op == 4) z = fp_neg(x);
+    else z = fp_sqr(x);
     st_elem(o, i, z);
 }
 

@@ -31,6 +31,9 @@ def test_vec_ops_bit_exact(sess, fld, p):
         got = sess.vec_op(fld, op, a, b)
         want = C.f_vec(fld, op, a, b)
         assert (got == want).all(), f"field {fld} op {op}: {(got != want).any(axis=1).sum()} mismatches"
+    # neg and square (bn254_differential.rs:75-99 also pins these): -a == 0 - a, a^2 == a * a
+    assert (sess.vec_op(fld, 4, a, b) == C.f_vec(fld, 1, np.zeros_like(a), a)).all()
+    assert (sess.vec_op(fld, 5, a, b) == C.f_vec(fld, 2, a, a)).all()
 
 
 def test_mul_by_challenge_limbs(sess):
