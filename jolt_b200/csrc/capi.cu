@@ -996,6 +996,7 @@ int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint
         *out = nullptr;
         return c->fail(JB_ERR_INVALID, "eq member: point length must equal log2(table length) >= 1");
     }
+    {
     Guard g(c);
     mem->eq = true;
     mem->eq_n = nvars;
@@ -1013,6 +1014,7 @@ int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint
         st = eq_build(c, w, k, nullptr, mem->eq_tabs + 4 * (((size_t)1 << k) - 1));
     for (size_t k = 0; k <= nin && st == JB_OK; ++k)
         st = eq_build(c, w + 4 * split, k, nullptr, mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << k) - 1));
+    }  // the context lock is released before the member is torn down (jb_member_destroy takes it)
     if (st != JB_OK) {
         jb_member_destroy(mem);
         *out = nullptr;
@@ -1037,7 +1039,7 @@ static __global__ void __launch_bounds__(256) interleave_shards_kernel(const uin
     st_elem(global, j * G + g, ld_elem<Fr>(gathered, idx));
 }
 
-static int gather_into_tail(jb_member* mem) {
+static int gather_into_tail(jb_member* mem) {  // called with the context lock held
     jb_ctx* c = mem->ctx;
     const size_t len = mem->len, G = (size_t)c->world;
     jb_member* tail = new (std::nothrow) jb_member();
@@ -1048,12 +1050,13 @@ static int gather_into_tail(jb_member* mem) {
     tail->len = len * G;
     tail->rounds = 0;
     while (((size_t)1 << tail->rounds) < tail->len) ++tail->rounds;
-    for (int j = 0; j < mem->m; ++j) {
+    int st = JB_OK;
+    for (int j = 0; j < mem->m && st == JB_OK; ++j) {
         Table t;
-        int st = c->dev_alloc((void**)&t.buf, tail->len * 32);
-        if (st != JB_OK) { delete tail; return st; }
+        st = c->dev_alloc((void**)&t.buf, tail->len * 32);
+        if (st != JB_OK) break;
         t.cap = t.len = tail->len;
-        tail->tables.push_back(t);
+        tail->tables.push_back(t);  // owned by the tail from here on (released below on failure)
         if (mem->order == JB_LOW_TO_HIGH) {
             // rank order == global order for contiguous blocks under LowToHigh binding
             st = c->comm_allgather(mem->tables[j].buf, t.buf, len * 4);
@@ -1068,7 +1071,11 @@ static int gather_into_tail(jb_member* mem) {
             }
             c->dev_free(tmp);
         }
-        if (st != JB_OK) { delete tail; return st; }
+    }
+    if (st != JB_OK) {
+        for (auto& t : tail->tables) c->release(t);
+        delete tail;
+        return st;
     }
     mem->tail = tail;
     return JB_OK;
