@@ -426,6 +426,16 @@ def run_ours(args):
             pass
         kernel_ms = sum(t["ms"] for t in timed) / K
         roof["timed_kernels_share_of_step"] = kernel_ms / ms_per_step
+        # every timed streaming pass of a step (CUDA events on the launching stream, averaged over the K steps):
+        # algorithmic bytes = m x 64 B read per pair (eval-only) or m x 192 B per pair (bind + eval: 4 reads, 2 writes)
+        groups = {}
+        for t in timed:
+            groups.setdefault((t["kind"], t["items"]), []).append(t["ms"])
+        roof["passes"] = [
+            {"kind": k, "pairs": it, "avg_ms": sum(v) / len(v),
+             "gb_per_s": (m * (192 if k == "fused_bind_eval" else 64) * it) / (sum(v) / len(v) * 1e-3) / 1e9,
+             "frac_of_peak": (m * (192 if k == "fused_bind_eval" else 64) * it) / (sum(v) / len(v) * 1e-3) / 1e9 / peak}
+            for (k, it), v in sorted(groups.items(), key=lambda kv: -kv[0][1]) if k in ("fused_bind_eval", "eval_only")]
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
