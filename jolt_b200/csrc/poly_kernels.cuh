@@ -295,10 +295,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
     }
 
     size_t stride = (size_t)gridDim.x * blockDim.x;
+    // Eval-only passes (no bind) have registers to spare: the NEXT iteration's pair is loaded into registers
+    // before the current one is multiplied (software pipelining), so the DRAM latency of an iteration hides
+    // behind the previous iteration's arithmetic instead of behind other warps - there are only 16 per SM.
+    // (ptxas sinks the L2 prefetch below to the end of the loop body, so on its own it buys no lead time.)
+    constexpr bool PIPE = !BIND && (M == 1 || (M == 2 && SKIP1));
+    Fr nlo[PIPE ? M : 1], nhi[PIPE ? M : 1];
+    if (PIPE) {
+        const size_t y0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (y0 < pairs) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                if (ORDER == ORDER_HIGH_TO_LOW) {
+                    nlo[j] = ld_elem<Fr>(tp.in[j], y0);
+                    nhi[j] = ld_elem<Fr>(tp.in[j], y0 + pairs);
+                } else {
+                    nlo[j] = ld_elem<Fr>(tp.in[j], 2 * y0);
+                    nhi[j] = ld_elem<Fr>(tp.in[j], 2 * y0 + 1);
+                }
+            }
+        }
+    }
     for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
-        // prefetch the next iteration's lines into L2 (ncu: long-scoreboard was the top stall)
-        if (y + stride < pairs) {
-            const size_t yn = y + stride;
+        // prefetch the lines of a later iteration into L2 (ncu: long-scoreboard was the top stall)
+        const size_t yp = y + (PIPE ? 2 : 1) * stride;
+        if (yp < pairs) {
+            const size_t yn = yp;
 #pragma unroll
             for (int j = 0; j < M; ++j) {
                 if (ORDER == ORDER_HIGH_TO_LOW) {
@@ -314,8 +336,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
             }
         }
         Fr lo[M], hi[M];
+        if (PIPE) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                lo[j] = nlo[j];
+                hi[j] = nhi[j];
+            }
+            const size_t yn = y + stride;
+            if (yn < pairs) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    if (ORDER == ORDER_HIGH_TO_LOW) {
+                        nlo[j] = ld_elem<Fr>(tp.in[j], yn);
+                        nhi[j] = ld_elem<Fr>(tp.in[j], yn + pairs);
+                    } else {
+                        nlo[j] = ld_elem<Fr>(tp.in[j], 2 * yn);
+                        nhi[j] = ld_elem<Fr>(tp.in[j], 2 * yn + 1);
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < M; ++j) {
+            if (PIPE) break;
             if (BIND) {
                 Fr a, b, c, d;
                 if (ORDER == ORDER_HIGH_TO_LOW) {
