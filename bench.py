@@ -418,7 +418,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms, "launches_timed": len(big),
                 "traffic": None}
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-            tr = json.load(open(ROOT / "profiles" / "r01_final_traffic.json"))
+            tr = json.load(open(ROOT / "profiles" / "r01b_traffic.json"))
             if args.log_n == 22 and m == 2 and args.order == "l2h":
                 roof["traffic"] = tr["fused_round_kernel m=2 l2h 2^22"]["traffic"]
                 roof["traffic_source"] = tr["source"]
