@@ -442,10 +442,46 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
         }
     }
     Fr acc[K];
+    if (M == 1) {
 #pragma unroll
-    for (int e = 0; e < K; ++e)
-        acc[e] = (M == 1) ? sum1[e] : reduce_wide17<FrParams>(wacc + (e * 17) * BLOCK + tid, BLOCK);
-    block_sum<K>(acc, red);
+        for (int e = 0; e < K; ++e) acc[e] = sum1[e];
+        block_sum<K>(acc, red);
+    } else {
+        // Block sum of the wide accumulators BEFORE the Montgomery reduction: the K x 17 word columns are summed
+        // over the block's threads as plain integers (a column sum is < 2^40; the block total stays far below
+        // 2^544: at most pairs / gridDim.x products of < 2^512 each), then lane e of warp 0 propagates the carries
+        // of value e and reduces ONCE. One reduction per block instead of one per thread: the per-thread
+        // reductions were ~13 % of the instructions a pass issued (ncu, profiles/r01b_ncu_fused_round_kernels.md).
+        uint64_t* colsum = reinterpret_cast<uint64_t*>(red);  // K * 17 u64 <= the 8 * K * 8 words of scratch
+        const int lane = tid & 31, warp = tid >> 5, nwarps = (int)blockDim.x >> 5;
+        __syncthreads();
+        for (int c = warp; c < K * 17; c += nwarps) {
+            uint64_t sacc = 0;
+            for (int t = lane; t < (int)blockDim.x; t += 32) sacc += wacc[c * BLOCK + t];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sacc += __shfl_down_sync(0xffffffffu, sacc, off);
+            if (lane == 0) colsum[c] = sacc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            Fr mine = Fr::zero();
+            if (lane < K) {
+                uint32_t T[17];
+                uint64_t carry = 0;
+#pragma unroll
+                for (int w = 0; w < 17; ++w) {
+                    const uint64_t t = colsum[lane * 17 + w] + carry;
+                    T[w] = (uint32_t)t;
+                    carry = t >> 32;
+                }
+                mine = reduce_wide17<FrParams>(T, 1);
+            }
+#pragma unroll
+            for (int e = 0; e < K; ++e)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) acc[e].v[w] = __shfl_sync(0xffffffffu, mine.v[w], e);
+        }
+    }
     __syncthreads();  // scratch is reused by the last block's fold
     round_epilogue<K>(acc, red, out);
 }
