@@ -1,0 +1,89 @@
+"""Known-answer tests the reference holds for the host side of the path, replayed against BOTH the oracle
+(oracle/bn254.py) and the product's host mirror (jolt_b200.UnivariatePoly) - no GPU needed. The numbers are the
+reference's own (file:line in each test); nothing here was generated."""
+import pytest
+
+import jolt_b200
+from jolt_b200 import UnivariatePoly
+from oracle import bn254 as O
+
+R = O.R_MOD
+
+
+def test_horner_known_polynomial():
+    # crates/jolt-poly/src/univariate.rs:563-569: p(x) = 3 + 2x + x^2
+    c = [3, 2, 1]
+    for x, want in ((0, 3), (1, 6), (2, 11)):
+        assert O.uni_evaluate(c, x) == want
+        assert UnivariatePoly(c).evaluate(x) == want
+
+
+def test_from_evals_quadratic_and_cubic():
+    # univariate.rs:848-855: p(0)=1, p(1)=6, p(2)=15 -> 2x^2 + 3x + 1
+    assert O.uni_from_evals([1, 6, 15]) == [1, 3, 2]
+    assert UnivariatePoly.from_evals([1, 6, 15]).coefficients == [1, 3, 2]
+    # univariate.rs:858-871: x^3 + 2x^2 + 3x + 1
+    assert O.uni_from_evals([1, 7, 23, 55]) == [1, 3, 2, 1]
+    assert UnivariatePoly.from_evals([1, 7, 23, 55]).coefficients == [1, 3, 2, 1]
+
+
+def test_from_evals_and_hint():
+    # univariate.rs:895-906: hint = p(0) + p(1) = 7, evals at [0, 2] = [1, 15] -> p(1) = 6
+    for poly_eval in (lambda x: O.uni_evaluate(O.uni_from_evals_and_hint(7, [1, 15]), x),
+                      lambda x: UnivariatePoly.from_evals_and_hint(7, [1, 15]).evaluate(x)):
+        assert [poly_eval(x) for x in (0, 1, 2)] == [1, 6, 15]
+
+
+def test_compress_then_evaluate_with_hint():
+    # univariate.rs:694-702: p = 1 + 3x + 2x^2; the compressed form drops the linear term, the hint restores it
+    p = [1, 3, 2]
+    hint = (O.uni_evaluate(p, 0) + O.uni_evaluate(p, 1)) % R
+    for compressed in (O.uni_compress(p), UnivariatePoly(p).compress()):
+        assert compressed == [1, 2]
+        c0, rest = compressed[0], compressed[1:]
+        linear = (hint - 2 * c0 - sum(rest)) % R          # CompressedPoly::evaluate_with_hint
+        assert O.uni_evaluate([c0, linear] + rest, 5) == O.uni_evaluate(p, 5) == 66
+
+
+def test_kzg_eval_univariate_kats():
+    # crates/jolt-hyperkzg/src/kzg.rs:253-264
+    assert O.eval_univariate([42, 7, 3], 0) == 42
+    assert O.eval_univariate([3, 5], 2) == 13
+
+
+def test_kzg_witness_polynomial_division():
+    # kzg.rs:229-251: f = 1 + 2x + 3x^2 + 4x^3, u = 2, f(2) = 49; (x - u) h(x) + f(u) == f(x)
+    f, u = [1, 2, 3, 4], 2
+    h = O.compute_witness_polynomial(f, u)
+    assert O.eval_univariate(f, u) == 49
+    assert h == [24, 11, 4]                                # synthetic division by (x - 2)
+    for x in (0, 1, 3, 5, 100):
+        assert O.eval_univariate(f, x) == ((x - u) * O.eval_univariate(h, x) + 49) % R
+
+
+def test_small_scalar_accumulator_kat():
+    # crates/jolt-field/src/bn254/mont.rs:663-676: 3*16 + 5*(-7) + 11 + 9*(-13) + 2*7 == -79
+    terms = [(3, 16), (5, -7), (11, 1), (9, -13), (2, 7)]
+    total = sum(O.fr_from_u64(a) * O.fr_from_i64(s) for a, s in terms) % R
+    assert total == (-79) % R == R - 79
+
+
+def test_constant_polynomial_sumcheck_kats():
+    # crates/jolt-sumcheck/tests/soundness.rs:440-462: f = 7 on {0,1}^3 -> sum 56, final evaluation 7 whatever the point
+    evals = [7] * 8
+    assert sum(evals) % R == 56
+    point = O.synthetic_point(3, 401)
+    assert O.evaluate(evals, point) == 7
+    mem = O.ProductMember([evals], O.HIGH_TO_LOW)
+    claim, bind = 56, None
+    for rnd in range(3):
+        coeffs = mem.prove_round(bind, rnd, claim)
+        assert (O.uni_evaluate(coeffs, 0) + O.uni_evaluate(coeffs, 1)) % R == claim
+        bind = point[rnd]
+        claim = O.uni_evaluate(coeffs, bind)
+    mem.finish_rounds(bind)
+    assert mem.final_evals() == [7] and claim == 7
+    # soundness.rs:395-408: zero rounds -> the claimed sum is returned as the evaluation
+    res = O.prove_batch([dict(input_claim=42, coefficient=1, rounds=0, offset=0)], [O.ProductMember([[42]], O.HIGH_TO_LOW)],
+                        0, 1, 42, lambda r, c: 1)
+    assert res["final_claim"] == 42 and res["round_polys"] == []
