@@ -218,3 +218,29 @@ def test_sumcheck_2pow22_first_rounds_vs_c_oracle(sess):
     gpu.finish_rounds(bind)
     fe = gpu.final_evals()
     assert fe[0] * fe[1] % O.R_MOD == claim
+
+
+def test_constant_polynomial_known_answers(sess):
+    # crates/jolt-sumcheck/tests/soundness.rs:440-462: f = 7 on {0,1}^3 -> sum 56, final evaluation 7 at ANY point;
+    # every round polynomial of a constant table is itself constant: s_k(X) = 7 * 2^(2-k)
+    for order in (HIGH_TO_LOW, LOW_TO_HIGH):
+        gpu = run_lockstep(sess, [[7] * 8], order, O.random_fr(9, 3))
+        assert gpu.final_evals() == [7]
+    gpu = ProductMember(sess, [Polynomial.from_ints(sess, [7] * 8)], HIGH_TO_LOW)
+    claim, bind = 56, None
+    for rnd, want in enumerate((28, 14, 7)):
+        poly = gpu.prove_round(bind, rnd, claim)
+        assert poly.coefficients[0] == want and all(c == 0 for c in poly.coefficients[1:])
+        bind = O.synthetic_point(3, 401)[rnd]
+        claim = poly.evaluate(bind)
+    gpu.finish_rounds(bind)
+    assert gpu.final_evals() == [7] and claim == 7
+
+
+def test_small_scalar_accumulator_known_answer_on_device(sess):
+    # crates/jolt-field/src/bn254/mont.rs:663-676 (3*16 + 5*(-7) + 11*1 + 9*(-13) + 2*7 == -79), with the device doing
+    # the signed promotions (jb_table_upload_small) and the products (jb_vec_op)
+    a = Polynomial.from_small(sess, np.array([3, 5, 11, 9, 2, 0, 0, 0], dtype=np.uint64)).evals()
+    s = Polynomial.from_small(sess, np.array([16, -7, 1, -13, 7, 0, 0, 0], dtype=np.int64)).evals()
+    prods = F.limbs_to_ints(sess.vec_op(0, 2, a, s))
+    assert sum(prods) % O.R_MOD == O.R_MOD - 79
