@@ -46,27 +46,43 @@ const HostFr* inverse_factorials() {
 
 UnivariatePoly UnivariatePoly::from_evals(const std::vector<HostFr>& evals) {
     const size_t n = evals.size();
-    std::vector<HostFr> diff(evals), newton(n, HostFr::zero());
+    UnivariatePoly out;
+    out.coefficients.assign(n, HostFr::zero());
+    if (n == 0) return out;
+    // This runs once per member per round on the Fiat-Shamir round trip: no heap traffic beyond the result for the
+    // degrees a sumcheck sees (n <= 16); larger inputs take the same path with heap scratch.
+    constexpr size_t STACK_N = 16;
+    HostFr stack_scratch[3 * STACK_N + 1];
+    std::vector<HostFr> heap_scratch;
+    HostFr* scratch = stack_scratch;
+    if (n > STACK_N) {
+        heap_scratch.resize(3 * n + 1);
+        scratch = heap_scratch.data();
+    }
+    HostFr* diff = scratch;              // n
+    HostFr* newton = scratch + n;        // n
+    HostFr* basis = scratch + 2 * n;     // n + 1
     const HostFr* inv_fact = inverse_factorials();
+    for (size_t i = 0; i < n; ++i) diff[i] = evals[i];
+    size_t dlen = n;
     for (size_t k = 0; k < n; ++k) {
         const HostFr fact_inv = k < 32 ? inv_fact[k] : HostFr::zero();
         newton[k] = diff[0] * fact_inv;  // k-th forward difference / k!
-        for (size_t i = 0; i + 1 < diff.size(); ++i) diff[i] = diff[i + 1] - diff[i];
-        if (!diff.empty()) diff.pop_back();
+        for (size_t i = 0; i + 1 < dlen; ++i) diff[i] = diff[i + 1] - diff[i];
+        if (dlen) --dlen;
     }
-    // expand sum_k newton[k] * x (x-1) ... (x-k+1)
-    UnivariatePoly out;
-    out.coefficients.assign(n, HostFr::zero());
-    std::vector<HostFr> basis{HostFr::one()};
+    // expand sum_k newton[k] * x (x-1) ... (x-k+1); basis holds the falling factorial of degree k (k + 1 coefficients)
+    basis[0] = HostFr::one();
+    size_t blen = 1;
     for (size_t k = 0; k < n; ++k) {
-        for (size_t i = 0; i < basis.size(); ++i) out.coefficients[i] = out.coefficients[i] + newton[k] * basis[i];
-        std::vector<HostFr> next(basis.size() + 1, HostFr::zero());
-        HostFr kk = HostFr::from_u64(k);
-        for (size_t i = 0; i < basis.size(); ++i) {
-            next[i + 1] = next[i + 1] + basis[i];
-            next[i] = next[i] - kk * basis[i];
-        }
-        basis.swap(next);
+        for (size_t i = 0; i < blen; ++i) out.coefficients[i] = out.coefficients[i] + newton[k] * basis[i];
+        if (k + 1 == n) break;
+        // basis *= (x - k), in place from the top coefficient down
+        const HostFr kk = HostFr::from_u64(k);
+        basis[blen] = basis[blen - 1];
+        for (size_t i = blen - 1; i > 0; --i) basis[i] = basis[i - 1] - kk * basis[i];
+        basis[0] = HostFr::zero() - kk * basis[0];
+        ++blen;
     }
     return out;
 }
@@ -82,13 +98,13 @@ int DeviceProductMember::prove_round(const HostFr* bind, size_t round, const Hos
                                      UnivariatePoly* out) {
     size_t degree = 0;
     jb_member_degree(mem_, &degree);
-    std::vector<uint64_t> ev((degree + 1) * 4);
-    int st = jb_member_prove_round(mem_, bind ? bind->l : nullptr, round, check_rounds_ ? previous_claim.l : nullptr,
-                                   ev.data());
+    uint64_t ev[8 * 4];  // degree + 1 <= 8 (JB_MAX_EVALS)
+    if (degree + 1 > 8) return JB_ERR_UNSUPPORTED;
+    int st = jb_member_prove_round(mem_, bind ? bind->l : nullptr, round, check_rounds_ ? previous_claim.l : nullptr, ev);
     if (st != JB_OK) return st;
-    std::vector<HostFr> evals(degree + 1);
-    for (size_t t = 0; t <= degree; ++t) evals[t] = HostFr::from_limbs(ev.data() + 4 * t);
-    *out = UnivariatePoly::from_evals(evals);
+    evals_.resize(degree + 1);
+    for (size_t t = 0; t <= degree; ++t) evals_[t] = HostFr::from_limbs(ev + 4 * t);
+    *out = UnivariatePoly::from_evals(evals_);
     return JB_OK;
 }
 
@@ -142,9 +158,14 @@ int prove_batch(const BatchPrelude& prelude, std::vector<ProveRounds*>& members,
     std::vector<HostFr> pending(members.size());
     std::vector<char> has_pending(members.size(), 0);
 
+    std::vector<HostFr> batched;
+    std::vector<MemberRound> work;
+    work.reserve(members.size());
+    out->challenges.reserve(max_num_vars);
+    out->round_polynomials.reserve(max_num_vars);
     for (size_t round = 0; round < max_num_vars; ++round) {
-        std::vector<HostFr> batched(prelude.max_degree + 1, HostFr::zero());
-        std::vector<MemberRound> work;
+        batched.assign(prelude.max_degree + 1, HostFr::zero());
+        work.clear();
         for (size_t i = 0; i < members.size(); ++i) {
             const BatchMember& d = prelude.members[i];
             bool active = round >= d.offset && round < d.offset + d.rounds;
@@ -206,8 +227,9 @@ namespace {
 struct CallbackRecorder : jb::AbsorbRound {
     jb_absorb_round_fn fn;
     void* user;
+    std::vector<uint64_t> flat;
     int absorb_round(size_t round, const jb::UnivariatePoly& poly, jb::HostFr* challenge) override {
-        std::vector<uint64_t> flat(poly.coefficients.size() * 4);
+        flat.resize(poly.coefficients.size() * 4);
         for (size_t i = 0; i < poly.coefficients.size(); ++i) poly.coefficients[i].store(flat.data() + 4 * i);
         uint64_t c[4];
         int st = fn(user, round, flat.data(), poly.coefficients.size(), c);

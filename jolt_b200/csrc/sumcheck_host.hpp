@@ -37,6 +37,7 @@ class DeviceProductMember : public ProveRounds {
    private:
     jb_member* mem_;
     bool check_rounds_;
+    std::vector<HostFr> evals_;  // reused across rounds (no allocation on the round trip)
 };
 
 // MemberRound / MemberFinish (prover.rs:75-104)
