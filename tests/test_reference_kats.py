@@ -87,3 +87,26 @@ def test_constant_polynomial_sumcheck_kats():
     res = O.prove_batch([dict(input_claim=42, coefficient=1, rounds=0, offset=0)], [O.ProductMember([[42]], O.HIGH_TO_LOW)],
                         0, 1, 42, lambda r, c: 1)
     assert res["final_claim"] == 42 and res["round_polys"] == []
+
+
+def test_g1_published_alt_bn128_vectors():
+    """The reference holds no serialized G1 point (G1 / MSM parity is unpinned by ITS vectors), so the
+    oracle's curve arithmetic is anchored on the published alt_bn128 constants instead: the generator (1, 2) and its
+    first multiples as used by the EIP-196 ecAdd / ecMul precompile test vectors, and the group order."""
+    two_g = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+             0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)
+    three_g = (0x0769BF9AC56BEA3FF40232BCB1B6BD159315D84715B8E679F2D355961915ABF0,
+               0x2AB799BEE0489429554FDB7C8D086475319E63B40B9C5B57CDF1FF3DD9FE2261)
+    G = O.G1_GEN
+    assert G == (1, 2) and O.g1_is_on_curve(G)
+    assert O.g1_add(G, G) == two_g == O.g1_scalar_mul(G, 2)
+    assert O.g1_add(two_g, G) == three_g == O.g1_scalar_mul(G, 3)
+    assert O.g1_scalar_mul(G, O.R_MOD) is None                      # the group order is r (cofactor 1)
+    assert O.g1_scalar_mul(G, O.R_MOD - 1) == O.g1_neg(G) == (1, O.Q_MOD - 2)
+    # and the C restatement agrees with the Python one on them
+    import numpy as np
+    from oracle import coracle as C
+    g_limbs = np.array(O.to_mont_limbs(1, O.Q_MOD) + O.to_mont_limbs(2, O.Q_MOD), dtype=np.uint64).reshape(1, 8)
+    for k, want in ((2, two_g), (3, three_g)):
+        xy, inf = C.g1_msm_naive(g_limbs, C.ints_to_mont([k]))
+        assert not inf and (O.from_mont_limbs(xy[:4], O.Q_MOD), O.from_mont_limbs(xy[4:], O.Q_MOD)) == want
