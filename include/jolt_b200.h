@@ -154,6 +154,16 @@ int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null,
 int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
 /* The host half of the above (carry-propagate + fold mod r) on `count` x 8 host lanes; needs no device. */
 int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out_elems);
+/* The host half of a round (needs no device). The round kernels emit, for a product of m tables,
+ *   s(0), [s(1) unless skip_t1], s(2), .., s(m-1), s(inf)      (m >= 2; s(inf) = the leading coefficient)
+ *   s(0), [s(1) unless skip_t1]                                (m == 1)
+ * and this rebuilds the m + 1 evaluations s(0), .., s(m) the interpolation takes: s(1) = claim - s(0) when it was
+ * skipped (round_poly_from_skipped_evals, crates/jolt-kernels/src/optimized/support.rs:450-460) and s(m) from the
+ * leading coefficient (the evaluation-at-infinity trade of UnivariatePoly::from_evals_toom). With a claim and
+ * skip_t1 == 0 the round check s(0) + s(1) == claim is applied (JB_ERR_ROUND_CHECK). jb_member_prove_round calls
+ * exactly this on the values the device published. */
+int jb_round_evals_from_kernel_values(int m, int skip_t1, const uint64_t* kernel_values, const uint64_t* claim_or_null,
+                                      uint64_t* out_evals);
 /* Copies table j of a member (current, possibly partly bound contents) to caller device memory -
  * used to all-gather the shards once they are small (jolt_b200/dist.py). */
 int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t cap_elems, size_t* len_out);

@@ -843,6 +843,31 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
 
 static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals);
 
+struct RoundConsts {
+    HostFr w[4], ipow[4], mpow;
+};
+static const RoundConsts& round_consts(int M) {  // M in 2..4
+    static RoundConsts table[5];
+    static const bool init = [] {
+        static const uint64_t binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+        for (int m = 2; m <= 4; ++m) {
+            for (int i = 0; i < m; ++i) {
+                HostFr ti = HostFr::one();  // i^m
+                for (int e = 0; e < m; ++e) ti = ti * HostFr::from_u64((uint64_t)i);
+                table[m].ipow[i] = ti;
+                const HostFr b = HostFr::from_u64(binom[m][i]);
+                table[m].w[i] = ((m - 1 - i) & 1) ? HostFr::zero() - b : b;
+            }
+            HostFr tm = HostFr::one();  // m^m
+            for (int e = 0; e < m; ++e) tm = tm * HostFr::from_u64((uint64_t)m);
+            table[m].mpow = tm;
+        }
+        return true;
+    }();
+    (void)init;
+    return table[M];
+}
+
 // Assembles s(0..M) from the K published values. Kernel order: s(0), [s(1)], s(2..M-1), s(inf) for
 // M >= 2 (s(0), [s(1)] for M == 1); with skip1, s(1) = claim - s(0). s(M) is rebuilt from the leading
 // coefficient: q(t) = s(t) - s(inf) t^M has degree < M, so q(M) = sum_{i<M} (-1)^(M-1-i) C(M,i) q(i).
@@ -857,25 +882,31 @@ static int assemble_evals(jb_ctx* c, int M, bool skip1, const uint64_t* vals, co
     if (M >= 2) {
         for (int t = 2; t < M; ++t) ev[t] = HostFr::from_limbs(vals + 4 * k++);
         const HostFr lead = HostFr::from_limbs(vals + 4 * k++);
-        static const uint64_t binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
+        // s(M) = sum_{i<M} w_i (s(i) - lead i^M) + lead M^M with w_i = (-1)^(M-1-i) C(M,i); the constants are built
+        // once (this runs on the Fiat-Shamir round trip of every round)
+        const RoundConsts& rc = round_consts(M);
         HostFr qM = HostFr::zero();
-        for (int i = 0; i < M; ++i) {
-            HostFr ti = HostFr::one();  // i^M
-            for (int e = 0; e < M; ++e) ti = ti * HostFr::from_u64((uint64_t)i);
-            HostFr term = (ev[i] - lead * ti) * HostFr::from_u64(binom[M][i]);
-            qM = ((M - 1 - i) & 1) ? qM - term : qM + term;
-        }
-        HostFr tM = HostFr::one();  // M^M
-        for (int e = 0; e < M; ++e) tM = tM * HostFr::from_u64((uint64_t)M);
-        ev[M] = qM + lead * tM;
+        for (int i = 0; i < M; ++i) qM = qM + rc.w[i] * (ev[i] - lead * rc.ipow[i]);
+        ev[M] = qM + lead * rc.mpow;
     }
     for (int t = 0; t <= M; ++t) ev[t].store(out_evals + 4 * t);
     if (claim && !skip1 && (ev[0] + ev[1]) != HostFr::from_limbs(claim)) {
         char buf[96];
         std::snprintf(buf, sizeof buf, "RoundCheckFailed { round: %zu }", round);
-        return c->fail(JB_ERR_ROUND_CHECK, buf);
+        return c ? c->fail(JB_ERR_ROUND_CHECK, buf) : (int)JB_ERR_ROUND_CHECK;
     }
     return JB_OK;
+}
+
+int jb_round_evals_from_kernel_values(int m, int skip_t1, const uint64_t* kernel_values, const uint64_t* claim_or_null,
+                                      uint64_t* out_evals) {
+    if (!kernel_values || !out_evals || m < 1 || m > 4) return JB_ERR_INVALID;
+    if (skip_t1 && !claim_or_null) return JB_ERR_INVALID;
+    const int k = m == 1 ? (skip_t1 ? 1 : 2) : (skip_t1 ? m : m + 1);
+    for (int t = 0; t < k; ++t)
+        if (!canonical_fr(kernel_values + 4 * t)) return JB_ERR_INVALID;
+    if (claim_or_null && !canonical_fr(claim_or_null)) return JB_ERR_INVALID;
+    return assemble_evals(nullptr, m, skip_t1 != 0, kernel_values, claim_or_null, 0, out_evals);
 }
 
 int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,

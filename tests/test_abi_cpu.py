@@ -114,3 +114,33 @@ def test_small_scalar_encoding_host_side():
         small_scalars([1 << 128], "u128")
     with pytest.raises(ValueError):
         small_scalars(np.zeros(2, dtype=np.float64))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+@pytest.mark.parametrize("skip1", [0, 1])
+def test_round_evals_from_kernel_values(m, skip1):
+    """The host half of jb_member_prove_round (no device): s(1) from the claim, s(m) from the leading coefficient
+    s(inf) the kernels emit instead of s(m) - checked against direct evaluation of random degree-m polynomials."""
+    import ctypes
+    import numpy as np
+    from jolt_b200 import field as F
+    from jolt_b200._lib import JB_OK
+    from jolt_b200.api import _p
+    lib = jolt_b200.load()
+    for seed in range(5):
+        coeffs = O.random_fr(100 * m + 10 * skip1 + seed, m + 1)
+        s = [O.uni_evaluate(coeffs, t) for t in range(m + 1)]
+        claim = (s[0] + s[1]) % O.R_MOD
+        vals = [s[0]] + ([] if skip1 else [s[1]])
+        if m >= 2:
+            vals += s[2:m] + [coeffs[m]]                    # s(2..m-1), then the leading coefficient
+        vin = F.ints_to_limbs(vals)
+        out = np.zeros((m + 1, 4), dtype=np.uint64)
+        cl = F.ints_to_limbs([claim])
+        assert lib.jb_round_evals_from_kernel_values(m, skip1, _p(vin), _p(cl), _p(out)) == JB_OK
+        assert F.limbs_to_ints(out) == s
+        if not skip1:   # verify mode: a wrong claim is a round-check failure; no claim, no check
+            bad = F.ints_to_limbs([(claim + 1) % O.R_MOD])
+            assert lib.jb_round_evals_from_kernel_values(m, 0, _p(vin), _p(bad), _p(out)) == jolt_b200._lib.JB_ERR_ROUND_CHECK
+            assert lib.jb_round_evals_from_kernel_values(m, 0, _p(vin), None, _p(out)) == JB_OK
+    assert lib.jb_round_evals_from_kernel_values(5, 0, _p(vin), None, _p(out)) == jolt_b200._lib.JB_ERR_INVALID
