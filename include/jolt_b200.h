@@ -146,9 +146,10 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
 int jb_eq_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, const uint64_t* w, size_t nvars,
                         const uint64_t* scale_or_null, int order, jb_member** out);
 int jb_eq_member_scalar(jb_member* mem, uint64_t out[4]);
-/* Multi-GPU: like prove_round but leaves this rank's partial sums - s(0..degree), or with skip_t1
- * s(0), s(2), .., s(degree) - on the device as count x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32
- * ranks); the caller all-reduces that buffer and calls jb_partials_finalize. No round check. */
+/* Multi-GPU: like prove_round but leaves this rank's partial sums - the kernel values s(0), [s(1) unless
+ * skip_t1], s(2), .., s(m-1), s(inf) in the order jb_round_evals_from_kernel_values documents - on the device as
+ * count x 8 uint64 lanes, each holding one 32-bit limb (exact under ncclSum over <= 2^32 ranks); the caller
+ * all-reduces that buffer, calls jb_partials_finalize and then jb_round_evals_from_kernel_values. No round check. */
 int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null, size_t round, int skip_t1,
                                    void* device_lanes_out);
 int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
