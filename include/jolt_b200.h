@@ -120,6 +120,17 @@ int jb_eq_evals_aligned_block(jb_ctx* ctx, const uint64_t* r, size_t nvars, size
  *      product-of-m-tables relation, degree m (naive.rs:241-316; tests/roundtrip.rs:26-97) ------- */
 /* Takes ownership of the m tables (all the same power-of-two length). m in 1..4. */
 int jb_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, int order, jb_member** out);
+/* Sum-of-products member: ProveRounds for  sum_x sum_{k < terms} prod_{j < factors} f_{k * factors + j}(x),
+ * degree = factors, over factors * terms dense tables (term k owns tables [k * factors, (k + 1) * factors)); every
+ * table is bound by every challenge (bind_all, crates/jolt-kernels/src/optimized/support.rs). This is the shape of the
+ * reference's optimized claim-reduction kernels after paired-eq fusion - e.g. IncClaimReduction's summand
+ * A * RamInc + B * RdInc (crates/jolt-kernels/src/optimized/inc_claim_reduction.rs:47-203: factors = 2, terms = 2,
+ * tables {A, RamInc, B, RdInc}); term weights are folded into one table of the term, as the reference folds gamma
+ * into A and B. Built shapes: terms = 1 with factors 1..4 (== jb_member_create) and factors = 2, terms = 2.
+ * jb_member_final_evals returns the factors * terms bound values in table order. */
+int jb_member_create_sop(jb_ctx* ctx, const jb_table* tables, size_t factors, size_t terms, int order, jb_member** out);
+int jb_member_num_tables(jb_member* mem, size_t* tables);
+jb_ctx* jb_member_context(jb_member* mem);
 int jb_member_num_rounds(jb_member* mem, size_t* rounds);
 int jb_member_degree(jb_member* mem, size_t* degree);
 /* prove_round(bind, round, previous_claim): binds `bind_or_null` (NULL on the first active round)
@@ -193,6 +204,33 @@ int jb_comm_p2p_open(jb_ctx* ctx, const uint8_t* handles_world_x_64);
  * ranks, identical to the single-GPU member over the global tables). `previous_claim` is the GLOBAL claim. */
 int jb_sharded_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, int order, size_t gather_log,
                              jb_member** out);
+
+/* ---- device RoundScheduler: jolt_sumcheck::RoundScheduler (crates/jolt-sumcheck/src/prover.rs:106-120), minted per
+ * stage by BuildRoundScheduler::build(session) (crates/jolt-kernels/src/backend.rs:64-70, "so a device traversal
+ * shares the carry"). "Order and transport are free": a batch round costs ONE host round trip whatever the member
+ * count. Homogeneous batches (same shape and order, <= 8 members) are served by ONE resident kernel - launched once,
+ * it takes every round's {per-member action, shared challenge} from a mailbox in host-mapped memory and answers
+ * with every member's round sums, so no kernel is launched per round; otherwise every active member's pass is
+ * enqueued before the first wait (one result slot per member). `work[i].member` indexes the member list given at
+ * creation; out_evals receives 8 elements (32 limbs) per work item, the first degree + 1 of them valid.
+ * Results are identical to calling jb_member_prove_round on each item. ------------------------------------------ */
+typedef struct jb_scheduler jb_scheduler;
+typedef struct jb_round_work {   /* MemberRound, prover.rs:75-92 */
+    size_t member;
+    size_t round;                /* member-local round */
+    int has_bind;                /* 0 exactly on the member's first active round */
+    int has_claim;               /* 0: compute every point, check nothing (as jb_member_prove_round without a claim) */
+    uint64_t bind[4];
+    uint64_t claim[4];
+} jb_round_work;
+typedef struct jb_finish_work {  /* MemberFinish, prover.rs:94-104 */
+    size_t member;
+    uint64_t bind[4];
+} jb_finish_work;
+int jb_scheduler_create(jb_ctx* ctx, jb_member** members, size_t n_members, jb_scheduler** out);
+int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t n_work, uint64_t* out_evals);
+int jb_scheduler_finish_rounds(jb_scheduler* s, const jb_finish_work* work, size_t n_work);
+void jb_scheduler_destroy(jb_scheduler* s);
 
 /* ---- batched engine: jolt_sumcheck::prove_batch (crates/jolt-sumcheck/src/prover.rs:193-362) over
  *      device members, SequentialRounds traversal. BatchMember = batch.rs:24-71. The transcript stays
@@ -284,6 +322,11 @@ int jb_vec_op(jb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t*
  * kind: 0 fused bind+eval, 1 bind, 2 eval-only, 3 eq, 4 msm bucket accumulation. */
 /* out[0] = ns the host spent waiting for round results since the last call, out[1] = number of waits. */
 int jb_ctx_diag(jb_ctx* ctx, double out[4]);
+/* Per round of the last completed resident-kernel run (<= 64 rounds), 8 values each: device %globaltimer (ns) when
+ * the command was decoded and when the last block had folded the round's sums; host CLOCK_MONOTONIC (ns) when the
+ * command was posted and when the answer was seen; device: block 0 done with its passes, block 0 arrived, the last
+ * block knew it was last, spare. The two clocks are unrelated: use differences. */
+int jb_ctx_run_log(jb_ctx* ctx, uint64_t* out, size_t cap_rounds, size_t* rounds);
 int jb_ctx_timing_enable(jb_ctx* ctx, int on, uint64_t min_items);
 int jb_ctx_timing_collect(jb_ctx* ctx, int* kinds, uint64_t* items, int* m, double* ms, size_t cap, size_t* count);
 

@@ -22,7 +22,9 @@ from .api import (  # noqa: F401
     Polynomial,
     ProductMember,
     ProvedBatch,
+    RoundScheduler,
     Session,
+    SumOfProductsMember,
     SumcheckError,
     UnivariatePoly,
     g1_affine_limbs,

@@ -41,6 +41,13 @@ SIGNATURES = {
     "jb_eq_evals": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p, c_u64p]),
     "jb_eq_evals_aligned_block": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_size_t, c_size_t, c_u64p]),
     "jb_member_create": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.c_int, ctypes.POINTER(c_void_p)]),
+    "jb_member_create_sop": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_size_t, ctypes.c_int, ctypes.POINTER(c_void_p)]),
+    "jb_member_num_tables": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
+    "jb_member_context": (c_void_p, [c_void_p]),
+    "jb_scheduler_create": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), c_size_t, ctypes.POINTER(c_void_p)]),
+    "jb_scheduler_prove_round": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_u64p]),
+    "jb_scheduler_finish_rounds": (ctypes.c_int, [c_void_p, c_void_p, c_size_t]),
+    "jb_scheduler_destroy": (None, [c_void_p]),
     "jb_member_num_rounds": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
     "jb_member_degree": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_size_t)]),
     "jb_member_prove_round": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, c_u64p, c_u64p]),
@@ -77,6 +84,7 @@ SIGNATURES = {
     "jb_msm_g1_small": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_void_p, c_size_t, ctypes.c_int, c_u64p]),
     "jb_msm_g1_table": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, ctypes.c_uint64, c_size_t, c_u64p]),
     "jb_ctx_diag": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "jb_ctx_run_log": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_ctx_timing_enable": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_uint64]),
     "jb_ctx_timing_collect": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_int), c_u64p, ctypes.POINTER(ctypes.c_int),
                                              ctypes.POINTER(ctypes.c_double), c_size_t, ctypes.POINTER(c_size_t)]),
@@ -102,6 +110,15 @@ class JoltB200Error(RuntimeError):
 class BatchMemberC(ctypes.Structure):
     _fields_ = [("input_claim", ctypes.c_uint64 * 4), ("coefficient", ctypes.c_uint64 * 4),
                 ("rounds", c_size_t), ("offset", c_size_t)]
+
+
+class RoundWorkC(ctypes.Structure):
+    _fields_ = [("member", c_size_t), ("round", c_size_t), ("has_bind", ctypes.c_int), ("has_claim", ctypes.c_int),
+                ("bind", ctypes.c_uint64 * 4), ("claim", ctypes.c_uint64 * 4)]
+
+
+class FinishWorkC(ctypes.Structure):
+    _fields_ = [("member", c_size_t), ("bind", ctypes.c_uint64 * 4)]
 
 
 HKZG_R_FN = ctypes.CFUNCTYPE(ctypes.c_int, c_void_p, c_u64p, c_size_t, c_u64p)

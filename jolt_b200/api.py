@@ -364,6 +364,83 @@ class ProductMember:
             pass
 
 
+class SumOfProductsMember(ProductMember):
+    """ProveRounds member for sum_x sum_{k<terms} prod_{j<factors} f_{k*factors+j}(x) (jb_member_create_sop) - the
+    shape of the reference's optimized claim-reduction kernels after paired-eq fusion, e.g. IncClaimReduction's
+    A * RamInc + B * RdInc (crates/jolt-kernels/src/optimized/inc_claim_reduction.rs:47-203). `polys` in term-major
+    order; degree = factors; final_evals() returns all factors * terms bound values."""
+
+    def __init__(self, session: Session, polys: list[Polynomial], factors: int, terms: int, order: int = HIGH_TO_LOW):
+        assert len(polys) == factors * terms
+        self.s = session
+        handles = np.array([p.handle for p in polys], dtype=np.uint64)
+        h = ctypes.c_void_p()
+        session.check(session.lib.jb_member_create_sop(session.h, _p(handles), factors, terms, order, ctypes.byref(h)))
+        for p in polys:
+            p.handle = 0
+        self.h = h
+        self.m = factors
+        self.terms = terms
+
+    def final_evals(self, raw: bool = False):
+        out = np.empty((self.m * self.terms, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_member_final_evals(self.h, _p(out)))
+        return out if raw else F.limbs_to_ints(out)
+
+
+class RoundScheduler:
+    """Device traversal of a batch (jolt_sumcheck::RoundScheduler, prover.rs:106-120; jb_scheduler_*): every active
+    member's round in one host round trip. `members`: ProductMember-likes of one session."""
+
+    def __init__(self, session: Session, members: list):
+        self.s = session
+        self.members = list(members)
+        arr = (ctypes.c_void_p * len(members))(*[m.h for m in members])
+        h = ctypes.c_void_p()
+        session.check(session.lib.jb_scheduler_create(session.h, arr, len(members), ctypes.byref(h)))
+        self.h = h
+
+    def batch_prove_round(self, work: list[tuple]) -> list[UnivariatePoly]:
+        """work: [(member_index, local_round, bind_or_None, claim_or_None)] -> one round polynomial per item."""
+        n = len(work)
+        arr = (_lib.RoundWorkC * max(n, 1))()
+        for i, (idx, rnd, bind, claim) in enumerate(work):
+            arr[i].member, arr[i].round = idx, rnd
+            arr[i].has_bind = 0 if bind is None else 1
+            arr[i].has_claim = 0 if claim is None else 1
+            if bind is not None:
+                arr[i].bind[:] = [int(x) for x in _limbs(bind)]
+            if claim is not None:
+                arr[i].claim[:] = [int(x) for x in _limbs(claim)]
+        out = np.zeros((max(n, 1), 8, 4), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_scheduler_prove_round(self.h, ctypes.cast(arr, ctypes.c_void_p), n, _p(out)))
+        res = []
+        for i, (idx, *_rest) in enumerate(work):
+            d = self.members[idx].degree()
+            res.append(UnivariatePoly.from_evals(F.limbs_to_ints(out[i, : d + 1])))
+        return res
+
+    def batch_finish_rounds(self, finishes: list[tuple]) -> None:
+        """finishes: [(member_index, bind)]."""
+        n = len(finishes)
+        arr = (_lib.FinishWorkC * max(n, 1))()
+        for i, (idx, bind) in enumerate(finishes):
+            arr[i].member = idx
+            arr[i].bind[:] = [int(x) for x in _limbs(bind)]
+        self.s.check(self.s.lib.jb_scheduler_finish_rounds(self.h, ctypes.cast(arr, ctypes.c_void_p), n))
+
+    def close(self):
+        if self.h:
+            self.s.lib.jb_scheduler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class EqProductMember(ProductMember):
     """ProveRounds member for sum_x eq(w, x) * prod_j f_j(x) (degree m + 1) with the eq polynomial kept
     split (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): no eq table is materialised,

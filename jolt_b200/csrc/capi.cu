@@ -1,12 +1,13 @@
 // C ABI of the B200 backend (see include/jolt_b200.h for the per-function reference citations).
 // The context mirrors ProofSession (crates/jolt-kernels/src/backend.rs:283-286): it owns the
 // stream, the stream-ordered device pool, and the small reduction / staging buffers.
+// This unit: library / context, tables, bind, eq expansion, element-wise harness, diagnostics.
+// Members and the round scheduler live in member.cu, the resident kernel service in resident.cu.
 #include "../../include/jolt_b200.h"
 
 #include <cuda_runtime.h>
 
 #include <cstdio>
-#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -15,38 +16,13 @@
 #include <unordered_map>
 #include <vector>
 
-#include "ctx.hpp"
-#include "host_fr.hpp"
-#include "poly_kernels.cuh"
-#include "sumcheck_host.hpp"
+#include "member.hpp"
 
 using namespace jb;
-
-static inline uint64_t now_ns() {
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
-}
+using namespace jbi;
+using Guard = CtxGuard;
 
 namespace {
-
-struct Guard {
-    jb_ctx* c;
-    std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* ctx) : c(ctx), lk(ctx->mu) { ctx->make_current(); }
-};
-
-BindScalar make_scalar(const uint64_t r[4], bool* hi4) {
-    BindScalar s;
-    for (int i = 0; i < 4; ++i) {
-        s.w[2 * i] = (uint32_t)r[i];
-        s.w[2 * i + 1] = (uint32_t)(r[i] >> 32);
-    }
-    *hi4 = (r[0] == 0 && r[1] == 0);
-    return s;
-}
-
-bool canonical_fr(const uint64_t r[4]) { return !HostFr::geq_p(r); }
 
 template <typename K>
 int blocks_per_sm(K kernel) {
@@ -73,8 +49,10 @@ int launch_bind(jb_ctx* c, const uint64_t* in, uint64_t* out, size_t half, const
     return c->check(cudaGetLastError(), "bind_kernel launch");
 }
 
+}  // namespace
+
 // Halves one table under `r` (Polynomial::bind_with_order).
-int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
+int jbi::bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
     if (t.len < 2 || (t.len & (t.len - 1))) return c->fail(JB_ERR_INVALID, "bind: table length must be a power of two >= 2");
     if (!canonical_fr(r)) return c->fail(JB_ERR_INVALID, "bind: challenge limbs not canonical (>= r)");
     bool hi4;
@@ -96,117 +74,8 @@ int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order) {
     return st;
 }
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB>
-int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
-    auto kernel = fused_round_kernel<M, ORDER, BIND, HI4, SKIP1, BLOCK, MINB>;
-    constexpr size_t smem = FusedShape<M, SKIP1>::smem_bytes(BLOCK);
-    static int per_sm = [&] {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, BLOCK, smem) != cudaSuccess || nb < 1) nb = 1;
-        return nb;
-    }();
-    // grid-stride over whole waves of resident blocks; tiny rounds take one (small) block
-    size_t need = (pairs + BLOCK - 1) / BLOCK;
-    size_t resident = (size_t)c->sm_count * per_sm;
-    size_t grid = need < resident ? need : resident;
-    if (grid < 1) grid = 1;
-    constexpr int K = FusedShape<M, SKIP1>::K;
-    int st = c->ensure_partial(grid * K);
-    if (st != JB_OK) return st;
-    out.partial = c->d_partial;
-    int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
-    // latency path: a round of <= 32 pairs runs as one warp (no barriers, no shared-memory stage)
-    const unsigned block = pairs <= 32 ? 32u : (unsigned)BLOCK;
-    kernel<<<(unsigned)grid, block, smem, c->stream>>>(tp, pairs, s, out);
-    c->timing_end(tix);
-    c->launches++;
-    return c->check(cudaGetLastError(), "fused_round_kernel launch");
-}
 
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1>
-int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, const RoundOut& out) {
-    // occupancy shapes (tuning knob JB_FUSED_SHAPE): 0 = 256 threads x 2 blocks (128 registers),
-    // 1 = 128 threads x 5 blocks (<= 102 registers, 20 warps/SM)
-    if constexpr (M == 2) {
-        if (c->fused_shape == 1) return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 128, 5>(c, tp, pairs, s, out);
-    }
-    return launch_fused_mb<M, ORDER, BIND, HI4, SKIP1, 256, 2>(c, tp, pairs, s, out);
-}
-
-// weighted (split-eq) passes: LowToHigh, s(1) from the claim, 256 x 2
-template <int M, bool BIND, bool HI4>
-int launch_weighted(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
-    auto kernel = fused_round_kernel<M, ORDER_LOW_TO_HIGH, BIND, HI4, true, 256, 2, true>;
-    constexpr size_t smem = FusedShape<M, true>::smem_bytes(256);
-    static int per_sm = [&] {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 256, smem) != cudaSuccess || nb < 1) nb = 1;
-        return nb;
-    }();
-    size_t need = (pairs + 255) / 256;
-    size_t resident = (size_t)c->sm_count * per_sm;
-    size_t grid = need < resident ? need : resident;
-    if (grid < 1) grid = 1;
-    int st = c->ensure_partial(grid * M);
-    if (st != JB_OK) return st;
-    out.partial = c->d_partial;
-    int tix = c->timing_begin(BIND ? 0 : 2, pairs, M);
-    const unsigned block = pairs <= 32 ? 32u : 256u;
-    kernel<<<(unsigned)grid, block, smem, c->stream>>>(tp, pairs, s, out);
-    c->timing_end(tix);
-    c->launches++;
-    return c->check(cudaGetLastError(), "fused_round_kernel (weighted) launch");
-}
-
-template <int M>
-int dispatch_weighted1(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
-                       const RoundOut& out) {
-    if (!bind) return launch_weighted<M, false, false>(c, tp, pairs, s, out);
-    return hi4 ? launch_weighted<M, true, true>(c, tp, pairs, s, out) : launch_weighted<M, true, false>(c, tp, pairs, s, out);
-}
-
-int dispatch_weighted(jb_ctx* c, int m, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
-                      const RoundOut& out) {
-    switch (m) {
-        case 1: return dispatch_weighted1<1>(c, tp, pairs, bind, hi4, s, out);
-        case 2: return dispatch_weighted1<2>(c, tp, pairs, bind, hi4, s, out);
-        case 3: return dispatch_weighted1<3>(c, tp, pairs, bind, hi4, s, out);
-        default: return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
-    }
-}
-
-template <int M, int ORDER, bool SKIP1>
-int dispatch_fused2(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
-                    const RoundOut& out) {
-    if (!bind) return launch_fused<M, ORDER, false, false, SKIP1>(c, tp, pairs, s, out);
-    return hi4 ? launch_fused<M, ORDER, true, true, SKIP1>(c, tp, pairs, s, out)
-               : launch_fused<M, ORDER, true, false, SKIP1>(c, tp, pairs, s, out);
-}
-
-template <int M>
-int dispatch_fused1(jb_ctx* c, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
-                    const BindScalar& s, const RoundOut& out) {
-    if (order == JB_HIGH_TO_LOW)
-        return skip1 ? dispatch_fused2<M, ORDER_HIGH_TO_LOW, true>(c, tp, pairs, bind, hi4, s, out)
-                     : dispatch_fused2<M, ORDER_HIGH_TO_LOW, false>(c, tp, pairs, bind, hi4, s, out);
-    return skip1 ? dispatch_fused2<M, ORDER_LOW_TO_HIGH, true>(c, tp, pairs, bind, hi4, s, out)
-                 : dispatch_fused2<M, ORDER_LOW_TO_HIGH, false>(c, tp, pairs, bind, hi4, s, out);
-}
-
-int dispatch_fused(jb_ctx* c, int m, int order, bool skip1, const TablePtrs& tp, size_t pairs, bool bind, bool hi4,
-                   const BindScalar& s, const RoundOut& out) {
-    if (m < 1 || m > 4) return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
-    switch (m) {
-        case 1: return dispatch_fused1<1>(c, order, skip1, tp, pairs, bind, hi4, s, out);
-        case 2: return dispatch_fused1<2>(c, order, skip1, tp, pairs, bind, hi4, s, out);
-        case 3: return dispatch_fused1<3>(c, order, skip1, tp, pairs, bind, hi4, s, out);
-        case 4: return dispatch_fused1<4>(c, order, skip1, tp, pairs, bind, hi4, s, out);
-        default: return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
-    }
-}
-
+namespace {
 // eq table for `nvars` variables (HOST limbs r, optional host scale); recursive prefix for n > 11.
 EqVars eq_vars(const uint64_t* r, size_t count, const uint64_t* scale) {
     EqVars v;
@@ -226,7 +95,9 @@ EqVars eq_vars(const uint64_t* r, size_t count, const uint64_t* scale) {
     return v;
 }
 
-int eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, uint64_t* d_out) {
+}  // namespace
+
+int jbi::eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, uint64_t* d_out) {
     if (nvars <= (size_t)EQ_BLOCK_VARS) {
         eq_expand_kernel<<<1, 256, 0, c->stream>>>(nullptr, eq_vars(r, nvars, scale), (int)nvars, d_out);
         c->launches++;
@@ -256,8 +127,6 @@ int eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, 
     if (d_low8) c->dev_free(d_low8);
     return st;
 }
-
-}  // namespace
 
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -309,6 +178,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     c->sm_count = prop.multiProcessorCount;
     if (const char* sh = std::getenv("JB_FUSED_SHAPE")) c->fused_shape = std::atoi(sh);  // tuning knob
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
+    if (const char* ml = std::getenv("JB_RESIDENT_MAX_LOG")) c->resident_max_log = std::atoi(ml);
     // A kernel-replaying profiler (ncu) or a serialising tool (compute-sanitizer, nsys CUDA trace) cannot
     // run a kernel that waits for host commands; under CUDA injection keep one launch per round.
     {
@@ -327,10 +197,10 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     }
     bool ok = cudaMalloc((void**)&c->d_small, JB_SMALL_BYTES) == cudaSuccess &&
               cudaMallocHost((void**)&c->h_small, JB_SMALL_BYTES) == cudaSuccess &&
-              cudaHostAlloc((void**)&c->h_result, 1024, cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostAlloc((void**)&c->h_result, 1024 * JB_RESULT_SLOTS, cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void**)&c->d_result_alias, c->h_result, 0) == cudaSuccess &&
               cudaMalloc((void**)&c->d_counter, 64) == cudaSuccess && cudaMemset(c->d_counter, 0, 64) == cudaSuccess;
-    if (ok) std::memset(c->h_result, 0, 1024);
+    if (ok) std::memset(c->h_result, 0, 1024 * JB_RESULT_SLOTS);
     if (!ok) {
         jb_ctx_destroy(c);
         return JB_ERR_OOM;
@@ -347,6 +217,11 @@ int jb_ctx_create_on_stream(int device, void* cuda_stream, jb_ctx** out) {
 
 void jb_ctx_destroy(jb_ctx* c) {
     if (!c) return;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        cudaSetDevice(c->device);
+        c->quiesce_resident(true);
+    }
     jb_comm_destroy(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
@@ -356,6 +231,7 @@ void jb_ctx_destroy(jb_ctx* c) {
         if (r.stream) { cudaStreamSynchronize(r.stream); cudaStreamDestroy(r.stream); }
         if (r.event) cudaEventDestroy(r.event);
         if (r.mb_host) cudaFreeHost(r.mb_host);
+        if (r.d_state) cudaFree(r.d_state);
     }
     c->tail_pool.clear();
     for (auto& kv : c->srs) {
@@ -395,6 +271,15 @@ int jb_ctx_diag(jb_ctx* c, double out[4]) {
     return JB_OK;
 }
 
+int jb_ctx_run_log(jb_ctx* c, uint64_t* out, size_t cap_rounds, size_t* rounds) {
+    if (!c || !out || !rounds) return JB_ERR_INVALID;
+    Guard g(c, true);
+    const size_t n = c->last_run_rounds < cap_rounds ? c->last_run_rounds : cap_rounds;
+    std::memcpy(out, c->last_run_log, n * 64);
+    *rounds = n;
+    return JB_OK;
+}
+
 int jb_ctx_timing_enable(jb_ctx* c, int on, uint64_t min_items) {
     if (!c) return JB_ERR_INVALID;
     Guard g(c);
@@ -410,8 +295,8 @@ int jb_ctx_timing_collect(jb_ctx* c, int* kinds, uint64_t* items, int* ms_m, dou
     if (st != JB_OK) return st;
     size_t n = 0;
     for (auto& t : c->timed) {
-        float f = 0;
-        cudaEventElapsedTime(&f, t.e0, t.e1);
+        float f = (float)t.ms_direct;
+        if (t.e0) cudaEventElapsedTime(&f, t.e0, t.e1);
         if (n < cap) {
             if (kinds) kinds[n] = t.kind;
             if (items) items[n] = t.items;
@@ -419,8 +304,10 @@ int jb_ctx_timing_collect(jb_ctx* c, int* kinds, uint64_t* items, int* ms_m, dou
             if (ms) ms[n] = f;
             ++n;
         }
-        cudaEventDestroy(t.e0);
-        cudaEventDestroy(t.e1);
+        if (t.e0) {
+            cudaEventDestroy(t.e0);
+            cudaEventDestroy(t.e1);
+        }
     }
     c->timed.clear();
     *count = n;
@@ -558,796 +445,6 @@ int jb_eq_evals_aligned_block(jb_ctx* c, const uint64_t* r, size_t nvars, size_t
     return jb_eq_evals(c, r + 4 * prefix_len, block_vars, scale.l, out);
 }
 
-// ---- sumcheck member -------------------------------------------------------------------
-struct jb_member {
-    jb_ctx* ctx;
-    std::vector<Table> tables;
-    int m;
-    int order;
-    size_t rounds;  // total (for a sharded member: local rounds + log2(world))
-    size_t len;     // current (local) table length
-    size_t rounds_done = 0;  // prove_round calls completed
-    // index-sharded member: this rank holds the contiguous block `rank` of the global
-    // tables; rounds run with one all-reduce each until the shard is `gather_len` long, then the
-    // shards are all-gathered into `tail`, which finishes the remaining rounds locally.
-    bool sharded = false;
-    size_t gather_len = 0;
-    jb_member* tail = nullptr;
-    // split-eq member (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): the relation is
-    // sum_x eq(w, x) prod_j f_j(x); eq is never materialised - per round the sweep is weighted by
-    // E_out (x) E_in over the not-yet-current variables and the current variable's linear factor
-    // l(t) = scalar * ((1 - w_cur) + t (2 w_cur - 1)) is multiplied in on the host.
-    bool eq = false;
-    size_t eq_n = 0, eq_split = 0;
-    std::vector<uint64_t> eq_w;        // n elements, w[0] <-> most significant index bit
-    uint64_t eq_scalar[4] = {0, 0, 0, 0};
-    uint64_t* eq_tabs = nullptr;       // prefix tables Eo[k] (k <= split) then Ei[k] (k <= n-1-split), table k at 2^k - 1
-    size_t eq_in_base = 0;             // element offset of the Ei family
-    // persistent tail kernel (poly_kernels.cuh, tail_rounds_kernel): serves the short rounds from a mailbox
-    bool pt_active = false;
-    bool has_final = false;
-    uint64_t final_vals[4 * 4];
-    TailMailbox* pt_host = nullptr;
-    TailMailbox* pt_dev = nullptr;
-    cudaStream_t pt_stream = nullptr;
-    cudaEvent_t pt_event = nullptr;
-    uint64_t pt_seq = 0;
-};
-
-int jb_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, jb_member** out) {
-    if (!c || !handles || !out) return JB_ERR_INVALID;
-    Guard g(c);
-    if (m < 1 || m > 4) return c->fail(JB_ERR_UNSUPPORTED, "member: m must be 1..4");
-    if (order != JB_HIGH_TO_LOW && order != JB_LOW_TO_HIGH) return c->fail(JB_ERR_INVALID, "member: unknown order");
-    size_t len = 0;
-    for (size_t j = 0; j < m; ++j) {
-        Table* t = c->find(handles[j]);
-        if (!t) return c->fail(JB_ERR_INVALID, "member: unknown table handle");
-        for (size_t k = 0; k < j; ++k)
-            if (handles[k] == handles[j]) return c->fail(JB_ERR_INVALID, "member: duplicate table handle");
-        if (j == 0) len = t->len;
-        if (t->len != len) return c->fail(JB_ERR_INVALID, "member: tables differ in length");
-    }
-    if (len == 0 || (len & (len - 1))) return c->fail(JB_ERR_INVALID, "member: table length must be a power of two");
-    jb_member* mem = new (std::nothrow) jb_member();
-    if (!mem) return JB_ERR_OOM;
-    mem->ctx = c;
-    mem->m = (int)m;
-    mem->order = order;
-    mem->len = len;
-    mem->rounds = 0;
-    while (((size_t)1 << mem->rounds) < len) ++mem->rounds;
-    for (size_t j = 0; j < m; ++j) {
-        auto it = c->tables.find(handles[j]);
-        mem->tables.push_back(it->second);
-        c->tables.erase(it);  // ownership moves into the member
-    }
-    *out = mem;
-    return JB_OK;
-}
-
-int jb_member_num_rounds(jb_member* mem, size_t* rounds) {
-    if (!mem || !rounds) return JB_ERR_INVALID;
-    *rounds = mem->rounds;
-    return JB_OK;
-}
-
-int jb_member_degree(jb_member* mem, size_t* degree) {
-    if (!mem || !degree) return JB_ERR_INVALID;
-    *degree = (size_t)mem->m + (mem->eq ? 1 : 0);
-    return JB_OK;
-}
-
-// Runs the fused pass; on return d_small[0..m] holds the m+1 sums (canonical) or, if lanes_out,
-// lanes_out holds them widened to one 32-bit limb per u64.
-static void* const JB_LANES_EXCHANGE = (void*)(uintptr_t)1;  // sentinel: all-reduce in the kernel epilogue
-
-struct EqRound {
-    const uint64_t* e_out;
-    const uint64_t* e_in;
-    int in_bits;
-};
-
-static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* lanes_out, const EqRound* eqr = nullptr) {
-    jb_ctx* c = mem->ctx;
-    bool do_bind = bind != nullptr;
-    bool hi4 = false;
-    BindScalar s;
-    std::memset(&s, 0, sizeof s);
-    size_t len = mem->len;
-    if (do_bind) {
-        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
-        if (len < 4) return c->fail(JB_ERR_INVALID, "prove_round: no round left after this bind (use finish_rounds)");
-        s = make_scalar(bind, &hi4);
-        len /= 2;
-    } else if (len < 2) {
-        return c->fail(JB_ERR_INVALID, "prove_round: member is fully bound");
-    }
-    size_t pairs = len / 2;
-    TablePtrs tp;
-    std::memset(&tp, 0, sizeof tp);
-    for (int j = 0; j < mem->m; ++j) {
-        Table& t = mem->tables[j];
-        tp.in[j] = t.buf;
-        tp.out[j] = t.buf;
-        if (do_bind && mem->order == JB_LOW_TO_HIGH) {
-            int st = c->ensure_alt(t, len);
-            if (st != JB_OK) return st;
-            tp.out[j] = t.alt;
-        }
-    }
-    RoundOut ro;
-    ro.partial = nullptr;  // set by launch_fused
-    ro.counter = c->d_counter;
-    ro.lanes = lanes_out ? 1 : 0;
-    ro.world = 1;
-    ro.rank = 0;
-    ro.xseq = 0;
-    ro.timeout_cycles = 0;
-    for (int g2 = 0; g2 < 16; ++g2) ro.peer[g2] = nullptr;
-    ro.seq = ++c->result_seq;
-    if (lanes_out == JB_LANES_EXCHANGE) {  // fused all-reduce over peer memory, totals (lanes) to the host
-        ro.lanes = 2;
-        ro.result = c->d_result_alias;
-        ro.flag = c->d_result_alias + 64;
-        for (int g2 = 0; g2 < 16; ++g2) ro.peer[g2] = c->xch_peer[g2];
-        ro.world = c->world;
-        ro.rank = c->rank;
-        ro.xseq = ++c->xch_seq;
-        ro.timeout_cycles = 20000000000LL;
-    } else if (lanes_out) {
-        ro.result = (uint64_t*)lanes_out;
-        ro.flag = nullptr;
-    } else {
-        ro.result = c->d_result_alias;
-        ro.flag = c->d_result_alias + 64;
-    }
-    int st;
-    if (eqr) {
-        tp.e_out = eqr->e_out;
-        tp.e_in = eqr->e_in;
-        tp.in_bits = eqr->in_bits;
-        st = dispatch_weighted(c, mem->m, tp, pairs, do_bind, hi4, s, ro);
-    } else {
-        st = dispatch_fused(c, mem->m, mem->order, skip1, tp, pairs, do_bind, hi4, s, ro);
-    }
-    if (st != JB_OK) return st;
-    if (do_bind) {
-        for (int j = 0; j < mem->m; ++j) {
-            if (mem->order == JB_LOW_TO_HIGH) mem->tables[j].swap_buffers();
-            mem->tables[j].len = len;
-        }
-        mem->len = len;
-    }
-    return JB_OK;
-}
-
-// Spin until the last block of the round's launch has published `seq` (results are then visible).
-static int wait_round_result(jb_ctx* c) {
-    struct Acc { jb_ctx* c; uint64_t t0; ~Acc() { c->diag_wait_ns += now_ns() - t0; c->diag_waits++; } } acc_{c, now_ns()};
-    volatile uint64_t* flag = c->h_result + 64;
-    const uint64_t want = c->result_seq;
-    uint64_t spins = 0;
-    while (*flag != want) {
-        if ((++spins & 0xfffff) == 0) {  // every ~1M spins make sure the stream has not died
-            cudaError_t e = cudaStreamQuery(c->stream);
-            if (e != cudaSuccess && e != cudaErrorNotReady) return c->check(e, "round kernel failed");
-            if (e == cudaSuccess && *flag != want) return c->fail(JB_ERR_CUDA, "round kernel finished without publishing its result");
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    return JB_OK;
-}
-
-// ---- persistent tail -----------------------------------------------------------------------------------
-extern "C++" {
-template <int M>
-static void launch_tail(jb_member* mem, const TailTables& tt) {
-    const long long timeout = 20000000000LL;  // ~10 s of SM clocks without a command: give the SM back
-    if (mem->order == JB_HIGH_TO_LOW)
-        tail_rounds_kernel<M, ORDER_HIGH_TO_LOW><<<1, 512, 0, mem->pt_stream>>>(tt, mem->pt_dev, timeout);
-    else
-        tail_rounds_kernel<M, ORDER_LOW_TO_HIGH><<<1, 512, 0, mem->pt_stream>>>(tt, mem->pt_dev, timeout);
-}
-}  // extern "C++"
-
-static int tail_start(jb_member* mem) {
-    jb_ctx* c = mem->ctx;
-    if (!mem->pt_host) {
-        TailRes r;
-        if (!c->tail_pool.empty()) {
-            r = c->tail_pool.back();
-            c->tail_pool.pop_back();
-        } else if (cudaHostAlloc(&r.mb_host, sizeof(TailMailbox), cudaHostAllocMapped) != cudaSuccess ||
-                   cudaHostGetDevicePointer(&r.mb_dev, r.mb_host, 0) != cudaSuccess ||
-                   cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking) != cudaSuccess ||
-                   cudaEventCreateWithFlags(&r.event, cudaEventDisableTiming) != cudaSuccess) {
-            return c->fail(JB_ERR_OOM, "tail: mailbox / stream allocation failed");
-        }
-        mem->pt_host = (TailMailbox*)r.mb_host;
-        mem->pt_dev = (TailMailbox*)r.mb_dev;
-        mem->pt_stream = r.stream;
-        mem->pt_event = r.event;
-    }
-    std::memset(mem->pt_host, 0, sizeof(TailMailbox));
-    mem->pt_seq = 0;
-    TailTables tt;
-    std::memset(&tt, 0, sizeof tt);
-    tt.len = mem->len;
-    for (int j = 0; j < mem->m; ++j) {
-        Table& t = mem->tables[j];
-        if (mem->order == JB_LOW_TO_HIGH) {
-            int st = c->ensure_alt(t, mem->len / 2 ? mem->len / 2 : 1);
-            if (st != JB_OK) return st;
-        }
-        tt.buf[j] = t.buf;
-        tt.alt[j] = t.alt;
-    }
-    // the tail kernel starts after everything already queued on the context's stream
-    cudaEventRecord(mem->pt_event, c->stream);
-    cudaStreamWaitEvent(mem->pt_stream, mem->pt_event, 0);
-    switch (mem->m) {
-        case 1: launch_tail<1>(mem, tt); break;
-        case 2: launch_tail<2>(mem, tt); break;
-        case 3: launch_tail<3>(mem, tt); break;
-        default: launch_tail<4>(mem, tt); break;
-    }
-    c->launches++;
-    int st = c->check(cudaGetLastError(), "tail_rounds_kernel launch");
-    if (st == JB_OK) mem->pt_active = true;
-    return st;
-}
-
-// Posts one command and spins until the kernel has answered it.
-static int tail_post(jb_member* mem, uint64_t cmd, const uint64_t* challenge, bool skip1) {
-    jb_ctx* c = mem->ctx;
-    const uint64_t t_begin = now_ns();
-    struct Acc { jb_ctx* c; uint64_t t0; ~Acc() { c->diag_wait_ns += now_ns() - t0; c->diag_waits++; } } acc_{c, t_begin};
-    TailMailbox* mb = mem->pt_host;
-    mb->cmd = cmd | ((uint64_t)(skip1 ? 1 : 0) << 8);
-    if (challenge) std::memcpy((void*)mb->challenge, challenge, 32);
-    const uint64_t seq = ++mem->pt_seq;
-    __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
-    uint64_t spins = 0;
-    while (__atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
-        if ((++spins & 0x3fffff) == 0) {
-            cudaError_t e = cudaStreamQuery(mem->pt_stream);
-            if (e != cudaErrorNotReady && __atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
-                mem->pt_active = false;
-                return c->check(e == cudaSuccess ? cudaErrorUnknown : e, "tail kernel exited without answering");
-            }
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    if (mb->status != 0) {
-        mem->pt_active = false;
-        return c->fail(JB_ERR_CUDA, "tail kernel aborted (timeout)");
-    }
-    return JB_OK;
-}
-
-// The kernel has exited (final bind or abort): later work on the context's stream waits for it.
-static void tail_finish(jb_member* mem) {
-    cudaEventRecord(mem->pt_event, mem->pt_stream);
-    cudaStreamWaitEvent(mem->ctx->stream, mem->pt_event, 0);
-    mem->pt_active = false;
-}
-
-static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
-                               uint64_t* out_evals);
-
-static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals);
-
-struct RoundConsts {
-    HostFr w[4], ipow[4], mpow;
-};
-static const RoundConsts& round_consts(int M) {  // M in 2..4
-    static RoundConsts table[5];
-    static const bool init = [] {
-        static const uint64_t binom[5][5] = {{1, 0, 0, 0, 0}, {1, 1, 0, 0, 0}, {1, 2, 1, 0, 0}, {1, 3, 3, 1, 0}, {1, 4, 6, 4, 1}};
-        for (int m = 2; m <= 4; ++m) {
-            for (int i = 0; i < m; ++i) {
-                HostFr ti = HostFr::one();  // i^m
-                for (int e = 0; e < m; ++e) ti = ti * HostFr::from_u64((uint64_t)i);
-                table[m].ipow[i] = ti;
-                const HostFr b = HostFr::from_u64(binom[m][i]);
-                table[m].w[i] = ((m - 1 - i) & 1) ? HostFr::zero() - b : b;
-            }
-            HostFr tm = HostFr::one();  // m^m
-            for (int e = 0; e < m; ++e) tm = tm * HostFr::from_u64((uint64_t)m);
-            table[m].mpow = tm;
-        }
-        return true;
-    }();
-    (void)init;
-    return table[M];
-}
-
-// Assembles s(0..M) from the K published values. Kernel order: s(0), [s(1)], s(2..M-1), s(inf) for
-// M >= 2 (s(0), [s(1)] for M == 1); with skip1, s(1) = claim - s(0). s(M) is rebuilt from the leading
-// coefficient: q(t) = s(t) - s(inf) t^M has degree < M, so q(M) = sum_{i<M} (-1)^(M-1-i) C(M,i) q(i).
-// In verify mode the claim is checked (naive.rs:301-308).
-static int assemble_evals(jb_ctx* c, int M, bool skip1, const uint64_t* vals, const uint64_t* claim, size_t round,
-                          uint64_t* out_evals) {
-    HostFr ev[JB_MAX_EVALS];
-    int k = 0;
-    ev[0] = HostFr::from_limbs(vals + 4 * k++);
-    if (skip1) ev[1] = HostFr::from_limbs(claim) - ev[0];
-    else ev[1] = HostFr::from_limbs(vals + 4 * k++);
-    if (M >= 2) {
-        for (int t = 2; t < M; ++t) ev[t] = HostFr::from_limbs(vals + 4 * k++);
-        const HostFr lead = HostFr::from_limbs(vals + 4 * k++);
-        // s(M) = sum_{i<M} w_i (s(i) - lead i^M) + lead M^M with w_i = (-1)^(M-1-i) C(M,i); the constants are built
-        // once (this runs on the Fiat-Shamir round trip of every round)
-        const RoundConsts& rc = round_consts(M);
-        HostFr qM = HostFr::zero();
-        for (int i = 0; i < M; ++i) qM = qM + rc.w[i] * (ev[i] - lead * rc.ipow[i]);
-        ev[M] = qM + lead * rc.mpow;
-    }
-    for (int t = 0; t <= M; ++t) ev[t].store(out_evals + 4 * t);
-    if (claim && !skip1 && (ev[0] + ev[1]) != HostFr::from_limbs(claim)) {
-        char buf[96];
-        std::snprintf(buf, sizeof buf, "RoundCheckFailed { round: %zu }", round);
-        return c ? c->fail(JB_ERR_ROUND_CHECK, buf) : (int)JB_ERR_ROUND_CHECK;
-    }
-    return JB_OK;
-}
-
-int jb_round_evals_from_kernel_values(int m, int skip_t1, const uint64_t* kernel_values, const uint64_t* claim_or_null,
-                                      uint64_t* out_evals) {
-    if (!kernel_values || !out_evals || m < 1 || m > 4) return JB_ERR_INVALID;
-    if (skip_t1 && !claim_or_null) return JB_ERR_INVALID;
-    const int k = m == 1 ? (skip_t1 ? 1 : 2) : (skip_t1 ? m : m + 1);
-    for (int t = 0; t < k; ++t)
-        if (!canonical_fr(kernel_values + 4 * t)) return JB_ERR_INVALID;
-    if (claim_or_null && !canonical_fr(claim_or_null)) return JB_ERR_INVALID;
-    return assemble_evals(nullptr, m, skip_t1 != 0, kernel_values, claim_or_null, 0, out_evals);
-}
-
-int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
-                          uint64_t* out_evals) {
-    if (!mem || !out_evals) return JB_ERR_INVALID;
-    jb_ctx* c = mem->ctx;
-    if (mem->sharded) {
-        int st = sharded_prove_round(mem, bind, round, claim, out_evals);
-        if (st == JB_OK) mem->rounds_done++;
-        return st;
-    }
-    Guard g(c);
-    if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
-    if ((mem->rounds_done == 0) != (bind == nullptr))
-        return c->fail(JB_ERR_INVALID, "prove_round: bind must be absent exactly on the first round");
-    if (mem->eq) {
-        int st = eq_prove_round(mem, bind, round, claim, out_evals);
-        if (st == JB_OK) mem->rounds_done++;
-        return st;
-    }
-    // With a claim and round verification off (the default, = the reference's optimized tier) the
-    // kernel skips t = 1 and s(1) = claim - s(0); with verification on (or no claim) it computes
-    // every point and the claim, if given, is checked (the reference tier, naive.rs:301-308).
-    const bool skip1 = claim != nullptr && !c->verify_rounds;
-    int st;
-    if (c->use_tail && mem->len <= TAIL_MAX_LEN && mem->len >= (bind ? 4u : 2u)) {
-        // latency path: the persistent tail kernel serves this and every later round of the member
-        if (bind && !canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
-        if (!mem->pt_active && (st = tail_start(mem)) != JB_OK) return st;
-        st = tail_post(mem, bind ? TAIL_CMD_BIND_ROUND : TAIL_CMD_EVAL_ROUND, bind, skip1);
-        if (st != JB_OK) return st;
-        if (bind) {
-            mem->len /= 2;
-            for (auto& t : mem->tables) t.len = mem->len;
-        }
-        st = assemble_evals(c, mem->m, skip1, (const uint64_t*)mem->pt_host->result, claim, round, out_evals);
-        if (st == JB_OK) mem->rounds_done++;
-        return st;
-    }
-    st = member_round(mem, bind, skip1, nullptr);
-    if (st != JB_OK) return st;
-    st = wait_round_result(c);
-    if (st != JB_OK) return st;
-    st = assemble_evals(c, mem->m, skip1, c->h_result, claim, round, out_evals);
-    if (st == JB_OK) mem->rounds_done++;
-    return st;
-}
-
-// ---- split-eq member: one round ------------------------------------------------------------------------
-// scalar <- scalar * eq(w_v, r) for the variable v just bound (GruenSplitEqPolynomial::bind, split_eq.rs:347-352)
-static void eq_absorb_bind(jb_member* mem, size_t var, const uint64_t* r) {
-    HostFr wv = HostFr::from_limbs(mem->eq_w.data() + 4 * var), rr = HostFr::from_limbs(r);
-    HostFr prod = wv * rr;
-    HostFr f = HostFr::one() - wv - rr + prod + prod;
-    (HostFr::from_limbs(mem->eq_scalar) * f).store(mem->eq_scalar);
-}
-
-static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals) {
-    jb_ctx* c = mem->ctx;
-    if (!claim) return c->fail(JB_ERR_INVALID, "eq member: the running claim is required (Gruen hint s(0)+s(1))");
-    const size_t n = mem->eq_n, M = (size_t)mem->m;
-    if (round >= n) return c->fail(JB_ERR_INVALID, "prove_round: member is fully bound");
-    if (bind) {
-        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
-        eq_absorb_bind(mem, n - round, bind);  // the previous round's variable
-    }
-    const size_t cur = n - round;  // unbound variables including the current one (index cur - 1, LowToHigh)
-    const size_t head = cur - 1;
-    const size_t out_bits = head < mem->eq_split ? head : mem->eq_split;
-    const size_t in_bits = head - out_bits;
-    EqRound er;
-    er.e_out = mem->eq_tabs + 4 * (((size_t)1 << out_bits) - 1);
-    er.e_in = mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << in_bits) - 1);
-    er.in_bits = (int)in_bits;
-    // the current variable's linear factor l(t) = l0 + t (l1 - l0) is known before the pass runs
-    const HostFr scalar = HostFr::from_limbs(mem->eq_scalar);
-    const HostFr wc = HostFr::from_limbs(mem->eq_w.data() + 4 * (cur - 1));
-    const HostFr l1 = scalar * wc, l0 = scalar - l1;
-    if (l1.is_zero()) return c->fail(JB_ERR_INVALID, "eq member: current eq evaluation at one must be invertible");
-    int st = member_round(mem, bind, true, nullptr, &er);
-    if (st != JB_OK) return st;
-    // a field inversion is ~400 host multiplications (~13 us): do it while the device runs the pass
-    const HostFr l1_inv = l1.inverse();
-    st = wait_round_result(c);
-    if (st != JB_OK) return st;
-    // kernel order: q(0), q(2), .., q(M-1), q(inf)   (M values; q(0) only for M == 1)
-    const HostFr q0 = HostFr::from_limbs(c->h_result);
-    const HostFr q1 = (HostFr::from_limbs(claim) - l0 * q0) * l1_inv;
-    uint64_t vals[JB_MAX_EVALS * 4], qe[JB_MAX_EVALS * 4];
-    q0.store(vals);
-    q1.store(vals + 4);
-    if (M > 1) std::memcpy(vals + 8, c->h_result + 4, (M - 1) * 32);
-    st = assemble_evals(c, (int)M, false, vals, nullptr, round, qe);  // q(0..M)
-    if (st != JB_OK) return st;
-    // q(M+1) by extrapolation (degree M), then s(t) = l(t) q(t), t = 0..M+1
-    std::vector<HostFr> qv(M + 1);
-    for (size_t t = 0; t <= M; ++t) qv[t] = HostFr::from_limbs(qe + 4 * t);
-    jb::UnivariatePoly qp = jb::UnivariatePoly::from_evals(qv);
-    const HostFr dl = l1 - l0;
-    HostFr lt = l0;
-    for (size_t t = 0; t <= M + 1; ++t) {
-        HostFr qt = t <= M ? qv[t] : qp.evaluate(HostFr::from_u64(t));
-        (lt * qt).store(out_evals + 4 * t);
-        lt = lt + dl;
-    }
-    return JB_OK;
-}
-
-int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint64_t* w, size_t nvars,
-                        const uint64_t* scale_or_null, int order, jb_member** out) {
-    if (!c || !handles || !w || !out) return JB_ERR_INVALID;
-    if (order != JB_LOW_TO_HIGH) return c->fail(JB_ERR_UNSUPPORTED, "eq member: LowToHigh binding only");
-    if (m < 1 || m > 3) return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
-    for (size_t i = 0; i < nvars; ++i)
-        if (!canonical_fr(w + 4 * i)) return c->fail(JB_ERR_INVALID, "eq member: point limbs not canonical");
-    if (scale_or_null && !canonical_fr(scale_or_null)) return c->fail(JB_ERR_INVALID, "eq member: scale not canonical");
-    int st = jb_member_create(c, handles, m, order, out);
-    if (st != JB_OK) return st;
-    jb_member* mem = *out;
-    if (mem->rounds != nvars || nvars == 0) {
-        jb_member_destroy(mem);
-        *out = nullptr;
-        return c->fail(JB_ERR_INVALID, "eq member: point length must equal log2(table length) >= 1");
-    }
-    {
-    Guard g(c);
-    mem->eq = true;
-    mem->eq_n = nvars;
-    mem->eq_split = nvars / 2;
-    mem->eq_w.assign(w, w + 4 * nvars);
-    HostFr sc = scale_or_null ? HostFr::from_limbs(scale_or_null) : HostFr::one();
-    sc.store(mem->eq_scalar);
-    // prefix tables (EqPolynomial::evals_cached, eq.rs:322-340): Eo[k] over w[0..k), Ei[k] over w[split..split+k)
-    const size_t split = mem->eq_split, nin = nvars - 1 - (split < nvars - 1 ? split : nvars - 1);
-    const size_t out_max = split < nvars - 1 ? split : nvars - 1;
-    mem->eq_in_base = ((size_t)2 << out_max) - 1;
-    const size_t total = mem->eq_in_base + ((size_t)2 << nin) - 1;
-    st = c->dev_alloc((void**)&mem->eq_tabs, total * 32);
-    for (size_t k = 0; k <= out_max && st == JB_OK; ++k)
-        st = eq_build(c, w, k, nullptr, mem->eq_tabs + 4 * (((size_t)1 << k) - 1));
-    for (size_t k = 0; k <= nin && st == JB_OK; ++k)
-        st = eq_build(c, w + 4 * split, k, nullptr, mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << k) - 1));
-    }  // the context lock is released before the member is torn down (jb_member_destroy takes it)
-    if (st != JB_OK) {
-        jb_member_destroy(mem);
-        *out = nullptr;
-    }
-    return st;
-}
-
-// eq(w, r) * scale after all rounds (the member's eq factor of the final claim)
-int jb_eq_member_scalar(jb_member* mem, uint64_t out[4]) {
-    if (!mem || !out || !mem->eq) return JB_ERR_INVALID;
-    std::memcpy(out, mem->eq_scalar, 32);
-    return JB_OK;
-}
-
-// ---- index-sharded member ----------------------------------------------------------------------
-// HighToLow shards are strided (rank g owns global[j * G + g]): gathered[g][j] -> global[j * G + g]
-static __global__ void __launch_bounds__(256) interleave_shards_kernel(const uint64_t* gathered, uint64_t* global, size_t len,
-                                                                       size_t G) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= len * G) return;
-    const size_t g = idx / len, j = idx % len;
-    st_elem(global, j * G + g, ld_elem<Fr>(gathered, idx));
-}
-
-static int gather_into_tail(jb_member* mem) {  // called with the context lock held
-    jb_ctx* c = mem->ctx;
-    const size_t len = mem->len, G = (size_t)c->world;
-    jb_member* tail = new (std::nothrow) jb_member();
-    if (!tail) return JB_ERR_OOM;
-    tail->ctx = c;
-    tail->m = mem->m;
-    tail->order = mem->order;
-    tail->len = len * G;
-    tail->rounds = 0;
-    while (((size_t)1 << tail->rounds) < tail->len) ++tail->rounds;
-    int st = JB_OK;
-    for (int j = 0; j < mem->m && st == JB_OK; ++j) {
-        Table t;
-        st = c->dev_alloc((void**)&t.buf, tail->len * 32);
-        if (st != JB_OK) break;
-        t.cap = t.len = tail->len;
-        tail->tables.push_back(t);  // owned by the tail from here on (released below on failure)
-        if (mem->order == JB_LOW_TO_HIGH) {
-            // rank order == global order for contiguous blocks under LowToHigh binding
-            st = c->comm_allgather(mem->tables[j].buf, t.buf, len * 4);
-        } else {
-            uint64_t* tmp = nullptr;
-            st = c->dev_alloc((void**)&tmp, tail->len * 32);
-            if (st == JB_OK) st = c->comm_allgather(mem->tables[j].buf, tmp, len * 4);
-            if (st == JB_OK) {
-                interleave_shards_kernel<<<(unsigned)((tail->len + 255) / 256), 256, 0, c->stream>>>(tmp, t.buf, len, G);
-                c->launches++;
-                st = c->check(cudaGetLastError(), "interleave_shards launch");
-            }
-            c->dev_free(tmp);
-        }
-    }
-    if (st != JB_OK) {
-        for (auto& t : tail->tables) c->release(t);
-        delete tail;
-        return st;
-    }
-    mem->tail = tail;
-    return JB_OK;
-}
-
-static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
-                               uint64_t* out_evals) {
-    jb_ctx* c = mem->ctx;
-    {
-        Guard g(c);
-        if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
-        if (!mem->tail) {
-            const size_t len_after = bind ? mem->len / 2 : mem->len;
-            if (len_after > mem->gather_len) {
-                // a sharded round: local fused pass -> lanes -> ONE all-reduce -> publish -> host fold
-                const bool skip1 = claim != nullptr && !c->verify_rounds;
-                const int K = skip1 ? mem->m : mem->m + 1;
-                int st;
-                if (c->xch_ready) {
-                    // the all-reduce rides in the round kernel's epilogue over NVLink peer memory
-                    st = member_round(mem, bind, skip1, JB_LANES_EXCHANGE);
-                } else {
-                    st = member_round(mem, bind, skip1, c->d_lanes);
-                    if (st == JB_OK) st = c->comm_allreduce_lanes(c->d_lanes, (size_t)K * 8);
-                    if (st == JB_OK) st = c->publish_lanes(c->d_lanes, K * 8);
-                }
-                if (st == JB_OK) st = wait_round_result(c);
-                if (st != JB_OK) return st;
-                if (c->h_result[0] == ~0ull && c->h_result[1] == ~0ull)
-                    return c->fail(JB_ERR_CUDA, "peer exchange timed out (a rank did not arrive)");
-                uint64_t vals[JB_MAX_EVALS * 4];
-                st = jb_lanes_reduce_host(c->h_result, (size_t)K, vals);
-                if (st != JB_OK) return st;
-                return assemble_evals(c, mem->m, skip1, vals, claim, round, out_evals);
-            }
-            // the shard is small: apply the pending bind, gather, continue on the tail
-            if (bind) {
-                for (int j = 0; j < mem->m; ++j) {
-                    int st = bind_table(c, mem->tables[j], bind, mem->order);
-                    if (st != JB_OK) return st;
-                }
-                mem->len /= 2;
-                bind = nullptr;
-            }
-            int st = gather_into_tail(mem);
-            if (st != JB_OK) return st;
-        }
-    }
-    return jb_member_prove_round(mem->tail, bind, mem->tail->rounds_done, claim, out_evals);
-}
-
-int jb_sharded_member_create(jb_ctx* c, const jb_table* handles, size_t m, int order, size_t gather_log, jb_member** out) {
-    if (!c || !out) return JB_ERR_INVALID;
-    if (!c->nccl_comm) return c->fail(JB_ERR_INVALID, "sharded member: no communicator (jb_comm_init)");
-    if (order != JB_LOW_TO_HIGH && order != JB_HIGH_TO_LOW) return c->fail(JB_ERR_INVALID, "sharded member: unknown binding order");
-    int st = jb_member_create(c, handles, m, order, out);
-    if (st != JB_OK) return st;
-    jb_member* mem = *out;
-    size_t log_g = 0;
-    while ((1 << log_g) < c->world) ++log_g;
-    mem->sharded = true;
-    mem->gather_len = (size_t)1 << gather_log;
-    if (mem->gather_len > mem->len) mem->gather_len = mem->len;
-    mem->rounds += log_g;
-    return JB_OK;
-}
-
-int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind, size_t round, int skip_t1, void* lanes_out) {
-    (void)round;
-    if (!mem || !lanes_out) return JB_ERR_INVALID;
-    Guard g(mem->ctx);
-    return member_round(mem, bind, skip_t1 != 0, lanes_out);
-}
-
-int jb_ctx_set_verify_rounds(jb_ctx* c, int on) {
-    if (!c) return JB_ERR_INVALID;
-    Guard g(c);
-    c->verify_rounds = on != 0;
-    return JB_OK;
-}
-
-// carry-propagate 8 x (sums of 32-bit limbs) and fold mod r: O(count) host work, no device needed.
-int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out) {
-    if (!lanes || !out) return JB_ERR_INVALID;
-    for (size_t k = 0; k < count; ++k) {
-        const uint64_t* lane = lanes + 8 * k;
-        uint32_t w[10];
-        unsigned __int128 carry = 0;
-        for (int i = 0; i < 8; ++i) {
-            carry += lane[i];
-            w[i] = (uint32_t)carry;
-            carry >>= 32;
-        }
-        w[8] = (uint32_t)carry;
-        w[9] = (uint32_t)(carry >> 32);
-        // value < 2^32 * r < 2^286; fold by subtracting (r << sh) from the top down
-        uint64_t v[5] = {(uint64_t)w[0] | ((uint64_t)w[1] << 32), (uint64_t)w[2] | ((uint64_t)w[3] << 32),
-                         (uint64_t)w[4] | ((uint64_t)w[5] << 32), (uint64_t)w[6] | ((uint64_t)w[7] << 32),
-                         (uint64_t)w[8] | ((uint64_t)w[9] << 32)};
-        for (int sh = 33; sh >= 0; --sh) {
-            uint64_t ps[5] = {0, 0, 0, 0, 0};  // r << sh
-            for (int i = 0; i < 4; ++i) {
-                ps[i] |= sh ? (HostFr::P[i] << sh) : HostFr::P[i];
-                if (sh) ps[i + 1] |= HostFr::P[i] >> (64 - sh);
-            }
-            bool ge = true;
-            for (int i = 4; i >= 0; --i)
-                if (v[i] != ps[i]) { ge = v[i] > ps[i]; break; }
-            if (ge) {
-                uint64_t borrow = 0;
-                for (int i = 0; i < 5; ++i) {
-                    unsigned __int128 t = (unsigned __int128)v[i] - ps[i] - borrow;
-                    v[i] = (uint64_t)t;
-                    borrow = (uint64_t)(t >> 64) & 1;
-                }
-            }
-        }
-        std::memcpy(out + 4 * k, v, 32);
-    }
-    return JB_OK;
-}
-
-int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint64_t* out) {
-    if (!c || !device_lanes || !out || count == 0 || count * 64 > JB_SMALL_BYTES) return JB_ERR_INVALID;
-    Guard g(c);
-    int st = c->check(cudaMemcpyAsync(c->h_small, device_lanes, count * 64, cudaMemcpyDeviceToHost, c->stream),
-                      "partials D2H");
-    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "partials sync");
-    if (st != JB_OK) return st;
-    return jb_lanes_reduce_host(c->h_small, count, out);
-}
-
-// Copies table j of a member (its current, possibly partly bound, contents) into caller device memory.
-int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t cap_elems, size_t* len_out) {
-    if (!mem || !device_dst) return JB_ERR_INVALID;
-    jb_ctx* c = mem->ctx;
-    Guard g(c);
-    if (j >= (size_t)mem->m) return c->fail(JB_ERR_INVALID, "export_table: table index out of range");
-    if (cap_elems < mem->len) return c->fail(JB_ERR_INVALID, "export_table: destination too small");
-    if (len_out) *len_out = mem->len;
-    return c->check(cudaMemcpyAsync(device_dst, mem->tables[j].buf, mem->len * 32, cudaMemcpyDeviceToDevice, c->stream),
-                    "export_table D2D");
-}
-
-int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
-    if (!mem || !bind) return JB_ERR_INVALID;
-    jb_ctx* c = mem->ctx;
-    if (mem->sharded) {
-        if (!mem->tail) return c->fail(JB_ERR_INVALID, "finish_rounds: sharded member has not reached its tail");
-        return jb_member_finish_rounds(mem->tail, bind);
-    }
-    Guard g(c);
-    if (mem->len < 2) return c->fail(JB_ERR_INVALID, "finish_rounds: member already fully bound");
-    if (mem->eq) {
-        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
-        size_t var = 0;
-        for (size_t l = mem->len; l > 2; l >>= 1) ++var;  // index of the variable being bound (LowToHigh)
-        eq_absorb_bind(mem, var, bind);
-    }
-    if (mem->pt_active) {
-        if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
-        int st = tail_post(mem, TAIL_CMD_FINAL_BIND, bind, false);
-        tail_finish(mem);
-        if (st != JB_OK) return st;
-        mem->len /= 2;
-        for (auto& t : mem->tables) t.len = mem->len;
-        if (mem->len == 1) {  // the kernel also returned the fully bound values: no device read-back later
-            std::memcpy(mem->final_vals, (const void*)mem->pt_host->result, (size_t)mem->m * 32);
-            mem->has_final = true;
-        }
-        return JB_OK;
-    }
-    for (int j = 0; j < mem->m; ++j) {
-        int st = bind_table(c, mem->tables[j], bind, mem->order);
-        if (st != JB_OK) return st;
-    }
-    mem->len /= 2;
-    return JB_OK;
-}
-
-int jb_member_final_evals(jb_member* mem, uint64_t* out) {
-    if (!mem || !out) return JB_ERR_INVALID;
-    jb_ctx* c = mem->ctx;
-    if (mem->sharded) {
-        if (!mem->tail) return c->fail(JB_ERR_INVALID, "NotFullyBound (sharded member before its tail)");
-        return jb_member_final_evals(mem->tail, out);
-    }
-    Guard g(c);
-    if (mem->has_final) {
-        std::memcpy(out, mem->final_vals, (size_t)mem->m * 32);
-        return JB_OK;
-    }
-    if (mem->len != 1) {
-        char buf[96];
-        size_t remaining = 0;
-        for (size_t l = mem->len; l > 1; l >>= 1) ++remaining;
-        std::snprintf(buf, sizeof buf, "NotFullyBound { remaining: %zu }", remaining);
-        return c->fail(JB_ERR_INVALID, buf);
-    }
-    for (int j = 0; j < mem->m; ++j) {
-        int st = c->check(cudaMemcpyAsync(c->h_small + 4 * j, mem->tables[j].buf, 32, cudaMemcpyDeviceToHost, c->stream),
-                          "final evals D2H");
-        if (st != JB_OK) return st;
-    }
-    int st = c->check(cudaStreamSynchronize(c->stream), "final evals sync");
-    if (st != JB_OK) return st;
-    std::memcpy(out, c->h_small, (size_t)mem->m * 32);
-    return JB_OK;
-}
-
-void jb_member_destroy(jb_member* mem) {
-    if (!mem) return;
-    if (mem->tail) jb_member_destroy(mem->tail);
-    if (mem->pt_active) {
-        Guard g(mem->ctx);
-        tail_post(mem, TAIL_CMD_ABORT, nullptr, false);
-        tail_finish(mem);
-    }
-    if (mem->eq_tabs) {
-        Guard g(mem->ctx);
-        mem->ctx->dev_free(mem->eq_tabs);
-    }
-    if (mem->pt_host) {  // back to the context's pool (the kernel has exited: tail_finish ran)
-        Guard g(mem->ctx);
-        TailRes r;
-        r.mb_host = mem->pt_host;
-        r.mb_dev = mem->pt_dev;
-        r.stream = mem->pt_stream;
-        r.event = mem->pt_event;
-        mem->ctx->tail_pool.push_back(r);
-    }
-    {
-        Guard g(mem->ctx);
-        for (auto& t : mem->tables) mem->ctx->release(t);
-    }
-    delete mem;
-}
 
 // ---- element-wise parity harness ---------------------------------------------------------------
 int jb_vec_op(jb_ctx* c, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {

@@ -19,10 +19,7 @@ using namespace jb;
 
 namespace {
 
-struct Guard {
-    std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
-};
+using Guard = CtxGuard;
 
 __device__ __forceinline__ Fr promote(const uint32_t mag[4], bool neg) {
     Fr k = Fr::zero();

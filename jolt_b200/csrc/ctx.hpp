@@ -13,6 +13,7 @@
 
 constexpr int JB_MAX_EVALS = 8;                 // degree + 1 <= 8
 constexpr size_t JB_SMALL_BYTES = 4096;         // staging for round evaluations / points
+constexpr int JB_RESULT_SLOTS = 16;             // host-mapped round-result slots (1 KiB each; slot 0 = in-place rounds)
 
 struct Table {
     uint64_t* buf = nullptr;  // current data (len elements)
@@ -41,12 +42,14 @@ struct Srs {
 };
 
 struct MsmWorkspace;  // msm.cu
+struct ResidentRun;   // resident.cu: one launched resident_rounds_kernel and the members it serves
 
-// Host-mapped mailbox + private stream + event for one persistent tail kernel; pooled per context so a
-// member entering its tail pays no allocation (cudaHostAlloc / stream creation cost tens of microseconds).
+// Host-mapped mailbox + device state + private stream + event for one resident kernel; pooled per context so
+// a batch entering resident service pays no allocation (cudaHostAlloc / stream creation cost tens of microseconds).
 struct TailRes {
     void* mb_host = nullptr;
     void* mb_dev = nullptr;
+    void* d_state = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t event = nullptr;
 };
@@ -54,7 +57,8 @@ struct TailRes {
 // Optional per-launch CUDA-event timing of the dominant kernels (bench.py's roofline figure is
 // measured live, on this stream, inside the timed region).
 struct TimedLaunch {
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;  // null: a pass inside a resident kernel, timed by the device (ms_direct)
+    double ms_direct = 0;
     int kind;        // 0 = fused bind+eval, 1 = bind, 2 = eval-only, 3 = eq, 4 = msm bucket accumulation
     uint64_t items;  // pairs / outputs / terms
     int m;
@@ -75,12 +79,23 @@ struct jb_ctx {
     size_t partial_cap = 0;         // in elements
     std::vector<TailRes> tail_pool;
     uint64_t diag_wait_ns = 0, diag_waits = 0;  // host time spent waiting for round results
-    bool use_tail = true;           // persistent tail kernel for short rounds
+    bool use_tail = true;           // resident kernel service (off under profilers / JB_NO_TAIL: one launch per round)
+    int resident_max_log = 40;      // a member may enter resident service when log2(len) <= this (JB_RESIDENT_MAX_LOG)
+    std::vector<ResidentRun*> runs; // live resident kernels of this context
+    // diagnostics: per round of the last completed run: device %globaltimer at command decode / after the fold,
+    // host CLOCK_MONOTONIC at post / at receipt (ns)
+    uint64_t last_run_log[8 * 64] = {0};
+    size_t last_run_rounds = 0;
+    // Stops resident kernels that would starve other work of SMs (an exclusive run holds every block slot of the
+    // device): called by every entry point that launches or waits on the context's stream. `all`: also the small
+    // (<= half the device) runs. The members they served continue with one launch per round.
+    void quiesce_resident(bool all = false);
+    bool has_exclusive_run() const;
     int fused_shape = 0;            // fused-kernel occupancy shape (see launch_fused)
     bool verify_rounds = false;     // compute s(1) and check s(0)+s(1)==claim instead of deriving s(1)
     uint64_t* d_small = nullptr;    // device staging
     uint64_t* h_small = nullptr;    // pinned host staging
-    // zero-copy round results: pinned + mapped; [0, 64) u64 results, [64] sequence flag
+    // zero-copy round results: pinned + mapped; JB_RESULT_SLOTS slots of 128 u64: [0, 64) results, [64] sequence flag
     uint64_t* h_result = nullptr;
     uint64_t* d_result_alias = nullptr;  // device address of h_result
     unsigned int* d_counter = nullptr;   // last-block ticket counter (zero between launches)
@@ -174,4 +189,15 @@ struct jb_ctx {
         t.buf = t.alt = nullptr;
     }
     void msm_release();
+};
+
+// Serialises a context's entry points (a context = one ProofSession; Rayon threads may call msm concurrently,
+// crates/jolt-hyperkzg/src/scheme.rs:141-145). keep_resident: the caller is the resident round path itself.
+struct CtxGuard {
+    jb_ctx* c;
+    std::lock_guard<std::mutex> lk;
+    explicit CtxGuard(jb_ctx* ctx, bool keep_resident = false) : c(ctx), lk(ctx->mu) {
+        ctx->make_current();
+        if (!keep_resident && !ctx->runs.empty()) ctx->quiesce_resident(false);
+    }
 };

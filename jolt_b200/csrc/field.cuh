@@ -431,72 +431,31 @@ __device__ __forceinline__ void mul_wide_acc_smem(uint32_t* acc, int stride, con
     for (int k = 0; k < 17; ++k) acc[k * stride] = A[k];
 }
 
-// 544-bit accumulator (17 words at acc[k * stride]) -> canonical acc * R^-1 mod p. One-off per thread.
+// 544-bit accumulator (17 words at acc[k * stride]) -> canonical acc * R^-1 mod p. It sits on the latency path of
+// every sumcheck round (one lane per value reduces the block's column sums), so it is three Montgomery products on
+// the fast IMAD.WIDE rows instead of a word-serial 64-bit loop: with acc = lo + hi R + top R^2 (R = 2^256),
+//   acc R^-1 = REDC(lo) + hi + top R  (mod p),   REDC(lo) = montmul(1, lo),  hi mod p = montmul(R mod p, hi),
+//   top R mod p = montmul(R^2 mod p, top).
+// The wide operand is always the MULTIPLIER (consumed one 32-bit word per row, any value allowed); the multiplicand
+// is a constant < p, which is what the row bounds of mont_step assume. Each product is < 2p, the sum < 5p + 1 < 2^256.
 template <class PR>
 __device__ __forceinline__ Fp<PR> reduce_wide17(const uint32_t* acc, int stride) {
-    uint32_t T[17];
-#pragma unroll
-    for (int k = 0; k < 17; ++k) T[k] = acc[k * stride];
-    // fold the top word: 2^512 == R^2 (mod p). Twice: the first fold can carry out once more.
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        uint32_t top = T[16];
-        T[16] = 0;
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint64_t t = (uint64_t)top * PR::R2(j) + T[j] + carry;
-            T[j] = (uint32_t)t;
-            carry = t >> 32;
-        }
-#pragma unroll
-        for (int l = 8; l < 17; ++l) {
-            uint64_t t = (uint64_t)T[l] + carry;
-            T[l] = (uint32_t)t;
-            carry = t >> 32;
-        }
-    }
-    // Montgomery reduction of T[0..15] with T[16] catching the carry
+    Fp<PR> lo, hi, top = Fp<PR>::zero(), one_raw = Fp<PR>::zero();
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        uint32_t m = T[k] * PR::INV;
-        uint64_t carry = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint64_t t = (uint64_t)m * PR::P(j) + T[k + j] + carry;
-            T[k + j] = (uint32_t)t;
-            carry = t >> 32;
-        }
-#pragma unroll
-        for (int l = k + 8; l < 17; ++l) {
-            uint64_t t = (uint64_t)T[l] + carry;
-            T[l] = (uint32_t)t;
-            carry = t >> 32;
-        }
+        lo.v[k] = acc[k * stride];
+        hi.v[k] = acc[(8 + k) * stride];
     }
-    // result = T[8..16] < 2^256 + p: subtract p while it does not fit / is not canonical
-    uint32_t r[9];
+    top.v[0] = acc[16 * stride];
+    one_raw.v[0] = 1;
+    Fp<PR> r = fp_mul_lazy(one_raw, lo);
+    const Fp<PR> h = fp_mul_lazy(Fp<PR>::one(), hi);
+    const Fp<PR> t = fp_mul_lazy(Fp<PR>::r2(), top);
+    add8<PR>(r.v, r.v, h.v);
+    add8<PR>(r.v, r.v, t.v);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) r[k] = T[8 + k];
-#pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-        uint32_t t[9];
-        uint64_t borrow = 0;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) {
-            uint64_t pj = j < 8 ? PR::P(j) : 0u;
-            uint64_t d = (uint64_t)r[j] - pj - borrow;
-            t[j] = (uint32_t)d;
-            borrow = (d >> 32) & 1u;
-        }
-        if (borrow) break;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) r[j] = t[j];
-    }
-    Fp<PR> out;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out.v[k] = r[k];
-    return out;
+    for (int it = 0; it < 5; ++it) cond_sub_p<PR>(r.v);
+    return r;
 }
 
 using Fr = Fp<FrParams>;

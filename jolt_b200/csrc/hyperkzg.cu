@@ -238,10 +238,7 @@ HornerParams horner_params(const HostFr u[HZ_POINTS], int L) {
     return hp;
 }
 
-struct Guard {
-    std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
-};
+using Guard = CtxGuard;
 
 // chunk length so that a polynomial of `len` coefficients needs <= 1024 blocks of 256 chunks
 int chunk_for(size_t len) {

@@ -1,0 +1,104 @@
+// Internals shared by the sumcheck-member translation units (member.cu, resident.cu, capi.cu).
+#pragma once
+#include <cstring>
+#include <ctime>
+#include <vector>
+
+#include "ctx.hpp"
+#include "host_fr.hpp"
+#include "poly_kernels.cuh"
+
+namespace jbi {
+
+using jb::BindScalar;
+using jb::HostFr;
+
+inline uint64_t now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+inline BindScalar make_scalar(const uint64_t r[4], bool* hi4) {
+    BindScalar s;
+    for (int i = 0; i < 4; ++i) {
+        s.w[2 * i] = (uint32_t)r[i];
+        s.w[2 * i + 1] = (uint32_t)(r[i] >> 32);
+    }
+    *hi4 = (r[0] == 0 && r[1] == 0);
+    return s;
+}
+
+inline bool canonical_fr(const uint64_t r[4]) { return !HostFr::geq_p(r); }
+
+// capi.cu
+int bind_table(jb_ctx* c, Table& t, const uint64_t r[4], int order);  // Polynomial::bind_with_order on one table
+int eq_build(jb_ctx* c, const uint64_t* r, size_t nvars, const uint64_t* scale, uint64_t* d_out);
+
+// Accumulates the host time spent waiting for a round result (jb_ctx_diag).
+struct WaitAcc {
+    jb_ctx* c;
+    uint64_t t0;
+    explicit WaitAcc(jb_ctx* ctx) : c(ctx), t0(now_ns()) {}
+    ~WaitAcc() {
+        c->diag_wait_ns += now_ns() - t0;
+        c->diag_waits++;
+    }
+};
+
+}  // namespace jbi
+
+// One ProveRounds member on the device (~ Box<dyn SumcheckKernel>): the relation
+//   sum_x sum_{k<P} prod_{j<D} f_{kD+j}(x)       (degree D, T = D * P dense tables)
+// optionally weighted by a split eq polynomial, optionally index-sharded over ranks.
+struct jb_member {
+    jb_ctx* ctx;
+    std::vector<Table> tables;
+    int m;       // D: factors per term = degree of the (unweighted) relation
+    int terms = 1;  // P
+    int order;
+    size_t rounds;  // total (for a sharded member: local rounds + log2(world))
+    size_t len;     // current (local) table length
+    size_t rounds_done = 0;  // prove_round calls completed
+    // index-sharded member: this rank holds the contiguous block `rank` of the global
+    // tables; rounds run with one all-reduce each until the shard is `gather_len` long, then the
+    // shards are all-gathered into `tail`, which finishes the remaining rounds locally.
+    bool sharded = false;
+    size_t gather_len = 0;
+    jb_member* tail = nullptr;
+    // split-eq member (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): the relation is
+    // sum_x eq(w, x) prod_j f_j(x); eq is never materialised - per round the sweep is weighted by
+    // E_out (x) E_in over the not-yet-current variables and the current variable's linear factor
+    // l(t) = scalar * ((1 - w_cur) + t (2 w_cur - 1)) is multiplied in on the host.
+    bool eq = false;
+    size_t eq_n = 0, eq_split = 0;
+    std::vector<uint64_t> eq_w;        // n elements, w[0] <-> most significant index bit
+    uint64_t eq_scalar[4] = {0, 0, 0, 0};
+    uint64_t* eq_tabs = nullptr;       // prefix tables Eo[k] (k <= split) then Ei[k] (k <= n-1-split), table k at 2^k - 1
+    size_t eq_in_base = 0;             // element offset of the Ei family
+    // resident service (resident.cuh): the launched kernel that serves this member's rounds from a mailbox
+    ResidentRun* run = nullptr;
+    int run_idx = 0;
+    bool no_resident = false;  // a run of this member was stopped to make room for other work: stay on launches
+    bool has_final = false;
+    uint64_t final_vals[jb::JB_MAX_TABLES * 4];
+    int ntables() const { return m * terms; }
+};
+
+// resident.cu ------------------------------------------------------------------------------------------------
+// Starts a resident kernel serving `n` members (same D, P, order, same context; n <= RES_MAX_MEMBERS). Members
+// must be plain (not eq / sharded-with-tail). `exchange`: the kernel may be asked to all-reduce member 0's sums
+// over peer memory (sharded rounds). JB_ERR_UNSUPPORTED = not eligible (caller falls back to launches).
+int resident_begin(jb_ctx* c, jb_member** mems, int n);
+// One round for the whole run. actions[i] in RES_ACT_*; challenge may be null when no action binds. `out`
+// (may be null) receives n x RES_SLOT_U64 mailbox words: per member K canonical values (4 u64 each), or - with
+// `exchange` - member 0's K x 8 all-reduced u64 lanes. Host-side table state (len, ping-pong) is advanced and the
+// run is released when every member is fully bound (the run pointer is dead after that: check mem->run).
+// post + wait may be split to overlap several runs / launches.
+int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange);
+int resident_wait(ResidentRun* run, uint64_t* out);
+int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out);
+int resident_run_size(const ResidentRun* run);
+// Stops the kernel (if it still runs), orders the context's stream after it and detaches the members.
+void resident_end(ResidentRun* run, bool mark_no_resident);
+bool resident_eligible(const jb_member* mem);

@@ -625,10 +625,7 @@ bool canonical_q(const uint64_t* a) {
     return false;
 }
 
-struct Guard {
-    std::lock_guard<std::mutex> lk;
-    explicit Guard(jb_ctx* c) : lk(c->mu) { c->make_current(); }
-};
+using Guard = CtxGuard;
 
 // `srs`: the resident bases; terms are bases[offset .. offset + n).
 int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, size_t n, uint64_t out_xyz[12],

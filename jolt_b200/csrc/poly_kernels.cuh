@@ -232,9 +232,11 @@ __device__ __forceinline__ void round_epilogue(Fr (&acc)[K], uint32_t* smem, con
     }
 }
 
+constexpr int JB_MAX_TABLES = 8;  // tables of one member: D factors x P terms
+
 struct TablePtrs {
-    const uint64_t* in[4];
-    uint64_t* out[4];
+    const uint64_t* in[JB_MAX_TABLES];
+    uint64_t* out[JB_MAX_TABLES];
     // WEIGHTED passes (split-eq members): the pair y carries the weight e_out[y >> in_bits] * e_in[y & mask]
     // (TensorEqTable::evaluate_index, crates/jolt-poly/src/split_eq.rs:52-56); both tables are ~sqrt(N) long.
     const uint64_t* e_out;
@@ -242,49 +244,55 @@ struct TablePtrs {
     int in_bits;
 };
 
-// Fused pass for a product-of-M member:
+// Fused pass for a sum-of-products member  sum_x sum_{k<P} prod_{j<D} f_{kD+j}(x)  (degree D, T = D*P tables;
+// P = 1 is the plain product member; D = 2, P = 2 is the reference's IncClaimReduction summand
+// A*RamInc + B*RdInc, crates/jolt-kernels/src/optimized/inc_claim_reduction.rs:146-156):
 //   BIND: first fold every table under `s` (writing the bound table), then
-//   sweep the BOUND tables for the round polynomial s(t) = sum_y prod_j (lo_j(y) + t D_j(y)),
-//   D_j = hi_j - lo_j. The kernel emits K values, in this order:
-//     s(0), [s(1) unless SKIP1], s(2), .., s(M-1), s(inf)          (M >= 2)
-//     s(0), [s(1) unless SKIP1]                                    (M == 1)
-//   where s(inf) = sum_y prod_j D_j(y) is the leading coefficient: evaluating at infinity instead of
-//   t = M needs no lo + t*D advance at all for M = 2 (s(1) uses hi_j directly), the same trade the
+//   sweep the BOUND tables for the round polynomial s(t) = sum_y sum_k prod_j (lo_j(y) + t D_j(y)),
+//   D_j = hi_j - lo_j. The pass emits K values, in this order:
+//     s(0), [s(1) unless SKIP1], s(2), .., s(D-1), s(inf)          (D >= 2)
+//     s(0), [s(1) unless SKIP1]                                    (D == 1)
+//   where s(inf) = sum_y sum_k prod_j D_j(y) is the leading coefficient: evaluating at infinity instead of
+//   t = D needs no lo + t*D advance at all for D = 2 (s(1) uses hi_j directly), the same trade the
 //   reference makes in UnivariatePoly::from_evals_toom / the optimized tier's skipped evaluations
 //   (jolt-poly/src/univariate.rs:219-, jolt-kernels/src/optimized/support.rs:450-460). With SKIP1
-//   the host derives s(1) = previous_claim - s(0). The host rebuilds s(M) (capi.cu, assemble_evals).
+//   the host derives s(1) = previous_claim - s(0). The host rebuilds s(D) (capi.cu, assemble_evals).
 // `pairs` = number of y indices = (bound length)/2. Layout:
 //   HighToLow, BIND : reads e[y], e[y+P], e[y+2P], e[y+3P] (P = pairs); writes e'[y], e'[y+P] in place
 //   LowToHigh, BIND : reads e[4y..4y+3]; writes out[2y], out[2y+1]   (out-of-place)
 //   no BIND         : reads the pair only, writes nothing
 // The last factor of every product is multiplied in WITHOUT reduction into a 544-bit per-thread
 // accumulator kept in SHARED memory (mul_wide_acc_smem; the GPU form of the reference's
-// WideAccumulator) and reduced once after the loop, which keeps the register count low enough for
-// three blocks per SM. M == 1 has no product and accumulates plain field sums. Each block then
-// writes its sums and the last block folds them (round_epilogue). All sums are exact field values,
-// so the reduction order does not matter.
-template <int M, bool SKIP1>
+// WideAccumulator) and reduced once per BLOCK after the loop. D == 1 has no product and accumulates plain
+// field sums. All sums are exact field values, so the reduction order does not matter.
+template <int D, bool SKIP1>
 struct FusedShape {
-    static constexpr int K = SKIP1 ? M : M + 1;  // number of values produced
-    // dynamic shared memory: K accumulators x 17 words x 256 threads (M > 1) + the block-sum scratch
-    __host__ __device__ static constexpr size_t acc_words(int block) { return (M == 1) ? 0 : (size_t)K * 17 * block; }
+    static constexpr int K = SKIP1 ? D : D + 1;  // number of values produced
+    // dynamic shared memory: K accumulators x 17 words x BLOCK threads (D > 1) + the block-sum scratch
+    __host__ __device__ static constexpr size_t acc_words(int block) { return (D == 1) ? 0 : (size_t)K * 17 * block; }
     __host__ __device__ static constexpr size_t smem_bytes(int block) { return (acc_words(block) + 8 * K * 8) * 4; }
 };
 
-// BLOCK threads per block (256 or 128), MINB = resident blocks per SM requested from ptxas.
-// WEIGHTED: the sweep is sum_y E(y) prod_j(...) with the split-eq weight E(y) = e_out * e_in folded into
-// table 0's pair AFTER the bound values are stored (GruenSplitEqPolynomial, split_eq.rs:159-447: the eq
-// polynomial is never materialised or bound as a table; its current variable is a linear factor the host
-// multiplies in).
-template <int M, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB, bool WEIGHTED = false>
-__global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
-    constexpr int K = FusedShape<M, SKIP1>::K;
-    extern __shared__ uint32_t dsm[];
-    uint32_t* wacc = dsm;                                          // [e][word][tid]
-    uint32_t* red = dsm + FusedShape<M, SKIP1>::acc_words(BLOCK);  // block_sum scratch
+// NC: the tables are read-only for the lifetime of the kernel (one launch per round) -> non-coherent loads.
+// A resident kernel reads what OTHER blocks wrote in the previous round, so it takes the coherent path.
+template <bool NC>
+__device__ __forceinline__ Fr ld_tab(const uint64_t* base, size_t idx) {
+    return NC ? ld_elem<Fr>(base, idx) : ld_elem_rw<Fr>(base, idx);
+}
+
+// The body of a pass: thread `first` .. step `stride` over the pair indices. On return thread 0 of the block
+// holds the block's K sums in acc[] and a __syncthreads() has been executed (dsm may be reused).
+// dsm: FusedShape<D, SKIP1>::smem_bytes(BLOCK) bytes of dynamic shared memory.
+template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, bool WEIGHTED, bool NC>
+__device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, const BindScalar& s, uint32_t* dsm,
+                                           size_t first, size_t stride, Fr (&acc)[FusedShape<D, SKIP1>::K]) {
+    constexpr int K = FusedShape<D, SKIP1>::K;
+    constexpr int T = D * P;
+    uint32_t* wacc = dsm;                                       // [e][word][tid]
+    uint32_t* red = dsm + FusedShape<D, SKIP1>::acc_words(BLOCK);  // block_sum scratch
     const int tid = threadIdx.x;
-    Fr sum1[M == 1 ? K : 1];
-    if (M == 1) {
+    Fr sum1[D == 1 ? K : 1];
+    if (D == 1) {
 #pragma unroll
         for (int e = 0; e < K; ++e) sum1[e] = Fr::zero();
     } else {
@@ -294,35 +302,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
             for (int w = 0; w < 17; ++w) wacc[(e * 17 + w) * BLOCK + tid] = 0;
     }
 
-    size_t stride = (size_t)gridDim.x * blockDim.x;
     // Eval-only passes (no bind) have registers to spare: the NEXT iteration's pair is loaded into registers
     // before the current one is multiplied (software pipelining), so the DRAM latency of an iteration hides
     // behind the previous iteration's arithmetic instead of behind other warps - there are only 16 per SM.
     // (ptxas sinks the L2 prefetch below to the end of the loop body, so on its own it buys no lead time.)
-    constexpr bool PIPE = !BIND && (M == 1 || (M == 2 && SKIP1));
-    Fr nlo[PIPE ? M : 1], nhi[PIPE ? M : 1];
+    constexpr bool PIPE = !BIND && P == 1 && (D == 1 || (D == 2 && SKIP1));
+    Fr nlo[PIPE ? D : 1], nhi[PIPE ? D : 1];
     if (PIPE) {
-        const size_t y0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const size_t y0 = first;
         if (y0 < pairs) {
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
+            for (int j = 0; j < D; ++j) {
                 if (ORDER == ORDER_HIGH_TO_LOW) {
-                    nlo[j] = ld_elem<Fr>(tp.in[j], y0);
-                    nhi[j] = ld_elem<Fr>(tp.in[j], y0 + pairs);
+                    nlo[j] = ld_tab<NC>(tp.in[j], y0);
+                    nhi[j] = ld_tab<NC>(tp.in[j], y0 + pairs);
                 } else {
-                    nlo[j] = ld_elem<Fr>(tp.in[j], 2 * y0);
-                    nhi[j] = ld_elem<Fr>(tp.in[j], 2 * y0 + 1);
+                    nlo[j] = ld_tab<NC>(tp.in[j], 2 * y0);
+                    nhi[j] = ld_tab<NC>(tp.in[j], 2 * y0 + 1);
                 }
             }
         }
     }
-    for (size_t y = (size_t)blockIdx.x * blockDim.x + threadIdx.x; y < pairs; y += stride) {
+    for (size_t y = first; y < pairs; y += stride) {
         // prefetch the lines of a later iteration into L2 (ncu: long-scoreboard was the top stall)
         const size_t yp = y + (PIPE ? 2 : 1) * stride;
         if (yp < pairs) {
             const size_t yn = yp;
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
+            for (int j = 0; j < T; ++j) {
                 if (ORDER == ORDER_HIGH_TO_LOW) {
                     prefetch_l2(tp.in[j], yn);
                     prefetch_l2(tp.in[j], yn + pairs);
@@ -335,121 +342,128 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
                 }
             }
         }
-        Fr lo[M], hi[M];
-        if (PIPE) {
+        Fr wgt;
+        if (WEIGHTED) {
+            const size_t mask = ((size_t)1 << tp.in_bits) - 1;
+            wgt = fp_mul(ld_elem<Fr>(tp.e_out, y >> tp.in_bits), ld_elem<Fr>(tp.e_in, y & mask));
+        }
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                lo[j] = nlo[j];
-                hi[j] = nhi[j];
-            }
-            const size_t yn = y + stride;
-            if (yn < pairs) {
+        for (int k = 0; k < P; ++k) {  // one product term at a time: D tables live in registers
+            Fr lo[D], hi[D];
+            if (PIPE) {
 #pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    if (ORDER == ORDER_HIGH_TO_LOW) {
-                        nlo[j] = ld_elem<Fr>(tp.in[j], yn);
-                        nhi[j] = ld_elem<Fr>(tp.in[j], yn + pairs);
-                    } else {
-                        nlo[j] = ld_elem<Fr>(tp.in[j], 2 * yn);
-                        nhi[j] = ld_elem<Fr>(tp.in[j], 2 * yn + 1);
+                for (int j = 0; j < D; ++j) {
+                    lo[j] = nlo[j];
+                    hi[j] = nhi[j];
+                }
+                const size_t yn = y + stride;
+                if (yn < pairs) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        if (ORDER == ORDER_HIGH_TO_LOW) {
+                            nlo[j] = ld_tab<NC>(tp.in[j], yn);
+                            nhi[j] = ld_tab<NC>(tp.in[j], yn + pairs);
+                        } else {
+                            nlo[j] = ld_tab<NC>(tp.in[j], 2 * yn);
+                            nhi[j] = ld_tab<NC>(tp.in[j], 2 * yn + 1);
+                        }
                     }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            if (PIPE) break;
-            if (BIND) {
-                Fr a, b, c, d;
-                if (ORDER == ORDER_HIGH_TO_LOW) {
-                    a = ld_elem_rw<Fr>(tp.in[j], y);
-                    c = ld_elem_rw<Fr>(tp.in[j], y + 2 * pairs);
-                    b = ld_elem_rw<Fr>(tp.in[j], y + pairs);
-                    d = ld_elem_rw<Fr>(tp.in[j], y + 3 * pairs);
-                    lo[j] = bind_pair<HI4>(a, c, s);
-                    hi[j] = bind_pair<HI4>(b, d, s);
-                    st_elem(tp.out[j], y, lo[j]);
-                    st_elem(tp.out[j], y + pairs, hi[j]);
+            for (int j = 0; j < D; ++j) {
+                if (PIPE) break;
+                const uint64_t* in = tp.in[k * D + j];
+                uint64_t* out = tp.out[k * D + j];
+                if (BIND) {
+                    Fr a, b, c, d;
+                    if (ORDER == ORDER_HIGH_TO_LOW) {
+                        a = ld_elem_rw<Fr>(in, y);
+                        c = ld_elem_rw<Fr>(in, y + 2 * pairs);
+                        b = ld_elem_rw<Fr>(in, y + pairs);
+                        d = ld_elem_rw<Fr>(in, y + 3 * pairs);
+                        lo[j] = bind_pair<HI4>(a, c, s);
+                        hi[j] = bind_pair<HI4>(b, d, s);
+                        st_elem(out, y, lo[j]);
+                        st_elem(out, y + pairs, hi[j]);
+                    } else {
+                        a = ld_tab<NC>(in, 4 * y);
+                        b = ld_tab<NC>(in, 4 * y + 1);
+                        c = ld_tab<NC>(in, 4 * y + 2);
+                        d = ld_tab<NC>(in, 4 * y + 3);
+                        lo[j] = bind_pair<HI4>(a, b, s);
+                        hi[j] = bind_pair<HI4>(c, d, s);
+                        st_elem(out, 2 * y, lo[j]);
+                        st_elem(out, 2 * y + 1, hi[j]);
+                    }
                 } else {
-                    a = ld_elem<Fr>(tp.in[j], 4 * y);
-                    b = ld_elem<Fr>(tp.in[j], 4 * y + 1);
-                    c = ld_elem<Fr>(tp.in[j], 4 * y + 2);
-                    d = ld_elem<Fr>(tp.in[j], 4 * y + 3);
-                    lo[j] = bind_pair<HI4>(a, b, s);
-                    hi[j] = bind_pair<HI4>(c, d, s);
-                    st_elem(tp.out[j], 2 * y, lo[j]);
-                    st_elem(tp.out[j], 2 * y + 1, hi[j]);
+                    if (ORDER == ORDER_HIGH_TO_LOW) {
+                        lo[j] = ld_elem_rw<Fr>(in, y);
+                        hi[j] = ld_elem_rw<Fr>(in, y + pairs);
+                    } else {
+                        lo[j] = ld_tab<NC>(in, 2 * y);
+                        hi[j] = ld_tab<NC>(in, 2 * y + 1);
+                    }
                 }
+            }
+            if (WEIGHTED) {
+                lo[0] = fp_mul(lo[0], wgt);
+                hi[0] = fp_mul(hi[0], wgt);
+            }
+            if (D == 1) {
+                sum1[0] = fp_add(sum1[0], lo[0]);
+                if (!SKIP1) sum1[K - 1] = fp_add(sum1[K - 1], hi[0]);
             } else {
-                if (ORDER == ORDER_HIGH_TO_LOW) {
-                    lo[j] = ld_elem_rw<Fr>(tp.in[j], y);
-                    hi[j] = ld_elem_rw<Fr>(tp.in[j], y + pairs);
-                } else {
-                    lo[j] = ld_elem<Fr>(tp.in[j], 2 * y);
-                    hi[j] = ld_elem<Fr>(tp.in[j], 2 * y + 1);
-                }
-            }
-        }
-        if (WEIGHTED) {
-            const size_t mask = ((size_t)1 << tp.in_bits) - 1;
-            Fr wgt = fp_mul(ld_elem<Fr>(tp.e_out, y >> tp.in_bits), ld_elem<Fr>(tp.e_in, y & mask));
-            lo[0] = fp_mul(lo[0], wgt);
-            hi[0] = fp_mul(hi[0], wgt);
-        }
-        if (M == 1) {
-            sum1[0] = fp_add(sum1[0], lo[0]);
-            if (!SKIP1) sum1[K - 1] = fp_add(sum1[K - 1], hi[0]);
-        } else {
-            int e = 0;
-            {  // t = 0
-                Fr prod = lo[0];
+                int e = 0;
+                {  // t = 0
+                    Fr prod = lo[0];
 #pragma unroll
-                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, lo[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, lo[M - 1].v);
-                ++e;
-            }
-            if (!SKIP1) {  // t = 1: lo + D = hi
-                Fr prod = hi[0];
-#pragma unroll
-                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, hi[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, hi[M - 1].v);
-                ++e;
-            }
-            Fr dlt[M];
-#pragma unroll
-            for (int j = 0; j < M; ++j) dlt[j] = (M == 2) ? fp_sub_lazy(hi[j], lo[j]) : fp_sub(hi[j], lo[j]);
-            if (M > 2) {  // t = 2 .. M-1
-                Fr cur[M];
-#pragma unroll
-                for (int j = 0; j < M; ++j) cur[j] = hi[j];
-#pragma unroll
-                for (int t = 2; t < M; ++t) {
-#pragma unroll
-                    for (int j = 0; j < M; ++j) cur[j] = fp_add(cur[j], dlt[j]);
-                    Fr prod = cur[0];
-#pragma unroll
-                    for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, cur[j]);
-                    mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, cur[M - 1].v);
+                    for (int j = 1; j < D - 1; ++j) prod = fp_mul(prod, lo[j]);
+                    mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, lo[D - 1].v);
                     ++e;
                 }
-            }
-            {  // t = infinity: the leading coefficient prod_j D_j
-                Fr prod = dlt[0];
+                if (!SKIP1) {  // t = 1: lo + D = hi
+                    Fr prod = hi[0];
 #pragma unroll
-                for (int j = 1; j < M - 1; ++j) prod = fp_mul(prod, dlt[j]);
-                mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, dlt[M - 1].v);
+                    for (int j = 1; j < D - 1; ++j) prod = fp_mul(prod, hi[j]);
+                    mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, hi[D - 1].v);
+                    ++e;
+                }
+                Fr dlt[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) dlt[j] = (D == 2) ? fp_sub_lazy(hi[j], lo[j]) : fp_sub(hi[j], lo[j]);
+                if (D > 2) {  // t = 2 .. D-1
+                    Fr cur[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) cur[j] = hi[j];
+#pragma unroll
+                    for (int t = 2; t < D; ++t) {
+#pragma unroll
+                        for (int j = 0; j < D; ++j) cur[j] = fp_add(cur[j], dlt[j]);
+                        Fr prod = cur[0];
+#pragma unroll
+                        for (int j = 1; j < D - 1; ++j) prod = fp_mul(prod, cur[j]);
+                        mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, cur[D - 1].v);
+                        ++e;
+                    }
+                }
+                {  // t = infinity: the leading coefficient prod_j D_j
+                    Fr prod = dlt[0];
+#pragma unroll
+                    for (int j = 1; j < D - 1; ++j) prod = fp_mul(prod, dlt[j]);
+                    mul_wide_acc_smem(wacc + (e * 17) * BLOCK + tid, BLOCK, prod.v, dlt[D - 1].v);
+                }
             }
         }
     }
-    Fr acc[K];
-    if (M == 1) {
+    if (D == 1) {
 #pragma unroll
         for (int e = 0; e < K; ++e) acc[e] = sum1[e];
         block_sum<K>(acc, red);
     } else {
         // Block sum of the wide accumulators BEFORE the Montgomery reduction: the K x 17 word columns are summed
         // over the block's threads as plain integers (a column sum is < 2^40; the block total stays far below
-        // 2^544: at most pairs / gridDim.x products of < 2^512 each), then lane e of warp 0 propagates the carries
+        // 2^544: at most P * pairs / gridDim.x products of < 2^512 each), then lane e of warp 0 propagates the carries
         // of value e and reduces ONCE. One reduction per block instead of one per thread: the per-thread
         // reductions were ~13 % of the instructions a pass issued (ncu, profiles/r01b_ncu_fused_round_kernels.md).
         uint64_t* colsum = reinterpret_cast<uint64_t*>(red);  // K * 17 u64 <= the 8 * K * 8 words of scratch
@@ -466,15 +480,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
         if (warp == 0) {
             Fr mine = Fr::zero();
             if (lane < K) {
-                uint32_t T[17];
+                uint32_t Tw[17];
                 uint64_t carry = 0;
 #pragma unroll
                 for (int w = 0; w < 17; ++w) {
                     const uint64_t t = colsum[lane * 17 + w] + carry;
-                    T[w] = (uint32_t)t;
+                    Tw[w] = (uint32_t)t;
                     carry = t >> 32;
                 }
-                mine = reduce_wide17<FrParams>(T, 1);
+                mine = reduce_wide17<FrParams>(Tw, 1);
             }
 #pragma unroll
             for (int e = 0; e < K; ++e)
@@ -482,8 +496,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
                 for (int w = 0; w < 8; ++w) acc[e].v[w] = __shfl_sync(0xffffffffu, mine.v[w], e);
         }
     }
-    __syncthreads();  // scratch is reused by the last block's fold
-    round_epilogue<K>(acc, red, out);
+    __syncthreads();  // scratch is reused by the caller (the last block's fold)
+}
+
+// One launch per round: BLOCK threads per block (256 or 128), MINB = resident blocks per SM requested from
+// ptxas. WEIGHTED: the sweep is sum_y E(y) prod_j(...) with the split-eq weight E(y) = e_out * e_in folded into
+// table 0's pair AFTER the bound values are stored (GruenSplitEqPolynomial, split_eq.rs:159-447: the eq
+// polynomial is never materialised or bound as a table; its current variable is a linear factor the host
+// multiplies in). Each block writes its sums and the last block folds them (round_epilogue).
+template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, int MINB, bool WEIGHTED = false>
+__global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, size_t pairs, BindScalar s, RoundOut out) {
+    constexpr int K = FusedShape<D, SKIP1>::K;
+    extern __shared__ uint32_t dsm[];
+    Fr acc[K];
+    fused_pass<D, P, ORDER, BIND, HI4, SKIP1, BLOCK, WEIGHTED, true>(
+        tp, pairs, s, dsm, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, acc);
+    round_epilogue<K>(acc, dsm + FusedShape<D, SKIP1>::acc_words(BLOCK), out);
 }
 
 // ---- persistent tail: the last rounds of a member without a launch per round -------------------------

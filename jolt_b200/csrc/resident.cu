@@ -1,0 +1,368 @@
+// Host side of the resident kernel service (resident.cuh): start a run for a batch of members, drive one round
+// per mailbox command, stop it. The context lock is held by every caller.
+#include "../../include/jolt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "member.hpp"
+#include "resident.cuh"
+
+using namespace jb;
+using namespace jbi;
+
+struct ResidentRun {
+    jb_ctx* c = nullptr;
+    TailRes res;
+    ResMailbox* mb = nullptr;  // host view of the mailbox
+    uint64_t* d_partial = nullptr;
+    uint64_t seq = 0;
+    int n = 0;
+    jb_member* mem[RES_MAX_MEMBERS] = {nullptr};
+    unsigned grid = 0;
+    unsigned pending[RES_MAX_MEMBERS] = {0};  // actions of the command in flight
+    struct RoundInfo { int kind; uint64_t items; int m; };
+    RoundInfo info[64];                       // what command s (< 64) asked for, for the device-timed pass log
+    uint64_t host_post[64], host_recv[64];    // CLOCK_MONOTONIC ns (diagnostics)
+    bool kernel_live = false;
+    bool exclusive = false;  // holds more than half of the device's block slots: other kernels may starve
+};
+
+namespace {
+
+using ResKernel = void (*)(const ResArgs);
+
+template <int D, int P>
+ResKernel pick_order(int order) {
+    return order == JB_HIGH_TO_LOW ? (ResKernel)resident_rounds_kernel<D, P, ORDER_HIGH_TO_LOW>
+                                   : (ResKernel)resident_rounds_kernel<D, P, ORDER_LOW_TO_HIGH>;
+}
+
+// The instantiated shapes: plain products of 1..4 tables and the two-term degree-2 sum of products
+// (IncClaimReduction: A * RamInc + B * RdInc).
+ResKernel pick_kernel(int D, int P, int order, size_t* smem) {
+    *smem = 0;
+    if (P == 1) {
+        switch (D) {
+            case 1: *smem = FusedShape<1, true>::smem_bytes(RES_BLOCK); return pick_order<1, 1>(order);
+            case 2: *smem = FusedShape<2, true>::smem_bytes(RES_BLOCK); return pick_order<2, 1>(order);
+            case 3: *smem = FusedShape<3, true>::smem_bytes(RES_BLOCK); return pick_order<3, 1>(order);
+            case 4: *smem = FusedShape<4, true>::smem_bytes(RES_BLOCK); return pick_order<4, 1>(order);
+            default: return nullptr;
+        }
+    }
+    if (P == 2 && D == 2) {
+        *smem = FusedShape<2, true>::smem_bytes(RES_BLOCK);
+        return pick_order<2, 2>(order);
+    }
+    return nullptr;
+}
+
+// occupancy of a shape (cached): also forces the module to load before any resident kernel is alive
+int kernel_blocks_per_sm(ResKernel k, size_t smem) {
+    static std::mutex mu;
+    static std::vector<std::pair<ResKernel, int>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : cache)
+        if (kv.first == k) return kv.second;
+    cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k, RES_BLOCK, smem) != cudaSuccess || nb < 1) nb = 1;
+    cache.emplace_back(k, nb);
+    return nb;
+}
+
+int acquire_resources(jb_ctx* c, TailRes* r) {
+    if (!c->tail_pool.empty()) {
+        *r = c->tail_pool.back();
+        c->tail_pool.pop_back();
+        return JB_OK;
+    }
+    TailRes t;
+    if (cudaHostAlloc(&t.mb_host, sizeof(ResMailbox), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&t.mb_dev, t.mb_host, 0) != cudaSuccess ||
+        cudaMalloc(&t.d_state, sizeof(ResState)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t.event, cudaEventDisableTiming) != cudaSuccess) {
+        if (t.mb_host) cudaFreeHost(t.mb_host);
+        if (t.d_state) cudaFree(t.d_state);
+        if (t.stream) cudaStreamDestroy(t.stream);
+        if (t.event) cudaEventDestroy(t.event);
+        cudaGetLastError();
+        return c->fail(JB_ERR_OOM, "resident: mailbox / stream allocation failed");
+    }
+    *r = t;
+    return JB_OK;
+}
+
+// Spins until the kernel has answered command `seq`. Slow path: make sure the kernel is still alive.
+int wait_answer(ResidentRun* run, uint64_t seq) {
+    jb_ctx* c = run->c;
+    ResMailbox* mb = run->mb;
+    uint64_t spins = 0;
+    while (__atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+        if ((++spins & 0x3fffff) == 0) {
+            cudaError_t e = cudaStreamQuery(run->res.stream);
+            if (e != cudaErrorNotReady && __atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+                run->kernel_live = false;
+                return c->check(e == cudaSuccess ? cudaErrorUnknown : e, "resident kernel exited without answering");
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    return JB_OK;
+}
+
+void release_run(ResidentRun* run, bool mark_no_resident) {
+    jb_ctx* c = run->c;
+    {
+        const uint64_t nseq = run->seq < 64 ? run->seq : 64;
+        for (uint64_t s = 0; s < nseq; ++s) {
+            c->last_run_log[8 * s] = run->mb->tlog[2 * s];
+            c->last_run_log[8 * s + 1] = run->mb->tlog[2 * s + 1];
+            c->last_run_log[8 * s + 2] = run->host_post[s];
+            c->last_run_log[8 * s + 3] = run->host_recv[s];
+            for (int k = 0; k < 4; ++k) c->last_run_log[8 * s + 4 + k] = run->mb->tlog2[4 * s + k];
+        }
+        c->last_run_rounds = nseq;
+    }
+    if (c->timing) {  // the passes of this run, timed on the device (%globaltimer), as launch-like records
+        const uint64_t nseq = run->seq < 64 ? run->seq : 64;
+        for (uint64_t s = 0; s < nseq; ++s) {
+            const ResidentRun::RoundInfo& ri = run->info[s];
+            const uint64_t t0 = run->mb->tlog[2 * s], t1 = run->mb->tlog[2 * s + 1];
+            if (ri.kind < 0 || ri.items < c->timing_min_items || t1 <= t0 || c->timed.size() >= 4096) continue;
+            TimedLaunch t;
+            t.kind = ri.kind;
+            t.items = ri.items;
+            t.m = ri.m;
+            t.ms_direct = (double)(t1 - t0) * 1e-6;
+            c->timed.push_back(t);
+        }
+    }
+    // later work on the context's stream is ordered after the kernel's exit
+    cudaEventRecord(run->res.event, run->res.stream);
+    cudaStreamWaitEvent(c->stream, run->res.event, 0);
+    if (run->d_partial) c->dev_free(run->d_partial);
+    c->tail_pool.push_back(run->res);
+    for (int i = 0; i < run->n; ++i) {
+        if (run->mem[i]) {
+            run->mem[i]->run = nullptr;
+            if (mark_no_resident) run->mem[i]->no_resident = true;
+        }
+    }
+    auto it = std::find(c->runs.begin(), c->runs.end(), run);
+    if (it != c->runs.end()) c->runs.erase(it);
+    delete run;
+}
+
+}  // namespace
+
+bool resident_eligible(const jb_member* mem) {
+    if (!mem || !mem->ctx->use_tail || mem->eq || mem->run) return false;
+    if (mem->len < 2 || (mem->len & (mem->len - 1))) return false;
+    // a member whose big run had to make room for other work only re-enters service once its run is small
+    if (mem->no_resident && mem->len > RES_SMALL_LEN) return false;
+    size_t lg = 0;
+    while (((size_t)1 << lg) < mem->len) ++lg;
+    if ((int)lg > mem->ctx->resident_max_log) return false;
+    size_t smem;
+    return pick_kernel(mem->m, mem->terms, mem->order, &smem) != nullptr;
+}
+
+bool jb_ctx::has_exclusive_run() const {
+    for (auto* r : runs)
+        if (r->exclusive) return true;
+    return false;
+}
+
+void jb_ctx::quiesce_resident(bool all) {
+    std::vector<ResidentRun*> copy = runs;
+    for (auto* r : copy)
+        if (all || r->exclusive) resident_end(r, true);
+}
+
+int resident_begin(jb_ctx* c, jb_member** mems, int n) {
+    if (n < 1 || n > RES_MAX_MEMBERS) return JB_ERR_UNSUPPORTED;
+    const int D = mems[0]->m, P = mems[0]->terms, order = mems[0]->order, T = D * P;
+    uint64_t max_items = 1;
+    for (int i = 0; i < n; ++i) {
+        jb_member* m = mems[i];
+        if (m->ctx != c || m->m != D || m->terms != P || m->order != order || !resident_eligible(m)) return JB_ERR_UNSUPPORTED;
+        max_items = std::max<uint64_t>(max_items, m->len / 2);
+    }
+    size_t smem = 0;
+    ResKernel kernel = pick_kernel(D, P, order, &smem);
+    if (!kernel) return JB_ERR_UNSUPPORTED;
+    const int per_sm = kernel_blocks_per_sm(kernel, smem);
+    const unsigned cap = (unsigned)(c->sm_count * per_sm);
+    const unsigned grid = res_blocks_for(max_items, cap);
+    const bool exclusive = grid > (unsigned)c->sm_count;
+    // co-residency budget: small runs may share the device, a big one needs it alone
+    unsigned in_use = 0;
+    for (auto* r : c->runs) in_use += r->grid;
+    if (!c->runs.empty() && (exclusive || c->has_exclusive_run() || in_use + grid > (unsigned)c->sm_count))
+        c->quiesce_resident(true);
+
+    ResidentRun* run = new (std::nothrow) ResidentRun();
+    if (!run) return JB_ERR_OOM;
+    run->c = c;
+    run->n = n;
+    run->grid = grid;
+    run->exclusive = exclusive;
+    int st = acquire_resources(c, &run->res);
+    if (st != JB_OK) {
+        delete run;
+        return st;
+    }
+    run->mb = (ResMailbox*)run->res.mb_host;
+    ResArgs args;
+    std::memset(&args, 0, sizeof args);
+    args.n_members = n;
+    for (int i = 0; i < n && st == JB_OK; ++i) {
+        jb_member* m = mems[i];
+        args.mem[i].len = m->len;
+        for (int j = 0; j < T && st == JB_OK; ++j) {
+            Table& t = m->tables[j];
+            if (order == JB_LOW_TO_HIGH) st = c->ensure_alt(t, m->len / 2 ? m->len / 2 : 1);
+            args.mem[i].buf[j] = t.buf;
+            args.mem[i].alt[j] = t.alt;
+        }
+    }
+    if (st == JB_OK) st = c->dev_alloc((void**)&run->d_partial, (size_t)grid * n * D * 32);
+    if (st != JB_OK) {
+        if (run->d_partial) c->dev_free(run->d_partial);
+        c->tail_pool.push_back(run->res);
+        delete run;
+        return st;
+    }
+    std::memset(run->mb, 0, sizeof(ResMailbox));
+    args.mb = (ResMailbox*)run->res.mb_dev;
+    args.st = (ResState*)run->res.d_state;
+    args.partial = run->d_partial;
+    args.timeout_cycles = 20000000000LL;  // ~10 s of SM clocks without a command: give the SMs back
+    args.world = c->world;
+    args.rank = c->rank;
+    for (int g = 0; g < 16; ++g) args.peer[g] = c->xch_peer[g];
+    // the kernel starts after everything already queued on the context's stream (uploads, allocations)
+    cudaEventRecord(run->res.event, c->stream);
+    cudaStreamWaitEvent(run->res.stream, run->res.event, 0);
+    cudaMemsetAsync(run->res.d_state, 0, sizeof(ResState), run->res.stream);
+    void* kargs[] = {(void*)&args};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(RES_BLOCK), kargs, smem, run->res.stream);
+    c->launches++;
+    if (e != cudaSuccess) {
+        st = c->check(e, "resident_rounds_kernel launch");
+        c->dev_free(run->d_partial);
+        c->tail_pool.push_back(run->res);
+        delete run;
+        return st;
+    }
+    run->kernel_live = true;
+    for (int i = 0; i < n; ++i) {
+        run->mem[i] = mems[i];
+        mems[i]->run = run;
+        mems[i]->run_idx = i;
+    }
+    c->runs.push_back(run);
+    return JB_OK;
+}
+
+int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange) {
+    jb_ctx* c = run->c;
+    if (!run->kernel_live) return c->fail(JB_ERR_INVALID, "resident run is not live");
+    ResMailbox* mb = run->mb;
+    uint64_t cmd = RES_OP_ROUND;
+    if (exchange) {
+        cmd |= RES_FLAG_EXCHANGE;
+        mb->xseq = ++c->xch_seq;
+    }
+    for (int i = 0; i < run->n; ++i) {
+        run->pending[i] = actions[i] & 0xf;
+        cmd |= (uint64_t)run->pending[i] << (16 + 4 * i);
+    }
+    mb->cmd = cmd;
+    if (challenge) std::memcpy((void*)mb->challenge, challenge, 32);
+    const uint64_t seq = ++run->seq;
+    if (seq <= 64) {
+        ResidentRun::RoundInfo& ri = run->info[seq - 1];
+        ri.kind = -1;
+        ri.items = 0;
+        ri.m = 0;
+        for (int i = 0; i < run->n; ++i) {
+            const unsigned a = run->pending[i];
+            if (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) {
+                ri.kind = (a == RES_ACT_BIND_EVAL || ri.kind == 0) ? 0 : 2;
+                ri.items += (a == RES_ACT_BIND_EVAL ? run->mem[i]->len / 2 : run->mem[i]->len) / 2;
+                ri.m = run->mem[i]->ntables();
+            }
+        }
+    }
+    if (seq <= 64) run->host_post[seq - 1] = now_ns();
+    __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
+    return JB_OK;
+}
+
+int resident_wait(ResidentRun* run, uint64_t* out) {
+    jb_ctx* c = run->c;
+    WaitAcc acc(c);
+    ResMailbox* mb = run->mb;
+    int st = wait_answer(run, run->seq);
+    if (st != JB_OK) return st;
+    if (run->seq <= 64) run->host_recv[run->seq - 1] = now_ns();
+    if (mb->status != 0) {
+        run->kernel_live = false;
+        return c->fail(JB_ERR_CUDA, mb->status == 2 ? "peer exchange timed out (a rank did not arrive)"
+                                                    : "resident kernel aborted (timeout)");
+    }
+    if (out) std::memcpy(out, (const void*)mb->result, (size_t)run->n * RES_SLOT_U64 * 8);
+    // mirror the device's table state on the host: the member's tables are consistent at every round boundary
+    bool all_done = true;
+    for (int i = 0; i < run->n; ++i) {
+        jb_member* m = run->mem[i];
+        const unsigned a = run->pending[i];
+        if (a == RES_ACT_BIND_EVAL || a == RES_ACT_FINAL) {
+            m->len /= 2;
+            for (auto& t : m->tables) {
+                if (m->order == JB_LOW_TO_HIGH) t.swap_buffers();
+                t.len = m->len;
+            }
+            if (a == RES_ACT_FINAL && m->len == 1) {
+                std::memcpy(m->final_vals, (const void*)(mb->result + (size_t)i * RES_SLOT_U64), (size_t)m->ntables() * 32);
+                m->has_final = true;
+            }
+        }
+        if (m->len >= 2) all_done = false;
+    }
+    if (all_done) {  // every member is fully bound: the kernel has returned on its own
+        run->kernel_live = false;
+        release_run(run, false);
+    }
+    return JB_OK;
+}
+
+int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out) {
+    int st = resident_post(run, actions, challenge, exchange);
+    if (st != JB_OK) return st;
+    return resident_wait(run, out);
+}
+
+void resident_end(ResidentRun* run, bool mark_no_resident) {
+    if (!run) return;
+    if (run->kernel_live) {
+        ResMailbox* mb = run->mb;
+        mb->cmd = RES_OP_ABORT;
+        const uint64_t seq = ++run->seq;
+        __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
+        wait_answer(run, seq);
+        run->kernel_live = false;
+    }
+    release_run(run, mark_no_resident);
+}
+
+int resident_run_size(const ResidentRun* run) { return run ? run->n : 0; }

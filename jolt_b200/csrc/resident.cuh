@@ -1,0 +1,407 @@
+// Resident sumcheck kernel: ONE launch serves every round of a batch of members.
+//
+// A sumcheck has log N sequential Fiat-Shamir round trips (the challenge of round k depends on the round
+// polynomial of round k; the transcript is host-owned, specs/clean-slate-prover.md:579-584). With one launch per
+// round each trip costs launch + ramp + drain + publish (~19 us on top of the pass itself, r01 BENCH) - at 2^22
+// that was 65 % of the whole sumcheck. Here the kernel is launched once per batch (cooperatively: every block is
+// co-resident), and every round is driven through a mailbox in host-mapped pinned memory:
+//
+//   host : writes {actions, challenge} then cmd_seq            (one 64-byte line)
+//   blk 0: warp 0 polls that line over PCIe (one coalesced 64 B read per poll), then re-publishes it in DEVICE
+//          memory (ResState) with a release store; the other blocks spin on that word with acquire loads (L2)
+//   all  : run their share of the fused bind + sweep pass of every active member (the same fused_pass body as
+//          the one-launch-per-round kernel), store per-block partial sums, arrive on a ticket counter
+//   last : the last block to arrive folds the partials (one warp per value), resets the ticket and writes the
+//          K values per member to the mailbox followed by res_seq, which the host spins on
+//
+// The bind -> next round's reads dependency between DIFFERENT blocks is carried by that same chain
+// (stores -> bar.sync -> fence -> ticket atomic ... res_seq -> host -> cmd_seq -> release/acquire -> bar.sync ->
+// loads): it is the grid barrier of cooperative groups with the host's Fiat-Shamir step in the middle. Tables
+// are therefore read with coherent loads here (fused_pass<.., NC = false>), never through the read-only path.
+//
+// Blocks that can have no work in any later round (the tables only shrink) exit; the ticket target of a round is
+// the number of live blocks, which every block derives from the same state. With one live block the kernel
+// degenerates into the r01 "persistent tail": no broadcast, no ticket.
+//
+// Multi-GPU: for index-sharded rounds the last block also performs the all-reduce of the round sums over NVLink
+// peer memory (CUDA-IPC mapped exchange buffers): one warp stores this rank's lanes into every peer's slot,
+// raises a flag per peer, waits for the peers' flags in its own buffer and sums - before the totals go to the
+// host. No NCCL launch, no extra kernel (comm.cu owns the buffers).
+#pragma once
+#include "poly_kernels.cuh"
+
+namespace jb {
+
+constexpr int RES_MAX_MEMBERS = 8;
+constexpr int RES_BLOCK = 256;
+constexpr size_t RES_SMALL_LEN = 8192;  // tables this short need <= 16 blocks: such runs coexist with other work
+constexpr int RES_SLOT_U64 = 32;  // mailbox result words per member: 4 values x 8 u64 (lanes) or T finals x 4 u64
+
+// per-member action of a round command (4 bits each, member i at bits [16 + 4i, 20 + 4i) of cmd)
+enum : unsigned { RES_ACT_NONE = 0, RES_ACT_EVAL = 1, RES_ACT_BIND_EVAL = 2, RES_ACT_FINAL = 3 };
+enum : uint64_t { RES_OP_ROUND = 1, RES_OP_ABORT = 2 };
+constexpr uint64_t RES_FLAG_EXCHANGE = 1ull << 8;  // member 0's sums are all-reduced over peer memory (lanes out)
+
+struct alignas(64) ResMailbox {
+    // line 0 (64 B), host -> device. The host writes the payload first and cmd_seq last; the device reads the
+    // whole line with ONE coalesced 64-byte request, so a snapshot that shows the new sequence number also
+    // shows its payload.
+    volatile uint64_t cmd_seq;
+    uint64_t cmd;           // RES_OP_* | flags | actions << 16
+    uint64_t challenge[4];  // Montgomery limbs of the bind scalar (shared by every member of the batch round)
+    uint64_t xseq;          // exchange sequence number (RES_FLAG_EXCHANGE)
+    uint64_t pad0;
+    // line 1, device -> host
+    volatile uint64_t res_seq;
+    uint64_t status;  // 0 ok, 1 aborted / timed out, 2 exchange timed out
+    uint64_t pad1[6];
+    uint64_t result[RES_MAX_MEMBERS * RES_SLOT_U64];
+    // observability (specs/clean-slate-prover.md:585-587): %globaltimer (ns) when block 0 decoded command s and
+    // when the last block had folded its partials, at [2 (s - 1 mod 64)] and [.. + 1]
+    uint64_t tlog[2 * 64];
+    // finer stamps of the same rounds (diagnostics): [4 s + 0] block 0 finished its passes, [4 s + 1] block 0 arrived
+    // on the ticket, [4 s + 2] the last block saw that it is last, [4 s + 3] spare
+    uint64_t tlog2[4 * 64];
+};
+
+// Device-side re-publication of the command line + the arrival counter.
+struct alignas(128) ResState {
+    uint64_t seq;
+    uint64_t cmd[7];
+    uint64_t pad[8];
+    unsigned int ticket;
+    unsigned int pad2[31];
+};
+
+struct ResMemberArg {
+    uint64_t* buf[JB_MAX_TABLES];
+    uint64_t* alt[JB_MAX_TABLES];  // LowToHigh ping-pong partner (>= len/2 entries); unused under HighToLow
+    uint64_t len;
+};
+
+struct ResArgs {
+    ResMemberArg mem[RES_MAX_MEMBERS];
+    int n_members;
+    ResMailbox* mb;     // host-mapped
+    ResState* st;       // device
+    uint64_t* partial;  // gridDim.x * n_members * K canonical elements
+    long long timeout_cycles;
+    // peer exchange (world > 1): exchange buffer of every rank as mapped in THIS process
+    uint64_t* peer[16];
+    int world, rank;
+};
+
+__device__ __forceinline__ uint64_t ld_acquire_gpu(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__host__ __device__ inline unsigned res_blocks_for(uint64_t items, unsigned cap) {
+    const uint64_t need = (items + RES_BLOCK - 1) / RES_BLOCK;
+    return (unsigned)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+// One member's pass as an out-of-line call: the pass body gets the whole register budget to itself (the round
+// loop's own state is saved around ONE call per round instead of squeezing the inner loop into spills).
+// Thread 0 leaves the block's K sums at `g_dst` (global: one of several blocks) or, when this block is the only
+// live one, straight in shared memory at `s_dst` (K x 8 words) - no trip through L2 on the latency path.
+template <int D, int P, int ORDER, bool BIND, bool HI4>
+__device__ __noinline__ void resident_pass(const TablePtrs tp, size_t pairs, const BindScalar sc, uint32_t* dsm, size_t first,
+                                           size_t stride, uint64_t* g_dst, uint32_t* s_dst) {
+    constexpr int K = D;
+    Fr acc[K];
+    fused_pass<D, P, ORDER, BIND, HI4, true, RES_BLOCK, false, false>(tp, pairs, sc, dsm, first, stride, acc);
+    if (threadIdx.x == 0) {
+        if (s_dst) {
+#pragma unroll
+            for (int e = 0; e < K; ++e)
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s_dst[e * 8 + w] = acc[e].v[w];
+        } else {
+#pragma unroll
+            for (int e = 0; e < K; ++e) st_elem(g_dst, e, acc[e]);
+        }
+    }
+}
+
+template <int D, int P, int ORDER>
+__global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __grid_constant__ ResArgs a) {
+    constexpr int T = D * P;
+    constexpr int K = D;  // s(1) always comes from the running claim (the optimized tier's convention)
+    extern __shared__ uint32_t dsm[];
+    __shared__ uint64_t s_line[8];
+    __shared__ uint64_t* s_cur[RES_MAX_MEMBERS][T];
+    __shared__ uint64_t* s_oth[RES_MAX_MEMBERS][T];
+    __shared__ uint64_t s_len[RES_MAX_MEMBERS];
+    __shared__ unsigned s_nblk[RES_MAX_MEMBERS];
+    __shared__ unsigned s_live_next;
+    __shared__ int s_last;
+    __shared__ uint32_t s_tot[RES_MAX_MEMBERS * K * 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned b = blockIdx.x, grid = gridDim.x;
+    const int NM = a.n_members;
+    if (tid < NM) {
+        s_len[tid] = a.mem[tid].len;
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            s_cur[tid][j] = a.mem[tid].buf[j];
+            s_oth[tid][j] = a.mem[tid].alt[j];
+        }
+    }
+    __syncthreads();
+    unsigned live = grid;
+    uint64_t seq = 0;
+    while (true) {
+        // ---- receive command seq + 1 ------------------------------------------------------------------
+        if (b == 0) {
+            if (tid < 32) {
+                const long long t0 = clock64();
+                const volatile uint64_t* line = reinterpret_cast<const volatile uint64_t*>(a.mb);
+                uint64_t v = 0;
+                bool got = false;
+                while (true) {
+                    if (lane < 8) v = line[lane];
+                    const uint64_t sq = __shfl_sync(0xffffffffu, v, 0);
+                    if (sq == seq + 1) {
+                        got = true;
+                        break;
+                    }
+                    const int expired = __shfl_sync(0xffffffffu, (int)(clock64() - t0 > a.timeout_cycles), 0);
+                    if (expired) break;  // host went away: give the SMs back
+                    __nanosleep(20);
+                }
+                if (!got && lane == 1) v = RES_OP_ABORT;
+                if (lane < 8) s_line[lane] = v;
+                if (live > 1) {  // re-publish for the other blocks: payload, then the sequence number (release)
+                    uint64_t w[7];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) w[k] = __shfl_sync(0xffffffffu, v, k + 1);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) a.st->cmd[k] = w[k];
+                        st_release_gpu(&a.st->seq, seq + 1);
+                    }
+                }
+            }
+        } else if (tid == 0) {
+            const long long t0 = clock64();
+            bool got = true;
+            while (ld_acquire_gpu(&a.st->seq) != seq + 1) {
+                if (clock64() - t0 > a.timeout_cycles) {
+                    got = false;
+                    break;
+                }
+            }
+            if (got) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) s_line[k + 1] = a.st->cmd[k];
+            } else {
+                s_line[1] = RES_OP_ABORT;
+            }
+        }
+        __syncthreads();
+        ++seq;
+        const uint64_t cmdw = s_line[1];
+        if ((cmdw & 0xff) != RES_OP_ROUND) {
+            if (b == 0 && tid == 0) {
+                a.mb->status = 1;
+                __threadfence_system();
+                a.mb->res_seq = seq;
+            }
+            return;
+        }
+        if (b == 0 && tid == 0) a.mb->tlog[2 * ((seq - 1) & 63)] = global_timer_ns();
+        const unsigned actions = (unsigned)(cmdw >> 16);
+        BindScalar sc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sc.w[2 * i] = (uint32_t)s_line[2 + i];
+            sc.w[2 * i + 1] = (uint32_t)(s_line[2 + i] >> 32);
+        }
+        const bool hi4 = (s_line[2] | s_line[3]) == 0;  // 125-bit challenge [0,0,lo,hi]: 4-row product
+
+        // ---- this block's share of every active member's pass -------------------------------------------
+        for (int m = 0; m < NM; ++m) {
+            const unsigned act = (actions >> (4 * m)) & 0xf;
+            if (act == RES_ACT_NONE) continue;
+            const uint64_t len = s_len[m];
+            if (act == RES_ACT_FINAL) {  // terminal bind: no sweep
+                const uint64_t half = len / 2;
+                const unsigned nblk = res_blocks_for(half, grid);
+                if (b < nblk) {
+                    for (uint64_t i = (uint64_t)b * RES_BLOCK + tid; i < half; i += (uint64_t)nblk * RES_BLOCK) {
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            const uint64_t* in = s_cur[m][j];
+                            const Fr lo = ld_elem_rw<Fr>(in, ORDER == ORDER_HIGH_TO_LOW ? i : 2 * i);
+                            const Fr hi = ld_elem_rw<Fr>(in, ORDER == ORDER_HIGH_TO_LOW ? i + half : 2 * i + 1);
+                            const Fr o = hi4 ? bind_pair<true>(lo, hi, sc) : bind_pair<false>(lo, hi, sc);
+                            st_elem(ORDER == ORDER_HIGH_TO_LOW ? s_cur[m][j] : s_oth[m][j], i, o);
+                        }
+                    }
+                }
+                continue;
+            }
+            const bool bind = act == RES_ACT_BIND_EVAL;
+            const uint64_t pairs = (bind ? len / 2 : len) / 2;
+            const unsigned nblk = res_blocks_for(pairs, grid);
+            if (tid == 0) s_nblk[m] = nblk;
+            if (b < nblk) {
+                TablePtrs tp;
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    tp.in[j] = s_cur[m][j];
+                    tp.out[j] = (ORDER == ORDER_LOW_TO_HIGH && bind) ? s_oth[m][j] : s_cur[m][j];
+                }
+                tp.e_out = tp.e_in = nullptr;
+                tp.in_bits = 0;
+                const size_t first = (size_t)b * RES_BLOCK + tid, stride = (size_t)nblk * RES_BLOCK;
+                uint64_t* dst = a.partial + (((size_t)b * NM + m) * K) * 4;
+                uint32_t* sdst = live == 1 ? s_tot + m * K * 8 : nullptr;
+                if (!bind)
+                    resident_pass<D, P, ORDER, false, false>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+                else if (hi4)
+                    resident_pass<D, P, ORDER, true, true>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+                else
+                    resident_pass<D, P, ORDER, true, false>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+            }
+        }
+        if (b == 0 && tid == 0) a.mb->tlog2[4 * ((seq - 1) & 63)] = global_timer_ns();
+        __syncthreads();
+        // ---- state update (identical in every block) + arrival ------------------------------------------
+        if (tid == 0) {
+            unsigned ln = 0;
+            for (int m = 0; m < NM; ++m) {
+                const unsigned act = (actions >> (4 * m)) & 0xf;
+                if (act == RES_ACT_BIND_EVAL || act == RES_ACT_FINAL) {
+                    if (ORDER == ORDER_LOW_TO_HIGH) {
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            uint64_t* t = s_cur[m][j];
+                            s_cur[m][j] = s_oth[m][j];
+                            s_oth[m][j] = t;
+                        }
+                    }
+                    s_len[m] /= 2;
+                }
+                // largest pass this member can still ask for: an eval over len/2 pairs (not started) or a
+                // terminal bind over len/2 outputs
+                if (s_len[m] >= 2) {
+                    const unsigned need = res_blocks_for(s_len[m] / 2, grid);
+                    ln = need > ln ? need : ln;
+                }
+            }
+            s_live_next = ln;
+            if (live > 1) {
+                __threadfence();
+                const unsigned ticket = atomicAdd(&a.st->ticket, 1u);
+                s_last = (ticket == live - 1);
+            } else {
+                s_last = 1;
+            }
+            if (b == 0) a.mb->tlog2[4 * ((seq - 1) & 63) + 1] = global_timer_ns();
+            if (s_last) a.mb->tlog2[4 * ((seq - 1) & 63) + 2] = global_timer_ns();
+        }
+        __syncthreads();
+        if (s_last) {
+            // ---- the last block to arrive folds every member's partials and answers the host ------------
+            if (live > 1) __threadfence();
+            for (int it = warp; live > 1 && it < NM * K; it += RES_BLOCK / 32) {
+                const int m = it / K, e = it % K;
+                const unsigned act = (actions >> (4 * m)) & 0xf;
+                if (act != RES_ACT_EVAL && act != RES_ACT_BIND_EVAL) continue;
+                const unsigned nb = s_nblk[m];
+                Fr t = Fr::zero();
+                for (unsigned bb = lane; bb < nb; bb += 32)
+                    t = fp_add(t, ld_elem_cg<Fr>(a.partial, ((size_t)bb * NM + m) * K + e));
+                t = warp_sum(t);
+                if (lane == 0) {
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) s_tot[(m * K + e) * 8 + w] = t.v[w];
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint64_t status = 0;
+                if (lane == 0) a.mb->tlog[2 * ((seq - 1) & 63) + 1] = global_timer_ns();
+                if (lane == 0 && live > 1) a.st->ticket = 0;
+                if (cmdw & RES_FLAG_EXCHANGE) {
+                    // all-reduce of member 0's K sums over NVLink peer memory, as u64 lanes of 32-bit limbs
+                    const uint64_t xseq = s_line[6];
+                    const int par = (int)(xseq & 1);
+                    const int slot = (par * 16 + a.rank) * XCH_SLOT_U64;
+                    for (int idx = lane; idx < a.world * K * 8; idx += 32) {
+                        const int g = idx / (K * 8), i = idx % (K * 8);
+                        *(volatile uint64_t*)(a.peer[g] + slot + i) = (uint64_t)s_tot[i];
+                    }
+                    __syncwarp();
+                    __threadfence_system();  // cumulative: covers the other lanes' stores ordered by the barrier
+                    if (lane < a.world) *(volatile uint64_t*)(a.peer[lane] + XCH_FLAG_BASE + par * 16 + a.rank) = xseq;
+                    uint64_t* mine = a.peer[a.rank];
+                    bool ok = true;
+                    if (lane < a.world) {
+                        const long long t0 = clock64();
+                        while (*(volatile uint64_t*)(mine + XCH_FLAG_BASE + par * 16 + lane) != xseq) {
+                            if (clock64() - t0 > a.timeout_cycles) {
+                                ok = false;
+                                break;
+                            }
+                        }
+                    }
+                    ok = __all_sync(0xffffffffu, ok);
+                    __threadfence_system();
+                    if (lane < K * 8) {
+                        uint64_t sum = 0;
+                        for (int src = 0; src < a.world; ++src)
+                            sum += *(volatile uint64_t*)(mine + (par * 16 + src) * XCH_SLOT_U64 + lane);
+                        a.mb->result[lane] = sum;
+                    }
+                    if (!ok) status = 2;
+                } else {
+                    for (int idx = lane; idx < NM * K * 4; idx += 32) {
+                        const int m = idx / (K * 4), r = idx % (K * 4), e = r / 4, w = r % 4;
+                        const unsigned act = (actions >> (4 * m)) & 0xf;
+                        if (act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) {
+                            const uint32_t* t = s_tot + (m * K + e) * 8;
+                            a.mb->result[m * RES_SLOT_U64 + e * 4 + w] = (uint64_t)t[2 * w] | ((uint64_t)t[2 * w + 1] << 32);
+                        }
+                    }
+                }
+                // terminal binds that left a member fully bound hand the T values back with the acknowledgement
+                for (int idx = lane; idx < NM * T; idx += 32) {
+                    const int m = idx / T, j = idx % T;
+                    const unsigned act = (actions >> (4 * m)) & 0xf;
+                    if (act == RES_ACT_FINAL && s_len[m] == 1) {
+                        const Fr v = ld_elem_cg<Fr>(s_cur[m][j], 0);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w)
+                            a.mb->result[m * RES_SLOT_U64 + j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_system();  // cumulative over the warp's result stores (ordered by the barrier)
+                    a.mb->status = status;
+                    __threadfence_system();
+                    a.mb->res_seq = seq;
+                }
+            }
+        }
+        const unsigned ln = s_live_next;
+        if (b >= ln) return;
+        live = ln;
+        __syncthreads();  // s_line / s_nblk / s_last are rewritten by the next round
+    }
+}
+
+}  // namespace jb

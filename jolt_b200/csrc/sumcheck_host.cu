@@ -5,6 +5,7 @@
 // The Rust toolchain is absent from this image, so the host side above the C ABI is C++ (the
 // reference is compiled code); the Rust adapter a maintainer would write is in INTEGRATION.md.
 // Everything here is O(members * rounds * degree) field work; tables never leave the device.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -127,6 +128,62 @@ int SequentialRounds::batch_finish_rounds(std::vector<MemberFinish>& finishes) {
         if (st != JB_OK) return st;
     }
     return JB_OK;
+}
+
+// ---- DeviceRoundScheduler ---------------------------------------------------------------------------
+DeviceRoundScheduler::~DeviceRoundScheduler() {
+    if (sched_) jb_scheduler_destroy(sched_);
+}
+
+int DeviceRoundScheduler::init(jb_ctx* ctx, const std::vector<DeviceProductMember*>& members) {
+    members_ = members;
+    std::vector<jb_member*> raw;
+    for (auto* m : members) raw.push_back(m->device_member());
+    return jb_scheduler_create(ctx, raw.data(), raw.size(), &sched_);
+}
+
+size_t DeviceRoundScheduler::index_of(const ProveRounds* m) const {
+    for (size_t i = 0; i < members_.size(); ++i)
+        if (members_[i] == m) return i;
+    return members_.size();
+}
+
+int DeviceRoundScheduler::batch_prove_round(std::vector<MemberRound>& work) {
+    work_.resize(work.size());
+    evals_.resize(work.size() * 32);
+    for (size_t i = 0; i < work.size(); ++i) {
+        const size_t idx = index_of(work[i].member);
+        if (idx == members_.size()) return JB_ERR_INVALID;
+        jb_round_work& w = work_[i];
+        w.member = idx;
+        w.round = work[i].local_round;
+        w.has_bind = work[i].has_bind ? 1 : 0;
+        w.has_claim = members_[idx]->passes_claim() ? 1 : 0;
+        std::memcpy(w.bind, work[i].bind.l, 32);
+        std::memcpy(w.claim, work[i].claim.l, 32);
+    }
+    int st = jb_scheduler_prove_round(sched_, work_.data(), work_.size(), evals_.data());
+    if (st != JB_OK) return st;
+    for (size_t i = 0; i < work.size(); ++i) {
+        size_t degree = 0;
+        jb_member_degree(members_[work_[i].member]->device_member(), &degree);
+        tmp_.resize(degree + 1);
+        for (size_t t = 0; t <= degree; ++t) tmp_[t] = HostFr::from_limbs(evals_.data() + i * 32 + 4 * t);
+        work[i].message = UnivariatePoly::from_evals(tmp_);
+        work[i].has_message = true;
+    }
+    return JB_OK;
+}
+
+int DeviceRoundScheduler::batch_finish_rounds(std::vector<MemberFinish>& finishes) {
+    std::vector<jb_finish_work> fw(finishes.size());
+    for (size_t i = 0; i < finishes.size(); ++i) {
+        const size_t idx = index_of(finishes[i].member);
+        if (idx == members_.size()) return JB_ERR_INVALID;
+        fw[i].member = idx;
+        std::memcpy(fw[i].bind, finishes[i].bind.l, 32);
+    }
+    return jb_scheduler_finish_rounds(sched_, fw.data(), fw.size());
 }
 
 // ---- prove_batch (prover.rs:193-362) -----------------------------------------------------------------
@@ -292,7 +349,18 @@ int jb_prove_batch(jb_member** members, const jb_batch_member* desc, size_t n_me
         owned.emplace_back(members[i], check_member_rounds != 0);
     }
     for (auto& m : owned) ptrs.push_back(&m);
-    jb::SequentialRounds sched;
+    // the device traversal: one host round trip per batch round (JB_SEQUENTIAL_ROUNDS=1 selects the reference's
+    // declaration-order traversal, for comparison)
+    jb::SequentialRounds seq_sched;
+    jb::DeviceRoundScheduler dev_sched;
+    jb::RoundScheduler* sched_ptr = &seq_sched;
+    if (!std::getenv("JB_SEQUENTIAL_ROUNDS") && n_members > 0) {
+        std::vector<jb::DeviceProductMember*> dm;
+        for (auto& m : owned) dm.push_back(&m);
+        jb_ctx* ctx = jb_member_context(members[0]);
+        if (ctx && dev_sched.init(ctx, dm) == JB_OK) sched_ptr = &dev_sched;
+    }
+    jb::RoundScheduler& sched = *sched_ptr;
     CallbackRecorder rec;
     rec.fn = absorb;
     rec.user = user;

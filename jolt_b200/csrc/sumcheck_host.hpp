@@ -34,6 +34,9 @@ class DeviceProductMember : public ProveRounds {
     int prove_round(const HostFr* bind, size_t round, const HostFr& previous_claim, UnivariatePoly* out) override;
     int finish_rounds(const HostFr& bind) override;
 
+    jb_member* device_member() const { return mem_; }
+    bool passes_claim() const { return check_rounds_; }
+
    private:
     jb_member* mem_;
     bool check_rounds_;
@@ -65,6 +68,26 @@ struct RoundScheduler {
 struct SequentialRounds : RoundScheduler {
     int batch_prove_round(std::vector<MemberRound>& work) override;
     int batch_finish_rounds(std::vector<MemberFinish>& finishes) override;
+};
+
+// The device traversal (BuildRoundScheduler, crates/jolt-kernels/src/backend.rs:64-70): every active member's
+// round in ONE host round trip through jb_scheduler_* (a resident kernel for homogeneous batches, overlapped
+// launches otherwise). Members must be DeviceProductMember over one context.
+class DeviceRoundScheduler : public RoundScheduler {
+   public:
+    DeviceRoundScheduler() = default;
+    ~DeviceRoundScheduler() override;
+    int init(jb_ctx* ctx, const std::vector<DeviceProductMember*>& members);
+    int batch_prove_round(std::vector<MemberRound>& work) override;
+    int batch_finish_rounds(std::vector<MemberFinish>& finishes) override;
+
+   private:
+    jb_scheduler* sched_ = nullptr;
+    std::vector<DeviceProductMember*> members_;
+    std::vector<jb_round_work> work_;     // reused across rounds
+    std::vector<uint64_t> evals_;
+    std::vector<HostFr> tmp_;
+    size_t index_of(const ProveRounds* m) const;
 };
 
 // BatchMember / BatchPrelude (crates/jolt-sumcheck/src/batch.rs:24-71)

@@ -294,6 +294,66 @@ class ProductMember:
         return [t[0] for t in self.tables]
 
 
+class IncClaimReductionKernel:
+    """Restatement of the optimized stage-6b increment claim reduction
+    (crates/jolt-kernels/src/optimized/inc_claim_reduction.rs:47-203). prepare (:50-120): the four upstream eq
+    leaves collapse into A = eq(r_ram_rw) + gamma eq(r_ram_val), B = gamma^2 eq(s_reg_rw) + gamma^3 eq(s_reg_val)
+    (scaled_eq_table = EqPolynomial::evals(point, Some(scale)), big-endian); the summand is A*RamInc + B*RdInc.
+    prove_round (:166-186): bind_all low-to-high, group_evals at t in {0, 2} (:146-156),
+    round_poly_from_skipped_evals (support.rs:450-460). output_claims (:196-203): ram_inc[0], rd_inc[0]."""
+
+    def __init__(self, cycle_points, gamma, ram_inc, rd_inc, p=R_MOD):
+        self.p = p
+        n = len(ram_inc).bit_length() - 1
+        assert all(len(pt) == n for pt in cycle_points) and len(rd_inc) == len(ram_inc)
+        g2 = gamma * gamma % p
+        def combine(first, fs, second, ss):
+            a, b = eq_evals(first, fs, p), eq_evals(second, ss, p)
+            return [(x + y) % p for x, y in zip(a, b)]
+        self.ram_weights = combine(cycle_points[0], 1, cycle_points[1], gamma % p)
+        self.rd_weights = combine(cycle_points[2], g2, cycle_points[3], g2 * gamma % p)
+        self.ram_inc, self.rd_inc = [v % p for v in ram_inc], [v % p for v in rd_inc]
+        self.rounds = n
+
+    def tables(self):
+        """term-major order of the device member: (A, RamInc), (B, RdInc)"""
+        return [self.ram_weights, self.ram_inc, self.rd_weights, self.rd_inc]
+
+    def num_rounds(self):
+        return self.rounds
+
+    def _bind(self, c):
+        self.ram_inc = bind(self.ram_inc, c, LOW_TO_HIGH, self.p)
+        self.rd_inc = bind(self.rd_inc, c, LOW_TO_HIGH, self.p)
+        self.ram_weights = bind(self.ram_weights, c, LOW_TO_HIGH, self.p)
+        self.rd_weights = bind(self.rd_weights, c, LOW_TO_HIGH, self.p)
+
+    def prove_round(self, bind_c, rnd, previous_claim):
+        p = self.p
+        if bind_c is not None:
+            self._bind(bind_c)
+        half = len(self.ram_inc) // 2
+        e0 = e2 = 0
+        for y in range(half):
+            ram_lo, ram_hi = self.ram_inc[2 * y], self.ram_inc[2 * y + 1]
+            rd_lo, rd_hi = self.rd_inc[2 * y], self.rd_inc[2 * y + 1]
+            a_lo, a_hi = self.ram_weights[2 * y], self.ram_weights[2 * y + 1]
+            b_lo, b_hi = self.rd_weights[2 * y], self.rd_weights[2 * y + 1]
+            e0 += a_lo * ram_lo + b_lo * rd_lo
+            e2 += (a_hi + a_hi - a_lo) * (ram_hi + ram_hi - ram_lo) + (b_hi + b_hi - b_lo) * (rd_hi + rd_hi - rd_lo)
+        e0, e2 = e0 % p, e2 % p
+        return uni_from_evals([e0, (previous_claim - e0) % p, e2], p)   # round_poly_from_skipped_evals
+
+    def finish_rounds(self, bind_c):
+        self._bind(bind_c)
+
+    def final_evals(self):
+        return [self.ram_weights[0], self.ram_inc[0], self.rd_weights[0], self.rd_inc[0]]
+
+    def output_claims(self):
+        return {"ram_inc": self.ram_inc[0], "rd_inc": self.rd_inc[0]}
+
+
 def prove_batch(members_desc, members, max_num_vars, max_degree, claimed_sum, challenge_fn, p=R_MOD):
     """jolt-sumcheck/src/prover.rs:193-362. members_desc: list of dicts with
     input_claim, coefficient, rounds, offset. challenge_fn(round, coeffs)->challenge

@@ -24,6 +24,11 @@ int jb_member_num_rounds(jb_member*, size_t*) { return JB_ERR_NO_DEVICE; }
 int jb_member_degree(jb_member*, size_t*) { return JB_ERR_NO_DEVICE; }
 int jb_member_prove_round(jb_member*, const uint64_t*, size_t, const uint64_t*, uint64_t*) { return JB_ERR_NO_DEVICE; }
 int jb_member_finish_rounds(jb_member*, const uint64_t*) { return JB_ERR_NO_DEVICE; }
+jb_ctx* jb_member_context(jb_member*) { return nullptr; }
+int jb_scheduler_create(jb_ctx*, jb_member**, size_t, jb_scheduler**) { return JB_ERR_NO_DEVICE; }
+int jb_scheduler_prove_round(jb_scheduler*, const jb_round_work*, size_t, uint64_t*) { return JB_ERR_NO_DEVICE; }
+int jb_scheduler_finish_rounds(jb_scheduler*, const jb_finish_work*, size_t) { return JB_ERR_NO_DEVICE; }
+void jb_scheduler_destroy(jb_scheduler*) {}
 }
 
 namespace {

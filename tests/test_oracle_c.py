@@ -181,3 +181,39 @@ def test_hyperkzg_pieces():
     P = np.array([_aff(O.G1_GEN)], dtype=np.uint64)
     got = C.g1_powers(5, P[0], C.ints_to_mont([beta])[0])
     assert [_from_aff(got[i], False) for i in range(5)] == srs[:5]
+
+
+def test_inc_claim_reduction_restatement_matches_reference_tier_definition():
+    """The oracle's restatement of the optimized IncClaimReduction kernel (paired-eq fusion, evaluations at {0, 2},
+    s(1) from the claim; crates/jolt-kernels/src/optimized/inc_claim_reduction.rs:47-203) against the reference
+    tier's definition: the six-table summand (eq(r_ram_rw) + g eq(r_ram_val)) RamInc + (g^2 eq(s_reg_rw) +
+    g^3 eq(s_reg_val)) RdInc evaluated at t = 0, 1, 2 directly - the same lockstep the reference's own test runs."""
+    n, gamma = 6, 29
+    pts = [O.synthetic_point(n, s) for s in (3, 5, 7, 11)]
+    ram, rd = O.random_fr(1, 1 << n), O.random_fr(2, 1 << n)
+    k = O.IncClaimReductionKernel(pts, gamma, ram, rd)
+    eqs = [O.eq_evals(pt) for pt in pts]
+    scal = [1, gamma, gamma ** 2, gamma ** 3]
+    tabs = [list(ram), list(rd)] + [list(e) for e in eqs]
+    claim = sum((eqs[0][j] + gamma * eqs[1][j]) * ram[j] + (gamma ** 2 * eqs[2][j] + gamma ** 3 * eqs[3][j]) * rd[j]
+                for j in range(1 << n)) % O.R_MOD
+    ch = O.synthetic_point(n, 401)
+    bind = None
+    for rnd in range(n):
+        if bind is not None:
+            tabs = [O.bind(t, bind, O.LOW_TO_HIGH) for t in tabs]
+        ev = []
+        for t in range(3):
+            acc = 0
+            for y in range(len(tabs[0]) // 2):
+                v = [tb[2 * y] + t * (tb[2 * y + 1] - tb[2 * y]) for tb in tabs]
+                acc += (scal[0] * v[2] + scal[1] * v[3]) * v[0] + (scal[2] * v[4] + scal[3] * v[5]) * v[1]
+            ev.append(acc % O.R_MOD)
+        assert (ev[0] + ev[1]) % O.R_MOD == claim
+        got = k.prove_round(bind, rnd, claim)
+        assert got == O.uni_from_evals(ev), f"round {rnd}"
+        bind = ch[rnd]
+        claim = O.uni_evaluate(got, bind)
+    k.finish_rounds(bind)
+    tabs = [O.bind(t, bind, O.LOW_TO_HIGH) for t in tabs]
+    assert k.output_claims() == {"ram_inc": tabs[0][0], "rd_inc": tabs[1][0]}
