@@ -166,6 +166,12 @@ int jb_member_prove_round_partials(jb_member* mem, const uint64_t* bind_or_null,
 int jb_partials_finalize(jb_ctx* ctx, const void* device_lanes, size_t count, uint64_t* out_elems);
 /* The host half of the above (carry-propagate + fold mod r) on `count` x 8 host lanes; needs no device. */
 int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out_elems);
+/* The host half of a resident-kernel round (needs no device): `count` x 17 u64 lanes, each value the block-summed
+ * UNREDUCED accumulator sum_y a_y b_y over Montgomery operands (lane w = sum of the 32-bit limbs of weight 2^(32 w))
+ * -> canonical (sum) R^-1 mod r. The O(degree) serial tail of a round - carry propagation and the Montgomery
+ * reduction of a 544-bit sum - takes one CPU core ~0.2 us and one GPU lane ~2 us, and it sits on the latency path
+ * of every round, so the resident kernel hands it to the host (as the reference's host keeps interpolation). */
+int jb_wide_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out_elems);
 /* The host half of a round (needs no device). The round kernels emit, for a product of m tables,
  *   s(0), [s(1) unless skip_t1], s(2), .., s(m-1), s(inf)      (m >= 2; s(inf) = the leading coefficient)
  *   s(0), [s(1) unless skip_t1]                                (m == 1)

@@ -60,6 +60,7 @@ SIGNATURES = {
     "jb_ctx_set_verify_rounds": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "jb_partials_finalize": (ctypes.c_int, [c_void_p, c_void_p, c_size_t, c_u64p]),
     "jb_lanes_reduce_host": (ctypes.c_int, [c_u64p, c_size_t, c_u64p]),
+    "jb_wide_lanes_reduce_host": (ctypes.c_int, [c_u64p, c_size_t, c_u64p]),
     "jb_round_evals_from_kernel_values": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_u64p, c_u64p, c_u64p]),
     "jb_member_export_table": (ctypes.c_int, [c_void_p, c_size_t, c_void_p, c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_comm_unique_id": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint8), ctypes.c_char_p]),

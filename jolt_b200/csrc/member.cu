@@ -320,6 +320,7 @@ static int wait_round_result0(jb_ctx* c) { return wait_round_result(c, 0, c->res
 
 static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim,
                                uint64_t* out_evals);
+static int resident_values(int D, const uint64_t* lanes, uint64_t* vals);
 
 static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, const uint64_t* claim, uint64_t* out_evals);
 
@@ -451,9 +452,10 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     int st;
     if (skip1) {
         // the resident kernel serves this and every later round of the member: no launch per round
-        uint64_t vals[RES_SLOT_U64];
-        st = resident_member_round(mem, bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL, bind, false, vals);
+        uint64_t lanes[RES_SLOT_U64], vals[JB_MAX_EVALS * 4];
+        st = resident_member_round(mem, bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL, bind, false, lanes);
         if (st == JB_OK) {
+            resident_values(mem->m, lanes, vals);
             st = assemble_evals(c, mem->m, true, vals, claim, round, out_evals);
             if (st == JB_OK) mem->rounds_done++;
             return st;
@@ -669,7 +671,7 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
                     lanes_host = c->h_result;
                 }
                 uint64_t vals[JB_MAX_EVALS * 4];
-                st = jb_lanes_reduce_host(lanes_host, (size_t)K, vals);
+                st = lanes_host == lanes ? resident_values(mem->m, lanes, vals) : jb_lanes_reduce_host(lanes_host, (size_t)K, vals);
                 if (st != JB_OK) return st;
                 return assemble_evals(c, mem->m, skip1, vals, claim, round, out_evals);
             }
@@ -762,6 +764,45 @@ int jb_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out) {
         std::memcpy(out + 4 * k, v, 32);
     }
     return JB_OK;
+}
+
+// The serial tail of a round of the resident kernel: `count` values, each the 17 u64 lanes of a block-summed
+// unreduced accumulator sum_y a_y b_y over Montgomery operands (lane w = sum of the 32-bit limbs of weight 2^(32 w),
+// < 2^64). V = sum_w lane_w 2^(32 w) < 2^577 = lo + h0 2^256 + h1 2^512; the field value is V R^-1 mod p =
+// REDC(lo) + h0 + h1 R, each term one word-serial Montgomery product with the wide operand as the multiplier.
+int jb_wide_lanes_reduce_host(const uint64_t* lanes, size_t count, uint64_t* out) {
+    if (!lanes || !out) return JB_ERR_INVALID;
+    static const HostFr raw_one{{1, 0, 0, 0}};
+    static const HostFr r1{{HostFr::R1[0], HostFr::R1[1], HostFr::R1[2], HostFr::R1[3]}};
+    static const HostFr r2{{HostFr::R2[0], HostFr::R2[1], HostFr::R2[2], HostFr::R2[3]}};
+    for (size_t k = 0; k < count; ++k) {
+        const uint64_t* lane = lanes + 17 * k;
+        uint32_t w[20];
+        unsigned __int128 carry = 0;
+        for (int i = 0; i < 17; ++i) {
+            carry += lane[i];
+            w[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        for (int i = 17; i < 20; ++i) {
+            w[i] = (uint32_t)carry;
+            carry >>= 32;
+        }
+        HostFr lo, h0, h1;
+        for (int i = 0; i < 4; ++i) {
+            lo.l[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+            h0.l[i] = (uint64_t)w[8 + 2 * i] | ((uint64_t)w[8 + 2 * i + 1] << 32);
+        }
+        h1 = HostFr{{(uint64_t)w[16] | ((uint64_t)w[17] << 32), (uint64_t)w[18] | ((uint64_t)w[19] << 32), 0, 0}};
+        const HostFr v = raw_one * lo + r1 * h0 + r2 * h1;
+        v.store(out + 4 * k);
+    }
+    return JB_OK;
+}
+
+// lanes of one member's round (as the resident kernel publishes them) -> K canonical values
+static int resident_values(int D, const uint64_t* lanes, uint64_t* vals) {
+    return D == 1 ? jb_lanes_reduce_host(lanes, 1, vals) : jb_wide_lanes_reduce_host(lanes, (size_t)D, vals);
 }
 
 int jb_partials_finalize(jb_ctx* c, const void* device_lanes, size_t count, uint64_t* out) {
@@ -976,8 +1017,9 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
             if (st != JB_OK) return st;
             for (size_t i = 0; i < n_work; ++i) {
                 jb_member* m = s->members[work[i].member];
-                st = assemble_evals(c, m->m, true, out + (size_t)idx_of[i] * RES_SLOT_U64, work[i].claim, work[i].round,
-                                    out_evals + i * JB_MAX_EVALS * 4);
+                uint64_t vals[JB_MAX_EVALS * 4];
+                resident_values(m->m, out + (size_t)idx_of[i] * RES_SLOT_U64, vals);
+                st = assemble_evals(c, m->m, true, vals, work[i].claim, work[i].round, out_evals + i * JB_MAX_EVALS * 4);
                 if (st != JB_OK) return st;
                 m->rounds_done++;
             }
@@ -1010,7 +1052,7 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
             // short member: its own small resident kernel (a few blocks), one mailbox command
             if (!m->run) {
                 jb_member* one[1] = {m};
-                int st = resident_begin(c, one, 1);
+                int st = resident_begin(c, one, 1, len_after / 2, false);
                 if (st != JB_OK && st != JB_ERR_UNSUPPORTED) return st;
             }
             if (m->run && resident_run_size(m->run) == 1) {
@@ -1034,7 +1076,11 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
         if (via[i] == VIA_RUN) {
             uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
             st = resident_wait(m->run, out);
-            if (st == JB_OK) st = assemble_evals(c, m->m, true, out, w.claim, w.round, out_evals + i * JB_MAX_EVALS * 4);
+            if (st == JB_OK) {
+                uint64_t vals[JB_MAX_EVALS * 4];
+                resident_values(m->m, out, vals);
+                st = assemble_evals(c, m->m, true, vals, w.claim, w.round, out_evals + i * JB_MAX_EVALS * 4);
+            }
         } else {
             st = wait_round_result(c, (int)i + 1, seqs[i]);
             if (st == JB_OK)

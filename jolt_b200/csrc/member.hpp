@@ -89,7 +89,9 @@ struct jb_member {
 // Starts a resident kernel serving `n` members (same D, P, order, same context; n <= RES_MAX_MEMBERS). Members
 // must be plain (not eq / sharded-with-tail). `exchange`: the kernel may be asked to all-reduce member 0's sums
 // over peer memory (sharded rounds). JB_ERR_UNSUPPORTED = not eligible (caller falls back to launches).
-int resident_begin(jb_ctx* c, jb_member** mems, int n);
+// first_items: the largest pass the run will be asked for (0 = derive from the tables: len / 2); may_evict: stop
+// other runs of the context if the device cannot hold this one next to them (false: JB_ERR_UNSUPPORTED instead).
+int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_items = 0, bool may_evict = true);
 // One round for the whole run. actions[i] in RES_ACT_*; challenge may be null when no action binds. `out`
 // (may be null) receives n x RES_SLOT_U64 mailbox words: per member K canonical values (4 u64 each), or - with
 // `exchange` - member 0's K x 8 all-reduced u64 lanes. Host-side table state (len, ping-pong) is advanced and the

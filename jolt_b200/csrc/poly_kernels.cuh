@@ -127,7 +127,7 @@ struct RoundOut {
     uint64_t xseq;
     long long timeout_cycles;
 };
-constexpr int XCH_SLOT_U64 = 64;                 // u64 lanes per (parity, source) slot
+constexpr int XCH_SLOT_U64 = 72;                 // u64 lanes per (parity, source) slot (4 values x 17 lanes fit)
 constexpr int XCH_FLAG_BASE = 2 * 16 * XCH_SLOT_U64;  // flags[parity][source] follow the slots
 constexpr size_t XCH_BYTES = (size_t)(XCH_FLAG_BASE + 2 * 16) * 8;
 
@@ -283,7 +283,10 @@ __device__ __forceinline__ Fr ld_tab(const uint64_t* base, size_t idx) {
 // The body of a pass: thread `first` .. step `stride` over the pair indices. On return thread 0 of the block
 // holds the block's K sums in acc[] and a __syncthreads() has been executed (dsm may be reused).
 // dsm: FusedShape<D, SKIP1>::smem_bytes(BLOCK) bytes of dynamic shared memory.
-template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, bool WEIGHTED, bool NC>
+// RAW (D > 1): skip the block's Montgomery reduction and leave the K x 17 integer column sums (u64) in the scratch
+// area dsm + acc_words - the resident kernel ships them to the host, which does the O(K) serial reduction far
+// faster than one GPU lane can (acc[] is then not written).
+template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, bool WEIGHTED, bool NC, bool RAW = false>
 __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, const BindScalar& s, uint32_t* dsm,
                                            size_t first, size_t stride, Fr (&acc)[FusedShape<D, SKIP1>::K]) {
     constexpr int K = FusedShape<D, SKIP1>::K;
@@ -477,7 +480,7 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
             if (lane == 0) colsum[c] = sacc;
         }
         __syncthreads();
-        if (warp == 0) {
+        if (!RAW && warp == 0) {
             Fr mine = Fr::zero();
             if (lane < K) {
                 uint32_t Tw[17];

@@ -18,7 +18,6 @@ struct ResidentRun {
     jb_ctx* c = nullptr;
     TailRes res;
     ResMailbox* mb = nullptr;  // host view of the mailbox
-    uint64_t* d_partial = nullptr;
     uint64_t seq = 0;
     int n = 0;
     jb_member* mem[RES_MAX_MEMBERS] = {nullptr};
@@ -148,7 +147,6 @@ void release_run(ResidentRun* run, bool mark_no_resident) {
     // later work on the context's stream is ordered after the kernel's exit
     cudaEventRecord(run->res.event, run->res.stream);
     cudaStreamWaitEvent(c->stream, run->res.event, 0);
-    if (run->d_partial) c->dev_free(run->d_partial);
     c->tail_pool.push_back(run->res);
     for (int i = 0; i < run->n; ++i) {
         if (run->mem[i]) {
@@ -187,7 +185,7 @@ void jb_ctx::quiesce_resident(bool all) {
         if (all || r->exclusive) resident_end(r, true);
 }
 
-int resident_begin(jb_ctx* c, jb_member** mems, int n) {
+int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_items, bool may_evict) {
     if (n < 1 || n > RES_MAX_MEMBERS) return JB_ERR_UNSUPPORTED;
     const int D = mems[0]->m, P = mems[0]->terms, order = mems[0]->order, T = D * P;
     uint64_t max_items = 1;
@@ -196,6 +194,7 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n) {
         if (m->ctx != c || m->m != D || m->terms != P || m->order != order || !resident_eligible(m)) return JB_ERR_UNSUPPORTED;
         max_items = std::max<uint64_t>(max_items, m->len / 2);
     }
+    if (first_items) max_items = first_items;  // the caller knows the largest pass it will ever ask for
     size_t smem = 0;
     ResKernel kernel = pick_kernel(D, P, order, &smem);
     if (!kernel) return JB_ERR_UNSUPPORTED;
@@ -206,8 +205,10 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n) {
     // co-residency budget: small runs may share the device, a big one needs it alone
     unsigned in_use = 0;
     for (auto* r : c->runs) in_use += r->grid;
-    if (!c->runs.empty() && (exclusive || c->has_exclusive_run() || in_use + grid > (unsigned)c->sm_count))
+    if (!c->runs.empty() && (exclusive || c->has_exclusive_run() || in_use + grid > (unsigned)c->sm_count)) {
+        if (!may_evict) return JB_ERR_UNSUPPORTED;  // (other runs may have commands in flight)
         c->quiesce_resident(true);
+    }
 
     ResidentRun* run = new (std::nothrow) ResidentRun();
     if (!run) return JB_ERR_OOM;
@@ -234,9 +235,7 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n) {
             args.mem[i].alt[j] = t.alt;
         }
     }
-    if (st == JB_OK) st = c->dev_alloc((void**)&run->d_partial, (size_t)grid * n * D * 32);
     if (st != JB_OK) {
-        if (run->d_partial) c->dev_free(run->d_partial);
         c->tail_pool.push_back(run->res);
         delete run;
         return st;
@@ -244,7 +243,6 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n) {
     std::memset(run->mb, 0, sizeof(ResMailbox));
     args.mb = (ResMailbox*)run->res.mb_dev;
     args.st = (ResState*)run->res.d_state;
-    args.partial = run->d_partial;
     args.timeout_cycles = 20000000000LL;  // ~10 s of SM clocks without a command: give the SMs back
     args.world = c->world;
     args.rank = c->rank;
@@ -258,7 +256,6 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n) {
     c->launches++;
     if (e != cudaSuccess) {
         st = c->check(e, "resident_rounds_kernel launch");
-        c->dev_free(run->d_partial);
         c->tail_pool.push_back(run->res);
         delete run;
         return st;

@@ -10,9 +10,13 @@
 //   blk 0: warp 0 polls that line over PCIe (one coalesced 64 B read per poll), then re-publishes it in DEVICE
 //          memory (ResState) with a release store; the other blocks spin on that word with acquire loads (L2)
 //   all  : run their share of the fused bind + sweep pass of every active member (the same fused_pass body as
-//          the one-launch-per-round kernel), store per-block partial sums, arrive on a ticket counter
-//   last : the last block to arrive folds the partials (one warp per value), resets the ticket and writes the
-//          K values per member to the mailbox followed by res_seq, which the host spins on
+//          the one-launch-per-round kernel) and add the block's UNREDUCED column sums - K values x 17 u64 lanes of
+//          32-bit limb sums - into the round's lane accumulators with integer REDs (exact, order-free), then arrive
+//          on a ticket counter
+//   last : the last block to arrive copies the lanes to the mailbox (and zeroes them), resets the ticket and raises
+//          res_seq, which the host spins on. The O(K) serial tail - carry propagation and the Montgomery reduction
+//          of each 544-bit sum - runs on the HOST (jb_wide_lanes_reduce_host): one CPU core does it in ~0.2 us,
+//          one GPU lane needs ~2 us, and it sits on the latency path of every round.
 //
 // The bind -> next round's reads dependency between DIFFERENT blocks is carried by that same chain
 // (stores -> bar.sync -> fence -> ticket atomic ... res_seq -> host -> cmd_seq -> release/acquire -> bar.sync ->
@@ -34,13 +38,14 @@ namespace jb {
 
 constexpr int RES_MAX_MEMBERS = 8;
 constexpr int RES_BLOCK = 256;
-constexpr size_t RES_SMALL_LEN = 8192;  // tables this short need <= 16 blocks: such runs coexist with other work
-constexpr int RES_SLOT_U64 = 32;  // mailbox result words per member: 4 values x 8 u64 (lanes) or T finals x 4 u64
+constexpr size_t RES_SMALL_LEN = 8192;  // tables this short need few blocks: such runs coexist with other work
+// mailbox / accumulator words per member: K <= 4 values x 17 lanes (products) or x 8 lanes (D = 1), or T finals x 4
+constexpr int RES_SLOT_U64 = 72;
 
 // per-member action of a round command (4 bits each, member i at bits [16 + 4i, 20 + 4i) of cmd)
 enum : unsigned { RES_ACT_NONE = 0, RES_ACT_EVAL = 1, RES_ACT_BIND_EVAL = 2, RES_ACT_FINAL = 3 };
 enum : uint64_t { RES_OP_ROUND = 1, RES_OP_ABORT = 2 };
-constexpr uint64_t RES_FLAG_EXCHANGE = 1ull << 8;  // member 0's sums are all-reduced over peer memory (lanes out)
+constexpr uint64_t RES_FLAG_EXCHANGE = 1ull << 8;  // member 0's sums are all-reduced over peer memory
 
 struct alignas(64) ResMailbox {
     // line 0 (64 B), host -> device. The host writes the payload first and cmd_seq last; the device reads the
@@ -55,22 +60,26 @@ struct alignas(64) ResMailbox {
     volatile uint64_t res_seq;
     uint64_t status;  // 0 ok, 1 aborted / timed out, 2 exchange timed out
     uint64_t pad1[6];
+    // per member: the round's K sums as lanes - value e at [e * 17, e * 17 + 17) (D >= 2: 32-bit limb column sums
+    // of the unreduced 544-bit accumulators) or [e * 8, e * 8 + 8) (D = 1: limb sums of canonical values) - or,
+    // after a terminal bind that left the member fully bound, its T final values (4 limbs each)
     uint64_t result[RES_MAX_MEMBERS * RES_SLOT_U64];
     // observability (specs/clean-slate-prover.md:585-587): %globaltimer (ns) when block 0 decoded command s and
-    // when the last block had folded its partials, at [2 (s - 1 mod 64)] and [.. + 1]
+    // when the last block had collected the round's sums, at [2 (s - 1 mod 64)] and [.. + 1]
     uint64_t tlog[2 * 64];
     // finer stamps of the same rounds (diagnostics): [4 s + 0] block 0 finished its passes, [4 s + 1] block 0 arrived
     // on the ticket, [4 s + 2] the last block saw that it is last, [4 s + 3] spare
     uint64_t tlog2[4 * 64];
 };
 
-// Device-side re-publication of the command line + the arrival counter.
+// Device-side re-publication of the command line, the arrival counter and the round's lane accumulators.
 struct alignas(128) ResState {
     uint64_t seq;
     uint64_t cmd[7];
     uint64_t pad[8];
     unsigned int ticket;
     unsigned int pad2[31];
+    uint64_t lanes[RES_MAX_MEMBERS * RES_SLOT_U64];  // zero between rounds
 };
 
 struct ResMemberArg {
@@ -84,7 +93,6 @@ struct ResArgs {
     int n_members;
     ResMailbox* mb;     // host-mapped
     ResState* st;       // device
-    uint64_t* partial;  // gridDim.x * n_members * K canonical elements
     long long timeout_cycles;
     // peer exchange (world > 1): exchange buffer of every rank as mapped in THIS process
     uint64_t* peer[16];
@@ -99,38 +107,64 @@ __device__ __forceinline__ uint64_t ld_acquire_gpu(const uint64_t* p) {
 __device__ __forceinline__ void st_release_gpu(uint64_t* p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 
-__host__ __device__ inline unsigned res_blocks_for(uint64_t items, unsigned cap) {
-    const uint64_t need = (items + RES_BLOCK - 1) / RES_BLOCK;
-    return (unsigned)(need < cap ? (need < 1 ? 1 : need) : cap);
+// How `items` independent work items (pair indices / bind outputs) are laid over at most `cap` blocks.
+// Large rounds fill every block (256 threads, grid-stride). Once there is less than one item per thread the
+// pass is pure latency - a warp's chain of dependent IMAD.WIDEs - so the items are spread THIN: two warps per
+// block over as many SMs as are alive rather than eight warps contending for one SM's multiplier; up to 256
+// items stay in a single block (no broadcast, no ticket).
+struct ResShape {
+    unsigned nblk, tpb;
+};
+__host__ __device__ inline ResShape res_shape(uint64_t items, unsigned cap) {
+    ResShape s;
+    if (items <= (uint64_t)RES_BLOCK || cap <= 1) {
+        s.nblk = 1;
+        const uint64_t t = items < (uint64_t)RES_BLOCK ? ((items + 31) / 32) * 32 : RES_BLOCK;
+        s.tpb = t < 32 ? 32u : (unsigned)t;
+        return s;
+    }
+    const uint64_t want = (items + 63) / 64;
+    s.nblk = (unsigned)(want < cap ? want : cap);
+    const uint64_t per = (items + s.nblk - 1) / s.nblk;
+    const uint64_t t = ((per + 31) / 32) * 32;
+    s.tpb = t > (uint64_t)RES_BLOCK ? (unsigned)RES_BLOCK : (unsigned)t;
+    return s;
 }
+__host__ __device__ inline unsigned res_blocks_for(uint64_t items, unsigned cap) { return res_shape(items, cap).nblk; }
 
 // One member's pass as an out-of-line call: the pass body gets the whole register budget to itself (the round
 // loop's own state is saved around ONE call per round instead of squeezing the inner loop into spills).
-// Thread 0 leaves the block's K sums at `g_dst` (global: one of several blocks) or, when this block is the only
-// live one, straight in shared memory at `s_dst` (K x 8 words) - no trip through L2 on the latency path.
+// The block's sums leave as lanes (K x 17 column sums for products, K x 8 limbs for D = 1): added into the round's
+// accumulators at `g_lanes` with integer REDs, or - when this block is the only live one - left straight in
+// shared memory at `s_dst`: no trip through L2 on the latency path.
 template <int D, int P, int ORDER, bool BIND, bool HI4>
 __device__ __noinline__ void resident_pass(const TablePtrs tp, size_t pairs, const BindScalar sc, uint32_t* dsm, size_t first,
-                                           size_t stride, uint64_t* g_dst, uint32_t* s_dst) {
+                                           size_t stride, uint64_t* g_lanes, uint64_t* s_dst) {
     constexpr int K = D;
     Fr acc[K];
-    fused_pass<D, P, ORDER, BIND, HI4, true, RES_BLOCK, false, false>(tp, pairs, sc, dsm, first, stride, acc);
-    if (threadIdx.x == 0) {
-        if (s_dst) {
-#pragma unroll
-            for (int e = 0; e < K; ++e)
-#pragma unroll
-                for (int w = 0; w < 8; ++w) s_dst[e * 8 + w] = acc[e].v[w];
-        } else {
-#pragma unroll
-            for (int e = 0; e < K; ++e) st_elem(g_dst, e, acc[e]);
+    fused_pass<D, P, ORDER, BIND, HI4, true, RES_BLOCK, false, false, (D > 1)>(tp, pairs, sc, dsm, first, stride, acc);
+    const int tid = threadIdx.x;
+    if (D > 1) {
+        const uint64_t* colsum = reinterpret_cast<const uint64_t*>(dsm + FusedShape<D, true>::acc_words(RES_BLOCK));
+        if (tid < K * 17) {
+            const uint64_t v = colsum[tid];
+            if (s_dst) s_dst[tid] = v;
+            else atomicAdd(reinterpret_cast<unsigned long long*>(g_lanes) + tid, (unsigned long long)v);
         }
+    } else if (tid == 0) {
+#pragma unroll
+        for (int e = 0; e < K; ++e)
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                if (s_dst) s_dst[e * 8 + w] = acc[e].v[w];
+                else atomicAdd(reinterpret_cast<unsigned long long*>(g_lanes) + e * 8 + w, (unsigned long long)acc[e].v[w]);
+            }
     }
 }
 
@@ -138,15 +172,15 @@ template <int D, int P, int ORDER>
 __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __grid_constant__ ResArgs a) {
     constexpr int T = D * P;
     constexpr int K = D;  // s(1) always comes from the running claim (the optimized tier's convention)
+    constexpr int KL = D == 1 ? K * 8 : K * 17;  // lanes per member
     extern __shared__ uint32_t dsm[];
     __shared__ uint64_t s_line[8];
     __shared__ uint64_t* s_cur[RES_MAX_MEMBERS][T];
     __shared__ uint64_t* s_oth[RES_MAX_MEMBERS][T];
     __shared__ uint64_t s_len[RES_MAX_MEMBERS];
-    __shared__ unsigned s_nblk[RES_MAX_MEMBERS];
     __shared__ unsigned s_live_next;
     __shared__ int s_last;
-    __shared__ uint32_t s_tot[RES_MAX_MEMBERS * K * 8];
+    __shared__ uint64_t s_lanes[RES_MAX_MEMBERS * RES_SLOT_U64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned b = blockIdx.x, grid = gridDim.x;
     const int NM = a.n_members;
@@ -237,9 +271,9 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
             const uint64_t len = s_len[m];
             if (act == RES_ACT_FINAL) {  // terminal bind: no sweep
                 const uint64_t half = len / 2;
-                const unsigned nblk = res_blocks_for(half, grid);
-                if (b < nblk) {
-                    for (uint64_t i = (uint64_t)b * RES_BLOCK + tid; i < half; i += (uint64_t)nblk * RES_BLOCK) {
+                const ResShape sh = res_shape(half, live);
+                if (b < sh.nblk && tid < (int)sh.tpb) {
+                    for (uint64_t i = (uint64_t)b * sh.tpb + tid; i < half; i += (uint64_t)sh.nblk * sh.tpb) {
 #pragma unroll
                         for (int j = 0; j < T; ++j) {
                             const uint64_t* in = s_cur[m][j];
@@ -254,9 +288,8 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
             }
             const bool bind = act == RES_ACT_BIND_EVAL;
             const uint64_t pairs = (bind ? len / 2 : len) / 2;
-            const unsigned nblk = res_blocks_for(pairs, grid);
-            if (tid == 0) s_nblk[m] = nblk;
-            if (b < nblk) {
+            const ResShape sh = res_shape(pairs, live);
+            if (b < sh.nblk) {
                 TablePtrs tp;
 #pragma unroll
                 for (int j = 0; j < T; ++j) {
@@ -265,15 +298,17 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 }
                 tp.e_out = tp.e_in = nullptr;
                 tp.in_bits = 0;
-                const size_t first = (size_t)b * RES_BLOCK + tid, stride = (size_t)nblk * RES_BLOCK;
-                uint64_t* dst = a.partial + (((size_t)b * NM + m) * K) * 4;
-                uint32_t* sdst = live == 1 ? s_tot + m * K * 8 : nullptr;
+                // threads beyond this round's width have no pair (they still take part in the block reduction)
+                const size_t first = tid < (int)sh.tpb ? (size_t)b * sh.tpb + tid : (size_t)pairs;
+                const size_t stride = (size_t)sh.nblk * sh.tpb;
+                uint64_t* gl = a.st->lanes + m * RES_SLOT_U64;
+                uint64_t* sl = live == 1 ? s_lanes + m * RES_SLOT_U64 : nullptr;
                 if (!bind)
-                    resident_pass<D, P, ORDER, false, false>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+                    resident_pass<D, P, ORDER, false, false>(tp, pairs, sc, dsm, first, stride, gl, sl);
                 else if (hi4)
-                    resident_pass<D, P, ORDER, true, true>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+                    resident_pass<D, P, ORDER, true, true>(tp, pairs, sc, dsm, first, stride, gl, sl);
                 else
-                    resident_pass<D, P, ORDER, true, false>(tp, pairs, sc, dsm, first, stride, dst, sdst);
+                    resident_pass<D, P, ORDER, true, false>(tp, pairs, sc, dsm, first, stride, gl, sl);
             }
         }
         if (b == 0 && tid == 0) a.mb->tlog2[4 * ((seq - 1) & 63)] = global_timer_ns();
@@ -314,35 +349,29 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
         }
         __syncthreads();
         if (s_last) {
-            // ---- the last block to arrive folds every member's partials and answers the host ------------
-            if (live > 1) __threadfence();
-            for (int it = warp; live > 1 && it < NM * K; it += RES_BLOCK / 32) {
-                const int m = it / K, e = it % K;
-                const unsigned act = (actions >> (4 * m)) & 0xf;
-                if (act != RES_ACT_EVAL && act != RES_ACT_BIND_EVAL) continue;
-                const unsigned nb = s_nblk[m];
-                Fr t = Fr::zero();
-                for (unsigned bb = lane; bb < nb; bb += 32)
-                    t = fp_add(t, ld_elem_cg<Fr>(a.partial, ((size_t)bb * NM + m) * K + e));
-                t = warp_sum(t);
-                if (lane == 0) {
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) s_tot[(m * K + e) * 8 + w] = t.v[w];
+            // ---- the last block to arrive collects every member's lanes and answers the host ------------
+            if (live > 1) {
+                __threadfence();
+                for (int idx = tid; idx < NM * RES_SLOT_U64; idx += RES_BLOCK) {
+                    const int m = idx / RES_SLOT_U64, i = idx % RES_SLOT_U64;
+                    const unsigned act = (actions >> (4 * m)) & 0xf;
+                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < KL) {
+                        s_lanes[idx] = __ldcg(a.st->lanes + idx);
+                        a.st->lanes[idx] = 0;  // back to zero for the next round
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
-            if (warp == 0) {
-                uint64_t status = 0;
-                if (lane == 0) a.mb->tlog[2 * ((seq - 1) & 63) + 1] = global_timer_ns();
-                if (lane == 0 && live > 1) a.st->ticket = 0;
-                if (cmdw & RES_FLAG_EXCHANGE) {
-                    // all-reduce of member 0's K sums over NVLink peer memory, as u64 lanes of 32-bit limbs
+            uint64_t status = 0;
+            if (cmdw & RES_FLAG_EXCHANGE) {
+                // all-reduce of member 0's lanes over NVLink peer memory (integer sums: exact, order-free)
+                if (warp == 0) {
                     const uint64_t xseq = s_line[6];
                     const int par = (int)(xseq & 1);
                     const int slot = (par * 16 + a.rank) * XCH_SLOT_U64;
-                    for (int idx = lane; idx < a.world * K * 8; idx += 32) {
-                        const int g = idx / (K * 8), i = idx % (K * 8);
-                        *(volatile uint64_t*)(a.peer[g] + slot + i) = (uint64_t)s_tot[i];
+                    for (int idx = lane; idx < a.world * KL; idx += 32) {
+                        const int g = idx / KL, i = idx % KL;
+                        *(volatile uint64_t*)(a.peer[g] + slot + i) = s_lanes[i];
                     }
                     __syncwarp();
                     __threadfence_system();  // cumulative: covers the other lanes' stores ordered by the barrier
@@ -360,47 +389,46 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                     }
                     ok = __all_sync(0xffffffffu, ok);
                     __threadfence_system();
-                    if (lane < K * 8) {
+                    for (int i = lane; i < KL; i += 32) {
                         uint64_t sum = 0;
                         for (int src = 0; src < a.world; ++src)
-                            sum += *(volatile uint64_t*)(mine + (par * 16 + src) * XCH_SLOT_U64 + lane);
-                        a.mb->result[lane] = sum;
+                            sum += *(volatile uint64_t*)(mine + (par * 16 + src) * XCH_SLOT_U64 + i);
+                        a.mb->result[i] = sum;
                     }
                     if (!ok) status = 2;
-                } else {
-                    for (int idx = lane; idx < NM * K * 4; idx += 32) {
-                        const int m = idx / (K * 4), r = idx % (K * 4), e = r / 4, w = r % 4;
-                        const unsigned act = (actions >> (4 * m)) & 0xf;
-                        if (act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) {
-                            const uint32_t* t = s_tot + (m * K + e) * 8;
-                            a.mb->result[m * RES_SLOT_U64 + e * 4 + w] = (uint64_t)t[2 * w] | ((uint64_t)t[2 * w + 1] << 32);
-                        }
-                    }
                 }
-                // terminal binds that left a member fully bound hand the T values back with the acknowledgement
-                for (int idx = lane; idx < NM * T; idx += 32) {
-                    const int m = idx / T, j = idx % T;
+            } else {
+                for (int idx = tid; idx < NM * RES_SLOT_U64; idx += RES_BLOCK) {
+                    const int m = idx / RES_SLOT_U64, i = idx % RES_SLOT_U64;
                     const unsigned act = (actions >> (4 * m)) & 0xf;
-                    if (act == RES_ACT_FINAL && s_len[m] == 1) {
-                        const Fr v = ld_elem_cg<Fr>(s_cur[m][j], 0);
+                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < KL) a.mb->result[idx] = s_lanes[idx];
+                }
+            }
+            // terminal binds that left a member fully bound hand the T values back with the acknowledgement
+            for (int idx = tid; idx < NM * T; idx += RES_BLOCK) {
+                const int m = idx / T, j = idx % T;
+                const unsigned act = (actions >> (4 * m)) & 0xf;
+                if (act == RES_ACT_FINAL && s_len[m] == 1) {
+                    const Fr v = ld_elem_cg<Fr>(s_cur[m][j], 0);
 #pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                            a.mb->result[m * RES_SLOT_U64 + j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
-                    }
+                    for (int w = 0; w < 4; ++w)
+                        a.mb->result[m * RES_SLOT_U64 + j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_system();  // cumulative over the warp's result stores (ordered by the barrier)
-                    a.mb->status = status;
-                    __threadfence_system();
-                    a.mb->res_seq = seq;
-                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                a.mb->tlog[2 * ((seq - 1) & 63) + 1] = global_timer_ns();
+                if (live > 1) a.st->ticket = 0;
+                __threadfence_system();  // cumulative over the block's result stores (ordered by the barrier)
+                a.mb->status = status;
+                __threadfence_system();
+                a.mb->res_seq = seq;
             }
         }
         const unsigned ln = s_live_next;
         if (b >= ln) return;
         live = ln;
-        __syncthreads();  // s_line / s_nblk / s_last are rewritten by the next round
+        __syncthreads();  // s_line / s_last / s_lanes are rewritten by the next round
     }
 }
 

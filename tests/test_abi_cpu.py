@@ -144,3 +144,33 @@ def test_round_evals_from_kernel_values(m, skip1):
             assert lib.jb_round_evals_from_kernel_values(m, 0, _p(vin), _p(bad), _p(out)) == jolt_b200._lib.JB_ERR_ROUND_CHECK
             assert lib.jb_round_evals_from_kernel_values(m, 0, _p(vin), None, _p(out)) == JB_OK
     assert lib.jb_round_evals_from_kernel_values(5, 0, _p(vin), None, _p(out)) == jolt_b200._lib.JB_ERR_INVALID
+
+
+def test_wide_lanes_reduce_host_matches_big_int():
+    """jb_wide_lanes_reduce_host (the host tail of a resident-kernel round): 17 u64 lanes of 32-bit limb column sums
+    -> (sum) * R^-1 mod r, against Python integers; includes the all-ones extreme and real sums of products."""
+    lib = _lib.load()
+    rng = np.random.Generator(np.random.PCG64(11))
+    rows = [rng.integers(0, 1 << 63, size=17, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=17, dtype=np.uint64)
+            for _ in range(6)]
+    rows.append(np.full(17, (1 << 64) - 1, dtype=np.uint64))
+    rows.append(np.zeros(17, dtype=np.uint64))
+    # genuine accumulators: sum of 1000 products of Montgomery-form operands, limb columns summed separately
+    a = [O.mont_raw(O.to_mont_limbs(v)) for v in O.random_fr(1, 1000)]
+    b = [O.mont_raw(O.to_mont_limbs(v)) for v in O.random_fr(2, 1000)]
+    cols = [0] * 17
+    for x, y in zip(a, b):
+        pr = x * y
+        for w in range(16):
+            cols[w] += (pr >> (32 * w)) & 0xFFFFFFFF
+    rows.append(np.array(cols, dtype=np.uint64))
+    lanes = np.ascontiguousarray(np.stack(rows))
+    out = np.zeros((len(rows), 4), dtype=np.uint64)
+    assert lib.jb_wide_lanes_reduce_host(lanes.ctypes.data_as(_lib.c_u64p), len(rows), out.ctypes.data_as(_lib.c_u64p)) == 0
+    rinv = pow(1 << 256, -1, O.R_MOD)
+    for row, got in zip(rows, out):
+        v = sum(int(x) << (32 * w) for w, x in enumerate(row))
+        assert O.mont_raw([int(t) for t in got]) == v * rinv % O.R_MOD
+    # the last row is sum a_i b_i in Montgomery form: (sum aR bR) R^-1 = (sum a b) R
+    want = sum(x * y for x, y in zip(O.random_fr(1, 1000), O.random_fr(2, 1000))) % O.R_MOD
+    assert O.from_mont_limbs([int(t) for t in out[-1]]) == want
