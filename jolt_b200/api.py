@@ -354,7 +354,8 @@ class ProductMember:
 
     def close(self):
         if self.h:
-            self.s.lib.jb_member_destroy(self.h)
+            if self.s.h:  # (a member outliving its session was freed with the session's pools)
+                self.s.lib.jb_member_destroy(self.h)
             self.h = None
 
     def __del__(self):

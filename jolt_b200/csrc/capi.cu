@@ -179,6 +179,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     if (const char* sh = std::getenv("JB_FUSED_SHAPE")) c->fused_shape = std::atoi(sh);  // tuning knob
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
     if (const char* ml = std::getenv("JB_RESIDENT_MAX_LOG")) c->resident_max_log = std::atoi(ml);
+    if (std::getenv("JB_NO_LOOKAHEAD")) c->lookahead = false;  // diagnostics: every round waits for its own answer
     // A kernel-replaying profiler (ncu) or a serialising tool (compute-sanitizer, nsys CUDA trace) cannot
     // run a kernel that waits for host commands; under CUDA injection keep one launch per round.
     {
@@ -189,6 +190,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
                 c->use_tail = false;
         }
     }
+    if (std::getenv("JB_FORCE_RESIDENT")) c->use_tail = true;  // debugging: keep the resident kernel under a tool
     // keep freed blocks in the pool (ProofSession "device memory pools")
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

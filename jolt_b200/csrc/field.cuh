@@ -431,6 +431,62 @@ __device__ __forceinline__ void mul_wide_acc_smem(uint32_t* acc, int stride, con
     for (int k = 0; k < 17; ++k) acc[k * stride] = A[k];
 }
 
+// Register form: A[0..16] += a * b (plain 512-bit product of the limbs; operands may be lazy, < 2p).
+__device__ __forceinline__ void mul_wide_acc_reg(uint32_t (&A)[17], const uint32_t* a, const uint32_t* b) {
+    uint32_t E[17], O[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) E[k] = O[k] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+        chain8_top(E + i, E[i + 8], a[0], a[2], a[4], a[6], b[i]);
+        chain8_top(O + i, O[i + 8], a[1], a[3], a[5], a[7], b[i]);
+        chain8_top(O + i, O[i + 8], a[0], a[2], a[4], a[6], b[i + 1]);
+        chain8_top(E + i + 2, E[i + 10], a[1], a[3], a[5], a[7], b[i + 1]);
+    }
+    asm("add.cc.u32 %0, %0, %17;\n\t"
+        "addc.cc.u32 %1, %1, %18;\n\t"
+        "addc.cc.u32 %2, %2, %19;\n\t"
+        "addc.cc.u32 %3, %3, %20;\n\t"
+        "addc.cc.u32 %4, %4, %21;\n\t"
+        "addc.cc.u32 %5, %5, %22;\n\t"
+        "addc.cc.u32 %6, %6, %23;\n\t"
+        "addc.cc.u32 %7, %7, %24;\n\t"
+        "addc.cc.u32 %8, %8, %25;\n\t"
+        "addc.cc.u32 %9, %9, %26;\n\t"
+        "addc.cc.u32 %10, %10, %27;\n\t"
+        "addc.cc.u32 %11, %11, %28;\n\t"
+        "addc.cc.u32 %12, %12, %29;\n\t"
+        "addc.cc.u32 %13, %13, %30;\n\t"
+        "addc.cc.u32 %14, %14, %31;\n\t"
+        "addc.cc.u32 %15, %15, %32;\n\t"
+        "addc.u32 %16, %16, 0;"
+        : "+r"(A[0]), "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]),
+          "+r"(A[8]), "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15]),
+          "+r"(A[16])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
+          "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]));
+    asm("add.cc.u32 %0, %0, %16;\n\t"
+        "addc.cc.u32 %1, %1, %17;\n\t"
+        "addc.cc.u32 %2, %2, %18;\n\t"
+        "addc.cc.u32 %3, %3, %19;\n\t"
+        "addc.cc.u32 %4, %4, %20;\n\t"
+        "addc.cc.u32 %5, %5, %21;\n\t"
+        "addc.cc.u32 %6, %6, %22;\n\t"
+        "addc.cc.u32 %7, %7, %23;\n\t"
+        "addc.cc.u32 %8, %8, %24;\n\t"
+        "addc.cc.u32 %9, %9, %25;\n\t"
+        "addc.cc.u32 %10, %10, %26;\n\t"
+        "addc.cc.u32 %11, %11, %27;\n\t"
+        "addc.cc.u32 %12, %12, %28;\n\t"
+        "addc.cc.u32 %13, %13, %29;\n\t"
+        "addc.cc.u32 %14, %14, %30;\n\t"
+        "addc.u32 %15, %15, 0;"
+        : "+r"(A[1]), "+r"(A[2]), "+r"(A[3]), "+r"(A[4]), "+r"(A[5]), "+r"(A[6]), "+r"(A[7]), "+r"(A[8]),
+          "+r"(A[9]), "+r"(A[10]), "+r"(A[11]), "+r"(A[12]), "+r"(A[13]), "+r"(A[14]), "+r"(A[15]), "+r"(A[16])
+        : "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]),
+          "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+
 // 544-bit accumulator (17 words at acc[k * stride]) -> canonical acc * R^-1 mod p. It sits on the latency path of
 // every sumcheck round (one lane per value reduces the block's column sums), so it is three Montgomery products on
 // the fast IMAD.WIDE rows instead of a word-serial 64-bit loop: with acc = lo + hi R + top R^2 (R = 2^256),

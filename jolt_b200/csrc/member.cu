@@ -390,11 +390,99 @@ int jb_round_evals_from_kernel_values(int m, int skip_t1, const uint64_t* kernel
     return assemble_evals(nullptr, m, skip_t1 != 0, kernel_values, claim_or_null, 0, out_evals);
 }
 
-// ---- resident service of one member ------------------------------------------------------------------
-// Serves this round from the member's resident kernel (starting one if the member is eligible). Returns
-// JB_ERR_UNSUPPORTED if the member is not (or no longer) served by a run: the caller launches instead.
-// vals: K canonical values (or, with `exchange`, K x 8 lanes).
-static int resident_member_round(jb_member* mem, unsigned action, const uint64_t* bind, bool exchange, uint64_t* vals) {
+// ---- rounds served by a resident kernel -----------------------------------------------------------------
+// K canonical kernel values (s(0), [s(2..D-1)], s(inf)) of one member from an answer's lanes.
+static void answer_values(const jb_member* mem, const ResConsumed& info, const uint64_t* lanes, uint64_t* vals) {
+    if (info.thin) {  // s(0) = S0 + S6, s(inf) = S2 + S7: add the integer lanes, reduce once each
+        uint64_t sum[2 * 17];
+        for (int w = 0; w < 17; ++w) {
+            sum[w] = lanes[0 * 17 + w] + lanes[6 * 17 + w];
+            sum[17 + w] = lanes[2 * 17 + w] + lanes[7 * 17 + w];
+        }
+        jb_wide_lanes_reduce_host(sum, 2, vals);
+    } else {
+        resident_values(mem->m, lanes, vals);
+    }
+}
+
+// A thin answer also determines the NEXT round's polynomial as a function of the challenge that round binds.
+static void harvest_lookahead(jb_member* mem, const ResConsumed& info, const uint64_t* lanes) {
+    if ((info.act == RES_ACT_EVAL || info.act == RES_ACT_BIND_EVAL) && info.thin && info.nprime >= 4 && mem->ctx->lookahead) {
+        jb_wide_lanes_reduce_host(lanes, 6, mem->look);
+        mem->look_ok = true;
+        mem->look_round = info.round + 1;
+    } else if (info.act != RES_ACT_NONE) {
+        mem->look_ok = false;
+    }
+}
+
+// s(0)(r) = S0 + r (S1 - S0 - S2) + r^2 S2 and s(inf)(r) = S3 + r (S4 - S3 - S5) + r^2 S5 at the drawn challenge
+static void lookahead_values(const jb_member* mem, const uint64_t* r_limbs, uint64_t* vals) {
+    const HostFr r = HostFr::from_limbs(r_limbs);
+    for (int h = 0; h < 2; ++h) {
+        const HostFr a0 = HostFr::from_limbs(mem->look + (3 * h) * 4), a1 = HostFr::from_limbs(mem->look + (3 * h + 1) * 4),
+                     lead = HostFr::from_limbs(mem->look + (3 * h + 2) * 4);
+        ((lead * r + (a1 - a0 - lead)) * r + a0).store(vals + 4 * h);
+    }
+}
+
+struct RunItem {
+    jb_member* mem;
+    const uint64_t* bind;   // null on the member's first round
+    const uint64_t* claim;  // the running claim (s(1) = claim - s(0))
+    size_t round;
+    uint64_t* out_evals;
+};
+
+// One round of `n` members of one run: ONE mailbox command. Members whose previous answer carried lookahead sums
+// are answered at once from those (their command stays in flight: the device's bind + next sums overlap the
+// caller's Fiat-Shamir step); the others wait for this command's own answer.
+static int run_round(jb_ctx* c, ResidentRun* run, RunItem* items, int n, const uint64_t* shared_bind, bool exchange) {
+    unsigned actions[RES_MAX_MEMBERS] = {0};
+    for (int i = 0; i < n; ++i) actions[items[i].mem->run_idx] = items[i].bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL;
+    jb_member* mems[RES_MAX_MEMBERS];
+    const int rn = run->n;
+    for (int i = 0; i < rn; ++i) mems[i] = run->mem[i];
+    int st = resident_post(run, actions, shared_bind, exchange);
+    if (st != JB_OK) return st;
+    uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
+    ResConsumed info[RES_MAX_MEMBERS];
+    while (resident_inflight(run) > 1) {  // the previous command's answer: it carries this round's lookahead
+        st = resident_consume(run, out, info);
+        if (st != JB_OK) return st;
+        for (int i = 0; i < rn; ++i) harvest_lookahead(mems[i], info[i], out + (size_t)i * RES_SLOT_U64);
+    }
+    uint64_t vals[RES_MAX_MEMBERS][JB_MAX_EVALS * 4];
+    bool hit[RES_MAX_MEMBERS], need_now = false;
+    for (int i = 0; i < n; ++i) {
+        jb_member* m = items[i].mem;
+        hit[i] = c->lookahead && items[i].bind && m->look_ok && m->look_round == items[i].round && m->m == 2;
+        if (hit[i]) lookahead_values(m, items[i].bind, vals[i]);
+        else need_now = true;
+    }
+    if (need_now) {
+        st = resident_consume(run, out, info);  // (cannot release the run: the members of this round are not fully bound)
+        if (st != JB_OK) return st;
+        for (int i = 0; i < n; ++i)
+            if (!hit[i]) {
+                const int idx = items[i].mem->run_idx;
+                answer_values(items[i].mem, info[idx], out + (size_t)idx * RES_SLOT_U64, vals[i]);
+            }
+        for (int i = 0; i < rn; ++i) harvest_lookahead(mems[i], info[i], out + (size_t)i * RES_SLOT_U64);
+    }
+    for (int i = 0; i < n; ++i) {
+        jb_member* m = items[i].mem;
+        st = assemble_evals(c, m->m, true, vals[i], items[i].claim, items[i].round, items[i].out_evals);
+        if (st != JB_OK) return st;
+        m->rounds_done++;
+    }
+    return JB_OK;
+}
+
+// This round of one member through its resident kernel (starting one if the member is eligible). Returns
+// JB_ERR_UNSUPPORTED if the member is not served by a run: the caller launches instead.
+static int resident_member_prove(jb_member* mem, const uint64_t* bind, const uint64_t* claim, size_t round, bool exchange,
+                                 uint64_t* out_evals) {
     jb_ctx* c = mem->ctx;
     if (!mem->run) {
         if (!resident_eligible(mem)) return JB_ERR_UNSUPPORTED;
@@ -402,18 +490,19 @@ static int resident_member_round(jb_member* mem, unsigned action, const uint64_t
         int st = resident_begin(c, one, 1);
         if (st != JB_OK) return st;
     }
-    ResidentRun* run = mem->run;
-    const int idx = mem->run_idx;
+    RunItem it{mem, bind, claim, round, out_evals};
+    int st = run_round(c, mem->run, &it, 1, bind, exchange);
+    if (st != JB_OK && mem->run) resident_end(mem->run, true);
+    return st;
+}
+
+// The terminal bind of one member through its run (the run is released when every member is fully bound).
+static int resident_member_final(jb_member* mem, const uint64_t* bind) {
     unsigned actions[RES_MAX_MEMBERS] = {0};
-    actions[idx] = action;
-    uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
-    int st = resident_round(run, actions, bind, exchange, out);  // may release the run (member fully bound)
-    if (st != JB_OK) {
-        if (mem->run) resident_end(mem->run, true);
-        return st;
-    }
-    if (vals) std::memcpy(vals, out + (size_t)idx * RES_SLOT_U64, RES_SLOT_U64 * 8);
-    return JB_OK;
+    actions[mem->run_idx] = RES_ACT_FINAL;
+    int st = resident_round(mem->run, actions, bind, false, nullptr);
+    if (st != JB_OK && mem->run) resident_end(mem->run, true);
+    return st;
 }
 
 // Stops whatever resident kernel would be in the way of a launch for this member.
@@ -452,14 +541,7 @@ int jb_member_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     int st;
     if (skip1) {
         // the resident kernel serves this and every later round of the member: no launch per round
-        uint64_t lanes[RES_SLOT_U64], vals[JB_MAX_EVALS * 4];
-        st = resident_member_round(mem, bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL, bind, false, lanes);
-        if (st == JB_OK) {
-            resident_values(mem->m, lanes, vals);
-            st = assemble_evals(c, mem->m, true, vals, claim, round, out_evals);
-            if (st == JB_OK) mem->rounds_done++;
-            return st;
-        }
+        st = resident_member_prove(mem, bind, claim, round, false, out_evals);  // (counts the round itself)
         if (st != JB_ERR_UNSUPPORTED) return st;
     }
     before_launch(mem);
@@ -647,13 +729,12 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
                 const bool skip1 = claim != nullptr && !c->verify_rounds;
                 const int K = skip1 ? mem->m : mem->m + 1;
                 int st = JB_ERR_UNSUPPORTED;
-                uint64_t lanes[RES_SLOT_U64];
-                const uint64_t* lanes_host = lanes;
                 if (skip1 && c->xch_ready) {
                     // resident kernel: the all-reduce over NVLink peer memory rides in the round's own epilogue,
                     // no launch and no NCCL call per round
-                    st = resident_member_round(mem, bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL, bind, true, lanes);
-                    if (st != JB_OK && st != JB_ERR_UNSUPPORTED) return st;
+                    st = resident_member_prove(mem, bind, claim, round, true, out_evals);
+                    if (st == JB_OK) mem->rounds_done--;  // (the caller counts sharded rounds)
+                    if (st != JB_ERR_UNSUPPORTED) return st;
                 }
                 if (st == JB_ERR_UNSUPPORTED) {
                     before_launch(mem);
@@ -668,10 +749,9 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
                     if (st != JB_OK) return st;
                     if (c->h_result[0] == ~0ull && c->h_result[1] == ~0ull)
                         return c->fail(JB_ERR_CUDA, "peer exchange timed out (a rank did not arrive)");
-                    lanes_host = c->h_result;
                 }
                 uint64_t vals[JB_MAX_EVALS * 4];
-                st = lanes_host == lanes ? resident_values(mem->m, lanes, vals) : jb_lanes_reduce_host(lanes_host, (size_t)K, vals);
+                st = jb_lanes_reduce_host(c->h_result, (size_t)K, vals);
                 if (st != JB_OK) return st;
                 return assemble_evals(c, mem->m, skip1, vals, claim, round, out_evals);
             }
@@ -847,8 +927,7 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     if (mem->run) {
         // the terminal bind is one more mailbox command; a fully bound member gets its values back with the
         // acknowledgement (has_final), so nothing is read from the device afterwards
-        int st = resident_member_round(mem, RES_ACT_FINAL, bind, false, nullptr);
-        if (st != JB_ERR_UNSUPPORTED) return st;
+        return resident_member_final(mem, bind);
     }
     before_launch(mem);
     for (int j = 0; j < mem->ntables(); ++j) {
@@ -1007,23 +1086,13 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
         }
         for (size_t i = 0; ok && i < n_work; ++i) ok = s->members[work[i].member]->run == run;
         if (ok && run) {
-            unsigned actions[RES_MAX_MEMBERS] = {0};
+            RunItem items[RES_MAX_MEMBERS];
             for (size_t i = 0; i < n_work; ++i)
-                actions[s->members[work[i].member]->run_idx] = work[i].has_bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL;
-            int idx_of[RES_MAX_MEMBERS];
-            for (size_t i = 0; i < n_work; ++i) idx_of[i] = s->members[work[i].member]->run_idx;
-            uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
-            int st = resident_round(run, actions, shared_bind, false, out);
-            if (st != JB_OK) return st;
-            for (size_t i = 0; i < n_work; ++i) {
-                jb_member* m = s->members[work[i].member];
-                uint64_t vals[JB_MAX_EVALS * 4];
-                resident_values(m->m, out + (size_t)idx_of[i] * RES_SLOT_U64, vals);
-                st = assemble_evals(c, m->m, true, vals, work[i].claim, work[i].round, out_evals + i * JB_MAX_EVALS * 4);
-                if (st != JB_OK) return st;
-                m->rounds_done++;
-            }
-            return JB_OK;
+                items[i] = RunItem{s->members[work[i].member], work[i].has_bind ? work[i].bind : nullptr, work[i].claim,
+                                   work[i].round, out_evals + i * JB_MAX_EVALS * 4};
+            int st = run_round(c, run, items, (int)n_work, shared_bind, false);
+            if (st != JB_OK && s->members[work[0].member]->run) resident_end(s->members[work[0].member]->run, true);
+            return st;
         }
         s->run_failed = true;
     }
@@ -1052,14 +1121,17 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
             // short member: its own small resident kernel (a few blocks), one mailbox command
             if (!m->run) {
                 jb_member* one[1] = {m};
-                int st = resident_begin(c, one, 1, len_after / 2, false);
+                int st = resident_begin(c, one, 1, len_after, false);
                 if (st != JB_OK && st != JB_ERR_UNSUPPORTED) return st;
             }
             if (m->run && resident_run_size(m->run) == 1) {
                 unsigned actions[RES_MAX_MEMBERS] = {0};
                 actions[m->run_idx] = bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL;
-                int st = resident_post(m->run, actions, bind, false);
+                int st = JB_OK;
+                while (st == JB_OK && resident_inflight(m->run) > 0) st = resident_consume(m->run, nullptr, nullptr);
+                if (st == JB_OK) st = resident_post(m->run, actions, bind, false);
                 if (st != JB_OK) return st;
+                m->look_ok = false;
                 via[i] = VIA_RUN;
                 continue;
             }
@@ -1075,10 +1147,11 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
         int st;
         if (via[i] == VIA_RUN) {
             uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
-            st = resident_wait(m->run, out);
+            ResConsumed info[RES_MAX_MEMBERS];
+            st = resident_consume(m->run, out, info);
             if (st == JB_OK) {
                 uint64_t vals[JB_MAX_EVALS * 4];
-                resident_values(m->m, out, vals);
+                answer_values(m, info[0], out, vals);
                 st = assemble_evals(c, m->m, true, vals, w.claim, w.round, out_evals + i * JB_MAX_EVALS * 4);
             }
         } else {

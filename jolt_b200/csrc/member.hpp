@@ -7,6 +7,7 @@
 #include "ctx.hpp"
 #include "host_fr.hpp"
 #include "poly_kernels.cuh"
+#include "resident.cuh"
 
 namespace jbi {
 
@@ -82,6 +83,11 @@ struct jb_member {
     bool no_resident = false;  // a run of this member was stopped to make room for other work: stay on launches
     bool has_final = false;
     uint64_t final_vals[jb::JB_MAX_TABLES * 4];
+    // lookahead (thin rounds, resident.cuh): the sums S0..S5 that determine round `look_round`'s polynomial as a
+    // function of the challenge that round binds - harvested from the answer to the previous round's command
+    bool look_ok = false;
+    size_t look_round = 0;
+    uint64_t look[6 * 4];
     int ntables() const { return m * terms; }
 };
 
@@ -89,16 +95,44 @@ struct jb_member {
 // Starts a resident kernel serving `n` members (same D, P, order, same context; n <= RES_MAX_MEMBERS). Members
 // must be plain (not eq / sharded-with-tail). `exchange`: the kernel may be asked to all-reduce member 0's sums
 // over peer memory (sharded rounds). JB_ERR_UNSUPPORTED = not eligible (caller falls back to launches).
-// first_items: the largest pass the run will be asked for (0 = derive from the tables: len / 2); may_evict: stop
-// other runs of the context if the device cannot hold this one next to them (false: JB_ERR_UNSUPPORTED instead).
-int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_items = 0, bool may_evict = true);
-// One round for the whole run. actions[i] in RES_ACT_*; challenge may be null when no action binds. `out`
-// (may be null) receives n x RES_SLOT_U64 mailbox words: per member K canonical values (4 u64 each), or - with
-// `exchange` - member 0's K x 8 all-reduced u64 lanes. Host-side table state (len, ping-pong) is advanced and the
-// run is released when every member is fully bound (the run pointer is dead after that: check mem->run).
-// post + wait may be split to overlap several runs / launches.
+// first_len: entries of the largest pass a single-member run will be asked for (0 = the member's current length);
+// may_evict: stop other runs of the context if the device cannot hold this one next to them (false:
+// JB_ERR_UNSUPPORTED instead).
+int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_len = 0, bool may_evict = true);
+// What a consumed command had asked of member i of the run.
+struct ResConsumed {
+    unsigned act = 0;       // RES_ACT_*
+    bool thin = false;      // the answer carries the 8 thin sums (x 17 lanes) instead of K sums
+    size_t round = 0;       // member-local round the command proved
+    uint64_t nprime = 0;    // entries of the tables the round swept (after its bind)
+};
+// One launched resident_rounds_kernel and the members it serves.
+struct ResidentRun {
+    jb_ctx* c = nullptr;
+    TailRes res;
+    jb::ResMailbox* mb = nullptr;  // host view of the mailbox
+    uint64_t seq = 0;          // commands posted
+    uint64_t consumed = 0;     // answers consumed (<= seq <= consumed + 2: the mailbox is a ring of two)
+    int n = 0;
+    jb_member* mem[jb::RES_MAX_MEMBERS] = {nullptr};
+    unsigned grid = 0;
+    ResConsumed ring[2][jb::RES_MAX_MEMBERS];  // what command s (slot s & 1) asked of every member
+    struct RoundInfo { int kind; uint64_t items; int m; };
+    RoundInfo info[64];                       // what command s (< 64) asked for, for the device-timed pass log
+    uint64_t host_post[64], host_recv[64];    // CLOCK_MONOTONIC ns (diagnostics)
+    bool kernel_live = false;
+    bool exclusive = false;  // holds more than half of the device's block slots: other kernels may starve
+};
+
+// The mailbox is a ring of two commands. post: actions[i] in RES_ACT_* (challenge may be null when no action binds);
+// the host's view of the tables (len, ping-pong) advances at once - the device executes commands in order.
+// consume: waits for the OLDEST unanswered command; `out` (may be null) receives n x RES_SLOT_U64 mailbox words per
+// member (lanes, see resident.cuh; with `exchange` member 0's lanes are all-reduced over the ranks), `info` what
+// the command had asked. The run is released when every member is fully bound and nothing is in flight (the run
+// pointer is dead after that: check mem->run). round = drain + post + consume.
 int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange);
-int resident_wait(ResidentRun* run, uint64_t* out);
+int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info);
+int resident_inflight(const ResidentRun* run);
 int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out);
 int resident_run_size(const ResidentRun* run);
 // Stops the kernel (if it still runs), orders the context's stream after it and detaches the members.

@@ -127,7 +127,7 @@ struct RoundOut {
     uint64_t xseq;
     long long timeout_cycles;
 };
-constexpr int XCH_SLOT_U64 = 72;                 // u64 lanes per (parity, source) slot (4 values x 17 lanes fit)
+constexpr int XCH_SLOT_U64 = 136;                // u64 lanes per (parity, source) slot (a thin round: 8 sums x 17 lanes)
 constexpr int XCH_FLAG_BASE = 2 * 16 * XCH_SLOT_U64;  // flags[parity][source] follow the slots
 constexpr size_t XCH_BYTES = (size_t)(XCH_FLAG_BASE + 2 * 16) * 8;
 

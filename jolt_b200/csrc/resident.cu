@@ -14,22 +14,6 @@
 using namespace jb;
 using namespace jbi;
 
-struct ResidentRun {
-    jb_ctx* c = nullptr;
-    TailRes res;
-    ResMailbox* mb = nullptr;  // host view of the mailbox
-    uint64_t seq = 0;
-    int n = 0;
-    jb_member* mem[RES_MAX_MEMBERS] = {nullptr};
-    unsigned grid = 0;
-    unsigned pending[RES_MAX_MEMBERS] = {0};  // actions of the command in flight
-    struct RoundInfo { int kind; uint64_t items; int m; };
-    RoundInfo info[64];                       // what command s (< 64) asked for, for the device-timed pass log
-    uint64_t host_post[64], host_recv[64];    // CLOCK_MONOTONIC ns (diagnostics)
-    bool kernel_live = false;
-    bool exclusive = false;  // holds more than half of the device's block slots: other kernels may starve
-};
-
 namespace {
 
 using ResKernel = void (*)(const ResArgs);
@@ -102,10 +86,11 @@ int wait_answer(ResidentRun* run, uint64_t seq) {
     jb_ctx* c = run->c;
     ResMailbox* mb = run->mb;
     uint64_t spins = 0;
-    while (__atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+    volatile uint64_t* flag = &mb->ans[seq & 1].res_seq;
+    while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) != seq) {
         if ((++spins & 0x3fffff) == 0) {
             cudaError_t e = cudaStreamQuery(run->res.stream);
-            if (e != cudaErrorNotReady && __atomic_load_n(&mb->res_seq, __ATOMIC_ACQUIRE) != seq) {
+            if (e != cudaErrorNotReady && __atomic_load_n(flag, __ATOMIC_ACQUIRE) != seq) {
                 run->kernel_live = false;
                 return c->check(e == cudaSuccess ? cudaErrorUnknown : e, "resident kernel exited without answering");
             }
@@ -185,22 +170,24 @@ void jb_ctx::quiesce_resident(bool all) {
         if (all || r->exclusive) resident_end(r, true);
 }
 
-int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_items, bool may_evict) {
+int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_len, bool may_evict) {
     if (n < 1 || n > RES_MAX_MEMBERS) return JB_ERR_UNSUPPORTED;
     const int D = mems[0]->m, P = mems[0]->terms, order = mems[0]->order, T = D * P;
-    uint64_t max_items = 1;
     for (int i = 0; i < n; ++i) {
         jb_member* m = mems[i];
         if (m->ctx != c || m->m != D || m->terms != P || m->order != order || !resident_eligible(m)) return JB_ERR_UNSUPPORTED;
-        max_items = std::max<uint64_t>(max_items, m->len / 2);
     }
-    if (first_items) max_items = first_items;  // the caller knows the largest pass it will ever ask for
     size_t smem = 0;
     ResKernel kernel = pick_kernel(D, P, order, &smem);
     if (!kernel) return JB_ERR_UNSUPPORTED;
     const int per_sm = kernel_blocks_per_sm(kernel, smem);
     const unsigned cap = (unsigned)(c->sm_count * per_sm);
-    const unsigned grid = res_blocks_for(max_items, cap);
+    unsigned grid = 1;
+    for (int i = 0; i < n; ++i) {
+        // the largest pass member i can ask for: over first_len entries if the caller knows its first round binds
+        const uint64_t len0 = (first_len && n == 1) ? first_len : mems[i]->len;
+        grid = std::max(grid, res_need_blocks(D, P, len0, cap));
+    }
     const bool exclusive = grid > (unsigned)c->sm_count;
     // co-residency budget: small runs may share the device, a big one needs it alone
     unsigned in_use = 0;
@@ -270,69 +257,80 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_items, boo
     return JB_OK;
 }
 
+int resident_inflight(const ResidentRun* run) { return run ? (int)(run->seq - run->consumed) : 0; }
+
 int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange) {
     jb_ctx* c = run->c;
     if (!run->kernel_live) return c->fail(JB_ERR_INVALID, "resident run is not live");
+    if (run->seq - run->consumed >= 2) return c->fail(JB_ERR_INVALID, "resident run: two commands already in flight");
+    const uint64_t seq = run->seq + 1;
     ResMailbox* mb = run->mb;
+    ResCmdLine* line = &mb->cmd[seq & 1];
     uint64_t cmd = RES_OP_ROUND;
     if (exchange) {
         cmd |= RES_FLAG_EXCHANGE;
-        mb->xseq = ++c->xch_seq;
+        line->xseq = ++c->xch_seq;
     }
-    for (int i = 0; i < run->n; ++i) {
-        run->pending[i] = actions[i] & 0xf;
-        cmd |= (uint64_t)run->pending[i] << (16 + 4 * i);
-    }
-    mb->cmd = cmd;
-    if (challenge) std::memcpy((void*)mb->challenge, challenge, 32);
-    const uint64_t seq = ++run->seq;
-    if (seq <= 64) {
-        ResidentRun::RoundInfo& ri = run->info[seq - 1];
-        ri.kind = -1;
-        ri.items = 0;
-        ri.m = 0;
-        for (int i = 0; i < run->n; ++i) {
-            const unsigned a = run->pending[i];
-            if (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) {
-                ri.kind = (a == RES_ACT_BIND_EVAL || ri.kind == 0) ? 0 : 2;
-                ri.items += (a == RES_ACT_BIND_EVAL ? run->mem[i]->len / 2 : run->mem[i]->len) / 2;
-                ri.m = run->mem[i]->ntables();
-            }
-        }
-    }
-    if (seq <= 64) run->host_post[seq - 1] = now_ns();
-    __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
-    return JB_OK;
-}
-
-int resident_wait(ResidentRun* run, uint64_t* out) {
-    jb_ctx* c = run->c;
-    WaitAcc acc(c);
-    ResMailbox* mb = run->mb;
-    int st = wait_answer(run, run->seq);
-    if (st != JB_OK) return st;
-    if (run->seq <= 64) run->host_recv[run->seq - 1] = now_ns();
-    if (mb->status != 0) {
-        run->kernel_live = false;
-        return c->fail(JB_ERR_CUDA, mb->status == 2 ? "peer exchange timed out (a rank did not arrive)"
-                                                    : "resident kernel aborted (timeout)");
-    }
-    if (out) std::memcpy(out, (const void*)mb->result, (size_t)run->n * RES_SLOT_U64 * 8);
-    // mirror the device's table state on the host: the member's tables are consistent at every round boundary
-    bool all_done = true;
+    ResConsumed* slot = run->ring[seq & 1];
+    ResidentRun::RoundInfo ri{-1, 0, 0};
     for (int i = 0; i < run->n; ++i) {
         jb_member* m = run->mem[i];
-        const unsigned a = run->pending[i];
+        const unsigned a = actions[i] & 0xf;
+        cmd |= (uint64_t)a << (16 + 4 * i);
+        slot[i].act = a;
+        slot[i].round = m->rounds_done;
+        slot[i].nprime = a == RES_ACT_BIND_EVAL ? m->len / 2 : m->len;
+        slot[i].thin = (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) && res_is_thin(m->m, slot[i].nprime);
+        if (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) {
+            ri.kind = (a == RES_ACT_BIND_EVAL || ri.kind == 0) ? 0 : 2;
+            ri.items += slot[i].nprime / 2;
+            ri.m = m->ntables();
+        }
+        // the host's view of the tables follows the command stream: the device executes commands in order
         if (a == RES_ACT_BIND_EVAL || a == RES_ACT_FINAL) {
             m->len /= 2;
             for (auto& t : m->tables) {
                 if (m->order == JB_LOW_TO_HIGH) t.swap_buffers();
                 t.len = m->len;
             }
-            if (a == RES_ACT_FINAL && m->len == 1) {
-                std::memcpy(m->final_vals, (const void*)(mb->result + (size_t)i * RES_SLOT_U64), (size_t)m->ntables() * 32);
-                m->has_final = true;
-            }
+        }
+    }
+    line->cmd = cmd;
+    if (challenge) std::memcpy((void*)line->challenge, challenge, 32);
+    run->seq = seq;
+    if (seq <= 64) {
+        run->info[seq - 1] = ri;
+        run->host_post[seq - 1] = now_ns();
+    }
+    __atomic_store_n(&line->cmd_seq, seq, __ATOMIC_RELEASE);
+    return JB_OK;
+}
+
+int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info) {
+    jb_ctx* c = run->c;
+    if (run->consumed >= run->seq) return c->fail(JB_ERR_INVALID, "resident run: no command in flight");
+    WaitAcc acc(c);
+    const uint64_t seq = run->consumed + 1;
+    ResMailbox* mb = run->mb;
+    int st = wait_answer(run, seq);
+    if (st != JB_OK) return st;
+    if (seq <= 64) run->host_recv[seq - 1] = now_ns();
+    if (mb->ans[seq & 1].status != 0) {
+        run->kernel_live = false;
+        return c->fail(JB_ERR_CUDA, mb->ans[seq & 1].status == 2 ? "peer exchange timed out (a rank did not arrive)"
+                                                                 : "resident kernel aborted (timeout)");
+    }
+    run->consumed = seq;
+    const uint64_t* result = mb->result[seq & 1];
+    if (out) std::memcpy(out, (const void*)result, (size_t)run->n * RES_SLOT_U64 * 8);
+    const ResConsumed* slot = run->ring[seq & 1];
+    if (info) std::memcpy(info, slot, sizeof(ResConsumed) * run->n);
+    bool all_done = run->consumed == run->seq;
+    for (int i = 0; i < run->n; ++i) {
+        jb_member* m = run->mem[i];
+        if (slot[i].act == RES_ACT_FINAL && slot[i].nprime == 2) {  // the member is fully bound: its values came along
+            std::memcpy(m->final_vals, (const void*)(result + (size_t)i * RES_SLOT_U64), (size_t)m->ntables() * 32);
+            m->has_final = true;
         }
         if (m->len >= 2) all_done = false;
     }
@@ -344,18 +342,34 @@ int resident_wait(ResidentRun* run, uint64_t* out) {
 }
 
 int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out) {
-    int st = resident_post(run, actions, challenge, exchange);
+    int st = JB_OK;
+    while (st == JB_OK && run->consumed < run->seq) st = resident_consume(run, nullptr, nullptr);  // (never releases: a
+    if (st != JB_OK) return st;                                                                     //  round is still to come)
+    st = resident_post(run, actions, challenge, exchange);
     if (st != JB_OK) return st;
-    return resident_wait(run, out);
+    return resident_consume(run, out, nullptr);
 }
 
 void resident_end(ResidentRun* run, bool mark_no_resident) {
     if (!run) return;
+    // answers still on their way belong to commands the host's view of the tables already includes: take them first
+    while (run->kernel_live && run->consumed < run->seq) {
+        jb_ctx* c = run->c;
+        const bool last = run->consumed + 1 == run->seq;
+        bool done = last;
+        for (int i = 0; i < run->n && done; ++i) done = run->mem[i]->len < 2;
+        if (resident_consume(run, nullptr, nullptr) != JB_OK) break;
+        if (done) {  // that consume released the run (every member fully bound)
+            (void)c;
+            return;
+        }
+    }
     if (run->kernel_live) {
         ResMailbox* mb = run->mb;
-        mb->cmd = RES_OP_ABORT;
-        const uint64_t seq = ++run->seq;
-        __atomic_store_n(&mb->cmd_seq, seq, __ATOMIC_RELEASE);
+        const uint64_t seq = run->seq + 1;
+        mb->cmd[seq & 1].cmd = RES_OP_ABORT;
+        run->seq = seq;
+        __atomic_store_n(&mb->cmd[seq & 1].cmd_seq, seq, __ATOMIC_RELEASE);
         wait_answer(run, seq);
         run->kernel_live = false;
     }

@@ -39,31 +39,40 @@ namespace jb {
 constexpr int RES_MAX_MEMBERS = 8;
 constexpr int RES_BLOCK = 256;
 constexpr size_t RES_SMALL_LEN = 8192;  // tables this short need few blocks: such runs coexist with other work
-// mailbox / accumulator words per member: K <= 4 values x 17 lanes (products) or x 8 lanes (D = 1), or T finals x 4
-constexpr int RES_SLOT_U64 = 72;
+// Degree-2 rounds with at most this many pair indices run as THIN passes (thin_pass below): latency-shaped, and
+// they also return the lookahead sums that let the host answer the NEXT round without waiting for the device.
+constexpr uint64_t RES_THIN_PAIRS = 1ull << 16;
+// mailbox / accumulator words per member: a thin round returns 8 sums x 17 lanes; a generic round K <= 4 values
+// x 17 lanes (products) or x 8 lanes (D = 1); a terminal bind the T final values x 4 limbs
+constexpr int RES_SLOT_U64 = 136;
 
 // per-member action of a round command (4 bits each, member i at bits [16 + 4i, 20 + 4i) of cmd)
 enum : unsigned { RES_ACT_NONE = 0, RES_ACT_EVAL = 1, RES_ACT_BIND_EVAL = 2, RES_ACT_FINAL = 3 };
 enum : uint64_t { RES_OP_ROUND = 1, RES_OP_ABORT = 2 };
 constexpr uint64_t RES_FLAG_EXCHANGE = 1ull << 8;  // member 0's sums are all-reduced over peer memory
 
-struct alignas(64) ResMailbox {
-    // line 0 (64 B), host -> device. The host writes the payload first and cmd_seq last; the device reads the
-    // whole line with ONE coalesced 64-byte request, so a snapshot that shows the new sequence number also
-    // shows its payload.
+// The mailbox is a ring of TWO commands / answers (command s uses slot s & 1): with lookahead the host posts
+// command s + 1 while the answer to command s is still on its way.
+struct alignas(64) ResCmdLine {
+    // 64 B, host -> device. The host writes the payload first and cmd_seq last; the device reads the whole line
+    // with ONE coalesced 64-byte request, so a snapshot that shows the new sequence number also shows its payload.
     volatile uint64_t cmd_seq;
     uint64_t cmd;           // RES_OP_* | flags | actions << 16
     uint64_t challenge[4];  // Montgomery limbs of the bind scalar (shared by every member of the batch round)
     uint64_t xseq;          // exchange sequence number (RES_FLAG_EXCHANGE)
     uint64_t pad0;
-    // line 1, device -> host
+};
+struct alignas(64) ResAnswerLine {
     volatile uint64_t res_seq;
     uint64_t status;  // 0 ok, 1 aborted / timed out, 2 exchange timed out
     uint64_t pad1[6];
-    // per member: the round's K sums as lanes - value e at [e * 17, e * 17 + 17) (D >= 2: 32-bit limb column sums
-    // of the unreduced 544-bit accumulators) or [e * 8, e * 8 + 8) (D = 1: limb sums of canonical values) - or,
-    // after a terminal bind that left the member fully bound, its T final values (4 limbs each)
-    uint64_t result[RES_MAX_MEMBERS * RES_SLOT_U64];
+};
+struct alignas(64) ResMailbox {
+    ResCmdLine cmd[2];
+    ResAnswerLine ans[2];
+    // per answer, per member: the round's sums as lanes (32-bit limb column sums, see resident_pass / thin_pass),
+    // or - after a terminal bind that left the member fully bound - its T final values (4 limbs each)
+    uint64_t result[2][RES_MAX_MEMBERS * RES_SLOT_U64];
     // observability (specs/clean-slate-prover.md:585-587): %globaltimer (ns) when block 0 decoded command s and
     // when the last block had collected the round's sums, at [2 (s - 1 mod 64)] and [.. + 1]
     uint64_t tlog[2 * 64];
@@ -79,6 +88,11 @@ struct alignas(128) ResState {
     uint64_t pad[8];
     unsigned int ticket;
     unsigned int pad2[31];
+    // sequence number of the last round whose sums have been collected (lanes zeroed, ticket reset). With two
+    // commands in flight block 0 may SEE command s + 1 before round s is complete: it re-publishes it only after
+    // done == s, so no block can miss (or tear) a command and no RED of round s + 1 lands in round s's lanes.
+    uint64_t done;
+    uint64_t pad3[15];
     uint64_t lanes[RES_MAX_MEMBERS * RES_SLOT_U64];  // zero between rounds
 };
 
@@ -168,16 +182,134 @@ __device__ __noinline__ void resident_pass(const TablePtrs tp, size_t pairs, con
     }
 }
 
+// ---- thin pass (degree 2): short rounds are pure latency, and they come with lookahead ------------------------
+// T' = the tables of this round (after the pending bind, if any), n' entries each. The next bind will pair T'
+// entries again, so T' is walked in QUADS: (a, b) is the pair that the next challenge r folds into the next round's
+// lo, (c, d) the pair it folds into hi:   lo(r) = a + r (b - a),   hi(r) = c + r (d - c).
+//   LowToHigh : a, b, c, d = T'[4q .. 4q + 3]
+//   HighToLow : a = T'[q], b = T'[q + n'/2], c = T'[q + n'/4], d = T'[q + 3n'/4]
+// For every quad q and term k, EIGHT lanes - one per warp of the block, lane g of warp p serves group g - each
+// produce ONE of the 8 bound values (table j = p / 4, position p % 4: one load pair + one bind product), exchange
+// them through shared memory, and each accumulate ONE product of the pair (x, x') = (table 0, table 1):
+//   S0 = a a'          S1 = b b'           S2 = (b - a)(b' - a')
+//   S3 = (c - a)(..)'  S4 = (d - b)(..)'   S5 = (d - c - b + a)(..)'     S6 = c c'      S7 = (d - c)(d' - c')
+// so the longest dependent chain of a round is one bind and one product instead of four binds and two products.
+// This round's polynomial is  s(0) = S0 + S6,  s(inf) = S2 + S7.  And the NEXT round's polynomial, as a function
+// of the not yet known challenge r, is determined by S0..S5:
+//   s_next(0)(r)   = sum lo lo'  = S0 + r (S1 - S0 - S2) + r^2 S2
+//   s_next(inf)(r) = sum (hi - lo)(hi' - lo') = S3 + r (S4 - S3 - S5) + r^2 S5
+// - the host evaluates these the moment it has drawn r, posts r, and does NOT wait for the device: the device's
+// bind + sums for round k + 1 overlap the host's Fiat-Shamir step of round k (the answers trail one command behind).
+// Each warp's 17-word accumulator stays in registers and is summed over the warp with two REDUX per word.
+// n' == 2 (the last round): a and b only; c = d = 0, S6 = S7 = 0.
+template <int P, int ORDER, bool BIND>
+__device__ __noinline__ void thin_pass(const TablePtrs tp, uint64_t nprime, const BindScalar sc, bool hi4, uint32_t* dsm,
+                                       unsigned b, unsigned nblk, uint64_t* g_lanes, uint64_t* s_dst) {
+    const int tid = threadIdx.x, g = tid & 31, p = tid >> 5;
+    uint32_t* sval = dsm;  // [8 values][8 words][32 groups]
+    const uint64_t quads = nprime >= 4 ? nprime / 4 : 1;
+    const uint64_t ngroups = quads * P;
+    const int j = p >> 2, pos = p & 3;
+    uint32_t A[17];
+#pragma unroll
+    for (int w = 0; w < 17; ++w) A[w] = 0;
+    for (uint64_t base = (uint64_t)b * 32; base < ngroups; base += (uint64_t)nblk * 32) {
+        const uint64_t grp = base + g;
+        const bool valid = grp < ngroups;
+        const uint64_t q = P == 1 ? grp : grp / P;
+        const int k = P == 1 ? 0 : (int)(grp % P);
+        Fr v = Fr::zero();
+        if (valid && (nprime >= 4 || pos < 2)) {
+            const int t = k * 2 + j;
+            uint64_t ip;
+            if (nprime < 4) ip = (uint64_t)pos;
+            else if (ORDER == ORDER_LOW_TO_HIGH) ip = 4 * q + pos;
+            else ip = q + (uint64_t)(pos & 1) * (nprime / 2) + (uint64_t)(pos >> 1) * (nprime / 4);
+            if (BIND) {
+                const uint64_t* in = tp.in[t];
+                const Fr lo = ld_elem_rw<Fr>(in, ORDER == ORDER_LOW_TO_HIGH ? 2 * ip : ip);
+                const Fr hi = ld_elem_rw<Fr>(in, ORDER == ORDER_LOW_TO_HIGH ? 2 * ip + 1 : ip + nprime);
+                v = hi4 ? bind_pair<true>(lo, hi, sc) : bind_pair<false>(lo, hi, sc);
+                st_elem(tp.out[t], ip, v);
+            } else {
+                v = ld_elem_rw<Fr>(tp.in[t], ip);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sval[(p * 8 + w) * 32 + g] = v.v[w];
+        __syncthreads();
+        if (valid) {
+            Fr x[2];
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const uint32_t* sv = sval + jj * 4 * 8 * 32 + g;
+                auto rd = [&](int ps) {
+                    Fr r;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) r.v[w] = sv[(ps * 8 + w) * 32];
+                    return r;
+                };
+                switch (p) {  // warp-uniform
+                    case 0: x[jj] = rd(0); break;
+                    case 1: x[jj] = rd(1); break;
+                    case 2: x[jj] = fp_sub_lazy(rd(1), rd(0)); break;
+                    case 3: x[jj] = fp_sub_lazy(rd(2), rd(0)); break;
+                    case 4: x[jj] = fp_sub_lazy(rd(3), rd(1)); break;
+                    case 5: x[jj] = fp_sub_lazy(fp_sub(rd(3), rd(2)), fp_sub(rd(1), rd(0))); break;
+                    case 6: x[jj] = rd(2); break;
+                    default: x[jj] = fp_sub_lazy(rd(3), rd(2)); break;
+                }
+            }
+            mul_wide_acc_reg(A, x[0].v, x[1].v);
+        }
+        __syncthreads();
+    }
+    // warp p holds product p: sum each accumulator word over the 32 lanes (16-bit halves: no overflow in REDUX)
+    uint64_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < 17; ++w) {
+        const uint32_t lo = __reduce_add_sync(0xffffffffu, A[w] & 0xffffu);
+        const uint32_t hi = __reduce_add_sync(0xffffffffu, A[w] >> 16);
+        if (g == w) mine = (uint64_t)lo + ((uint64_t)hi << 16);
+    }
+    if (g < 17) {
+        if (s_dst) s_dst[p * 17 + g] = mine;
+        else atomicAdd(reinterpret_cast<unsigned long long*>(g_lanes) + p * 17 + g, (unsigned long long)mine);
+    }
+}
+
+// lanes a member's round leaves in the accumulators / mailbox
+template <int D>
+__host__ __device__ constexpr int res_lanes(bool thin) {
+    return thin ? 8 * 17 : (D == 1 ? 8 : D * 17);
+}
+__host__ __device__ inline bool res_is_thin(int D, uint64_t nprime) { return D == 2 && nprime / 2 <= RES_THIN_PAIRS; }
+// blocks a thin pass over n' entries (P terms) uses out of `cap`
+__host__ __device__ inline unsigned res_thin_blocks(uint64_t nprime, int P, unsigned cap) {
+    const uint64_t ngroups = (nprime >= 4 ? nprime / 4 : 1) * (uint64_t)P;
+    if (ngroups <= 64 || cap <= 1) return 1;
+    const uint64_t want = (ngroups + 31) / 32;
+    return (unsigned)(want < cap ? want : cap);
+}
+// blocks the largest pass a member with `len` entries can still ask for needs (an eval over len entries if it has
+// not started, else a bind + eval over len / 2, or a terminal bind over len / 2 outputs)
+__host__ __device__ inline unsigned res_need_blocks(int D, int P, uint64_t len, unsigned cap) {
+    if (len < 2) return 0;
+    unsigned need = res_is_thin(D, len) ? res_thin_blocks(len, P, cap) : res_blocks_for(len / 2, cap);
+    const unsigned fin = res_blocks_for(len / 2, cap);
+    return need > fin ? need : fin;
+}
+
 template <int D, int P, int ORDER>
 __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __grid_constant__ ResArgs a) {
     constexpr int T = D * P;
     constexpr int K = D;  // s(1) always comes from the running claim (the optimized tier's convention)
-    constexpr int KL = D == 1 ? K * 8 : K * 17;  // lanes per member
     extern __shared__ uint32_t dsm[];
     __shared__ uint64_t s_line[8];
     __shared__ uint64_t* s_cur[RES_MAX_MEMBERS][T];
     __shared__ uint64_t* s_oth[RES_MAX_MEMBERS][T];
     __shared__ uint64_t s_len[RES_MAX_MEMBERS];
+    __shared__ int s_kl[RES_MAX_MEMBERS];  // lanes each member produced this round
     __shared__ unsigned s_live_next;
     __shared__ int s_last;
     __shared__ uint64_t s_lanes[RES_MAX_MEMBERS * RES_SLOT_U64];
@@ -200,7 +332,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
         if (b == 0) {
             if (tid < 32) {
                 const long long t0 = clock64();
-                const volatile uint64_t* line = reinterpret_cast<const volatile uint64_t*>(a.mb);
+                const volatile uint64_t* line = reinterpret_cast<const volatile uint64_t*>(&a.mb->cmd[(seq + 1) & 1]);
                 uint64_t v = 0;
                 bool got = false;
                 while (true) {
@@ -221,6 +353,9 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
 #pragma unroll
                     for (int k = 0; k < 7; ++k) w[k] = __shfl_sync(0xffffffffu, v, k + 1);
                     if (lane == 0) {
+                        const long long t1 = clock64();
+                        while (ld_acquire_gpu(&a.st->done) != seq)  // the previous round is complete
+                            if (clock64() - t1 > a.timeout_cycles) break;
 #pragma unroll
                         for (int k = 0; k < 7; ++k) a.st->cmd[k] = w[k];
                         st_release_gpu(&a.st->seq, seq + 1);
@@ -246,11 +381,12 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
         __syncthreads();
         ++seq;
         const uint64_t cmdw = s_line[1];
+        const uint64_t xseq = s_line[6];
         if ((cmdw & 0xff) != RES_OP_ROUND) {
             if (b == 0 && tid == 0) {
-                a.mb->status = 1;
+                a.mb->ans[seq & 1].status = 1;
                 __threadfence_system();
-                a.mb->res_seq = seq;
+                a.mb->ans[seq & 1].res_seq = seq;
             }
             return;
         }
@@ -287,7 +423,28 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 continue;
             }
             const bool bind = act == RES_ACT_BIND_EVAL;
-            const uint64_t pairs = (bind ? len / 2 : len) / 2;
+            const uint64_t nprime = bind ? len / 2 : len;
+            const uint64_t pairs = nprime / 2;
+            const bool thin = res_is_thin(D, nprime);
+            if (tid == 0) s_kl[m] = res_lanes<D>(thin);
+            if constexpr (D == 2) if (thin) {
+                const unsigned nb = res_thin_blocks(nprime, P, live);
+                if (b < nb) {
+                    TablePtrs tp;
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        tp.in[j] = s_cur[m][j];
+                        tp.out[j] = (ORDER == ORDER_LOW_TO_HIGH && bind) ? s_oth[m][j] : s_cur[m][j];
+                    }
+                    tp.e_out = tp.e_in = nullptr;
+                    tp.in_bits = 0;
+                    uint64_t* gl = a.st->lanes + m * RES_SLOT_U64;
+                    uint64_t* sl = live == 1 ? s_lanes + m * RES_SLOT_U64 : nullptr;
+                    if (bind) thin_pass<P, ORDER, true>(tp, nprime, sc, hi4, dsm, b, nb, gl, sl);
+                    else thin_pass<P, ORDER, false>(tp, nprime, sc, hi4, dsm, b, nb, gl, sl);
+                }
+                continue;
+            }
             const ResShape sh = res_shape(pairs, live);
             if (b < sh.nblk) {
                 TablePtrs tp;
@@ -331,10 +488,8 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 }
                 // largest pass this member can still ask for: an eval over len/2 pairs (not started) or a
                 // terminal bind over len/2 outputs
-                if (s_len[m] >= 2) {
-                    const unsigned need = res_blocks_for(s_len[m] / 2, grid);
-                    ln = need > ln ? need : ln;
-                }
+                const unsigned need = res_need_blocks(D, P, s_len[m], grid);
+                ln = need > ln ? need : ln;
             }
             s_live_next = ln;
             if (live > 1) {
@@ -348,14 +503,21 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
             if (s_last) a.mb->tlog2[4 * ((seq - 1) & 63) + 2] = global_timer_ns();
         }
         __syncthreads();
-        if (s_last) {
+        const unsigned ln = s_live_next;
+        // A block that is alone (live == 1) is poller AND answerer: its warp 0 goes straight back to polling for the
+        // next command while warps 1..7 publish this round's answer - the system-scope fence of the publication
+        // (~2 us over PCIe) then overlaps the poll's PCIe read instead of preceding it. With lookahead the next
+        // command is usually already posted, so this is on the critical path of every short round.
+        const bool solo = live == 1;
+        if (s_last && !(solo && warp == 0)) {
             // ---- the last block to arrive collects every member's lanes and answers the host ------------
+            const int pt = solo ? tid - 32 : tid, pn = solo ? RES_BLOCK - 32 : RES_BLOCK;  // publisher threads
             if (live > 1) {
                 __threadfence();
                 for (int idx = tid; idx < NM * RES_SLOT_U64; idx += RES_BLOCK) {
                     const int m = idx / RES_SLOT_U64, i = idx % RES_SLOT_U64;
                     const unsigned act = (actions >> (4 * m)) & 0xf;
-                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < KL) {
+                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < s_kl[m]) {
                         s_lanes[idx] = __ldcg(a.st->lanes + idx);
                         a.st->lanes[idx] = 0;  // back to zero for the next round
                     }
@@ -363,10 +525,11 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 __syncthreads();
             }
             uint64_t status = 0;
+            uint64_t* const result = a.mb->result[seq & 1];
             if (cmdw & RES_FLAG_EXCHANGE) {
                 // all-reduce of member 0's lanes over NVLink peer memory (integer sums: exact, order-free)
-                if (warp == 0) {
-                    const uint64_t xseq = s_line[6];
+                if (pt < 32) {
+                    const int KL = s_kl[0];
                     const int par = (int)(xseq & 1);
                     const int slot = (par * 16 + a.rank) * XCH_SLOT_U64;
                     for (int idx = lane; idx < a.world * KL; idx += 32) {
@@ -393,42 +556,46 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                         uint64_t sum = 0;
                         for (int src = 0; src < a.world; ++src)
                             sum += *(volatile uint64_t*)(mine + (par * 16 + src) * XCH_SLOT_U64 + i);
-                        a.mb->result[i] = sum;
+                        result[i] = sum;
                     }
                     if (!ok) status = 2;
                 }
             } else {
-                for (int idx = tid; idx < NM * RES_SLOT_U64; idx += RES_BLOCK) {
+                for (int idx = pt; idx < NM * RES_SLOT_U64; idx += pn) {
                     const int m = idx / RES_SLOT_U64, i = idx % RES_SLOT_U64;
                     const unsigned act = (actions >> (4 * m)) & 0xf;
-                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < KL) a.mb->result[idx] = s_lanes[idx];
+                    if ((act == RES_ACT_EVAL || act == RES_ACT_BIND_EVAL) && i < s_kl[m]) result[idx] = s_lanes[idx];
                 }
             }
             // terminal binds that left a member fully bound hand the T values back with the acknowledgement
-            for (int idx = tid; idx < NM * T; idx += RES_BLOCK) {
+            for (int idx = pt; idx < NM * T; idx += pn) {
                 const int m = idx / T, j = idx % T;
                 const unsigned act = (actions >> (4 * m)) & 0xf;
                 if (act == RES_ACT_FINAL && s_len[m] == 1) {
                     const Fr v = ld_elem_cg<Fr>(s_cur[m][j], 0);
 #pragma unroll
                     for (int w = 0; w < 4; ++w)
-                        a.mb->result[m * RES_SLOT_U64 + j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
+                        result[m * RES_SLOT_U64 + j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
                 }
             }
-            __syncthreads();
-            if (tid == 0) {
+            if (solo) asm volatile("bar.sync 1, 224;" ::: "memory");  // the seven publishing warps
+            else __syncthreads();
+            if (pt == 0) {
                 a.mb->tlog[2 * ((seq - 1) & 63) + 1] = global_timer_ns();
-                if (live > 1) a.st->ticket = 0;
-                __threadfence_system();  // cumulative over the block's result stores (ordered by the barrier)
-                a.mb->status = status;
-                __threadfence_system();
-                a.mb->res_seq = seq;
+                if (live > 1) {
+                    a.st->ticket = 0;
+                    st_release_gpu(&a.st->done, seq);  // (orders the lane zeroing and the ticket reset before it)
+                }
+                a.mb->ans[seq & 1].status = status;
+                __threadfence_system();  // cumulative over the publishers' result stores (ordered by the barrier)
+                a.mb->ans[seq & 1].res_seq = seq;
             }
         }
-        const unsigned ln = s_live_next;
         if (b >= ln) return;
         live = ln;
-        __syncthreads();  // s_line / s_last / s_lanes are rewritten by the next round
+        // s_last / s_lanes / s_kl are rewritten only after the next command's barrier; a solo block's warp 0 must
+        // not wait for its publishers here (it only touches s_line while it polls)
+        if (!solo) __syncthreads();
     }
 }
 
