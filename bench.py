@@ -299,11 +299,16 @@ def run_ours(args):
         t[:, 3] &= (1 << 60) - 1  # raw value < 2^252 < r: canonical Montgomery limbs
         return t
 
+    parity = None
     if world > 1:
         # each rank's synthetic tables ARE its shard: the contiguous block of the global tables under LowToHigh,
         # the strided slice under HighToLow (jb_sharded_member_create)
-        from jolt_b200.dist import init_comm, prove_sharded, sharded_claim
+        from jolt_b200.dist import init_comm, parity_self_check, prove_sharded, sharded_claim
         init_comm(sess, dist)
+        # before anything is timed: the sharded proof must equal the single-GPU proof of the same global polynomial
+        parity = parity_self_check(sess, dist, log_n=14, m=m, order=order)
+        if rank == 0 and not parity.get("identical_to_single_gpu"):
+            raise SystemExit(f"bench.py: sharded proof differs from the single-GPU proof: {parity}")
 
     def one_step(bufs, seed):
         polys = [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in bufs]
@@ -390,6 +395,14 @@ def run_ours(args):
         e2e_s = float(tmax.item())
     # same inputs + same stand-in transcript => identical proofs through both arms
     assert all((a == b).all() for a, b in zip(e2e_res, res)) and (e2e_fe == fe).all(), "value arm and e2e arm disagree"
+    # the full-size timed run must end where a sumcheck has to: final claim == prod_j f_j(point)
+    fin_claim = F.from_limbs(res[1])
+    prod = 1
+    for v in F.limbs_to_ints(fe):
+        prod = prod * v % F.R_MOD
+    assert prod == fin_claim, "full-size run: final claim != product of the final evaluations"
+    if parity is not None:
+        parity["full_size_final_claim_is_product_of_final_evals"] = True
 
     if rank != 0:
         if dist:
@@ -446,6 +459,9 @@ def run_ours(args):
                 "h2d_bytes_per_step": m * n * 32 * world,
                 "d2h_bytes_per_step": (args.log_n * (m + 1) * 32 + m * 32) * world},
         "gpu_launches": int(launches),
+        "parity_checked": parity if parity is not None else {
+            "full_size_final_claim_is_product_of_final_evals": True, "value_arm_equals_e2e_arm": True,
+            "note": "N = 1: bit-exact parity against the oracle is tests/ (-m gpu); the bench asserts the sumcheck identity"},
         "clocks": clocks,
         "roofline": roof,
         "all_field_ops_per_s": all_ops(args.log_n, m) * world / (ms_per_step * 1e-3),

@@ -140,3 +140,63 @@ def prove_sharded(sess: Session, polys: list[Polynomial], claim: int, seed: int,
     fe = mem.final_evals(raw=raw)
     mem.close()
     return res, fe
+
+
+def parity_self_check(sess: Session, dist, log_n: int = 14, m: int = 2, order: int = LOW_TO_HIGH, seed: int = 7) -> dict:
+    """Driver-visible multi-GPU parity (the optimized tier's run_lockstep, crates/jolt-kernels/src/optimized/parity.rs:
+    79-118, across ranks): an index-sharded product sumcheck over 2^log_n entries per rank against the single-GPU
+    proof of the same GLOBAL polynomial on rank 0 - challenges, every round polynomial, the final claim and the
+    final evaluations must be identical on every rank and equal to the single-GPU run. Collective: call on every rank."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n = 1 << log_n
+    shards = []
+    for j in range(m):
+        g = torch.Generator(device="cuda").manual_seed(0x9A17 + 64 * rank + j)
+        t = torch.randint(0, 2 ** 62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+        t[:, 3] &= (1 << 60) - 1
+        shards.append(t)
+    clones = [t.clone() for t in shards]  # the proof binds its tables in place: work on copies (kept alive below)
+    polys = [Polynomial.wrap_device(sess, c.data_ptr(), n) for c in clones]
+    claim = sharded_claim(sess, polys, dist)
+    res, fe = prove_sharded(sess, polys, claim, seed, order=order)
+    # every rank must hold the same proof
+    digest = torch.tensor([hash((tuple(res.challenges), res.final_claim, tuple(fe),
+                                 tuple(tuple(p.coefficients) for p in res.round_polynomials))) & ((1 << 62) - 1)],
+                          dtype=torch.int64, device="cuda")
+    lo, hi = digest.clone(), digest.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same_on_all_ranks = bool(int(lo.item()) == int(hi.item()))
+    gathered = [[torch.empty_like(t) for _ in range(world)] for t in shards]
+    for j, t in enumerate(shards):
+        dist.all_gather(gathered[j], t)
+    out = {"log_n_per_gpu": log_n, "world": world, "m": m, "order": "l2h" if order == LOW_TO_HIGH else "h2l",
+           "same_on_all_ranks": same_on_all_ranks}
+    if rank == 0:
+        tabs = []
+        for j in range(m):
+            if order == LOW_TO_HIGH:
+                tabs.append(torch.cat(gathered[j], dim=0).contiguous())                       # contiguous blocks
+            else:
+                tabs.append(torch.stack(gathered[j], dim=1).reshape(n * world, 4).contiguous())  # global[j * G + g]
+        gp = [Polynomial.wrap_device(sess, t.data_ptr(), n * world) for t in tabs]
+        mem = ProductMember(sess, gp, order)
+        rounds = log_n + world.bit_length() - 1
+        one = prove_batch_native([BatchMember(claim, 1, rounds, 0)], [mem], rounds, m, claim, seed=seed)
+        one_fe = mem.final_evals()
+        mem.close()
+        prod = 1
+        for v in fe:
+            prod = prod * v % F.R_MOD
+        out.update(
+            challenges_equal=one.challenges == res.challenges,
+            round_polynomials_equal=[p.coefficients for p in one.round_polynomials] == [p.coefficients for p in res.round_polynomials],
+            final_claim_equal=one.final_claim == res.final_claim,
+            final_evals_equal=one_fe == fe,
+            final_claim_is_product_of_final_evals=prod == res.final_claim)
+        out["identical_to_single_gpu"] = bool(out["challenges_equal"] and out["round_polynomials_equal"] and
+                                              out["final_claim_equal"] and out["final_evals_equal"] and same_on_all_ranks)
+    sess.synchronize()
+    del clones
+    return out
