@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-msm", action="store_true", help="skip the secondary G1 MSM measurement")
     ap.add_argument("--msm-log-n", type=int, default=20)
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section (bind, eq, MSM 2^20/2^24, HyperKZG, split-eq)")
     return ap.parse_args()
 
 
@@ -153,7 +154,7 @@ def host_threads() -> int:
     return n
 
 
-def cpu_sumcheck_times(log_n: int, m: int, order: int, threads: int, reps: int) -> list[float]:
+def cpu_sumcheck_times(log_n: int, m: int, order: int, threads: int, reps: int, budget_s: float | None = None) -> list[float]:
     """`reps` full sumchecks of the workload on the host cores with the C restatement of the reference
     algorithm (bind pass + eval pass per round, OpenMP static chunks of >= 1024 like Rayon's PAR_THRESHOLD).
     Returns the seconds of every repetition; the first one pays the page faults of freshly mapped buffers
@@ -162,7 +163,10 @@ def cpu_sumcheck_times(log_n: int, m: int, order: int, threads: int, reps: int) 
     from oracle.coracle import rand_limbs, rand_challenge
     tabs0 = [rand_limbs(0xB200 + j, 1 << log_n) for j in range(m)]
     out = []
+    t_begin = time.perf_counter()
     for rep in range(reps):
+        if budget_s is not None and rep >= 3 and time.perf_counter() - t_begin > budget_s:
+            break
         tabs = [t.copy() for t in tabs0]
         t0 = time.perf_counter()
         bind = None
@@ -191,19 +195,23 @@ def run_reference(args):
     world = args.gpus
     # bounded sample: the per-GPU workload (2^log_n); warm-up and timed repetitions in ONE run so the timed
     # ones see a warm allocator (first-touch page faults of fresh 64-128 MiB buffers cost ~10x on 64 threads)
-    total = max(1, min(args.steps, 5))
-    nwarm = max(1, min(args.warmup, 2))
-    secs = cpu_sumcheck_times(args.log_n, args.m, order, threads, nwarm + total)[nwarm:]
+    # --steps / --warmup are honoured as given; one step (a full 2^log_n sumcheck) takes ~0.2 s on the GPU boxes' host
+    # cores, so the default 50 + 5 still ends within a minute (a wall-clock guard stops a slow box at ~150 s)
+    total = max(1, args.steps)
+    nwarm = max(1, args.warmup)
+    secs = cpu_sumcheck_times(args.log_n, args.m, order, threads, nwarm + total, budget_s=150.0)[nwarm:]
+    total = len(secs)
     per = sum(secs) / len(secs)
     value = bind_ops(args.log_n, args.m) / per
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": total,
         "warmup": nwarm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (4-limb 256-bit Montgomery integers)", "data": "synthetic",
-        "config": config(args, 1),
+        "config": config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"mean of {total} full 2^{args.log_n} m={args.m} sumchecks after {nwarm} warm-up (bind pass + eval pass per round), "
-                                   "C restatement of the reference algorithm with OpenMP; not the Rust binary"},
+                         "sample": f"mean of {total} full 2^{args.log_n} m={args.m} sumchecks after {nwarm} warm-up (bind pass + eval pass per round) - "
+                                   f"the per-GPU share of the workload, a bounded sample when n_gpus > 1 (field-ops/s does not depend on which "
+                                   f"2^{args.log_n} block is swept); C restatement of the reference algorithm with OpenMP, not the Rust binary"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "all_field_ops_per_s": all_ops(args.log_n, args.m) / per,
     }
@@ -257,14 +265,172 @@ def msm_section(sess, log_n: int, with_cpu: bool):
     if with_cpu:
         from oracle import coracle as C
         from oracle import bn254 as O
-        t0 = time.perf_counter()
-        cpu_xy, cpu_inf = C.g1_msm_pippenger(xy, sc, 0, host_threads())
-        dt = time.perf_counter() - t0
+        dts = []
+        for _ in range(4):  # one warm-up (first-touch page faults, thread start-up) + best of 3
+            t0 = time.perf_counter()
+            cpu_xy, cpu_inf = C.g1_msm_pippenger(xy, sc, 0, host_threads())
+            dts.append(time.perf_counter() - t0)
+        dt = min(dts[1:])
         out["cpu_baseline"] = {"ms": dt * 1e3, "terms_per_s": n / dt, "cores": host_threads(), "kind": "port",
-                               "sample": "one Pippenger MSM (arkworks window heuristic) with the C restatement, OpenMP over windows"}
+                               "sample": "best of 3 after 1 warm-up: Pippenger MSM (arkworks window heuristic) with the C restatement, OpenMP over windows"}
         out["matches_cpu_port"] = (not cpu_inf) and gpu_pt == (
             O.from_mont_limbs(cpu_xy[:4], O.Q_MOD), O.from_mont_limbs(cpu_xy[4:], O.Q_MOD))
     tab.free()
+    return out
+
+
+def kernels_section(sess, peak_hbm: float, with_cpu: bool):
+    """Every streaming kernel of the path against its roofline, on ONE GPU, timed with CUDA events on the launching
+    stream (best of 5 after a warm-up, a 512 MiB L2 flush between repetitions). HBM-bound kernels report algorithmic
+    GB/s over the measured copy peak; the MSM bucket accumulation is integer-bound and reports bucket additions/s over
+    the measured Montgomery-product ceiling (jb_diag_mul_throughput, 10 Fq products per mixed XYZZ addition)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from jolt_b200 import BatchMember, EqPolynomial, EqProductMember, G1Bases, HyperKZG, LOW_TO_HIGH, HIGH_TO_LOW, Polynomial
+    from jolt_b200 import field as F
+    from oracle.coracle import rand_challenge, rand_limbs
+    out = {"timing": "CUDA events on the launching stream, best of 5 after 1 warm-up, 512 MiB L2 flush between repetitions"}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def timed(fn, setup=None, reps=5):
+        best = 1e30
+        for rep in range(reps + 1):
+            arg = setup() if setup else None
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(arg)
+            e1.record()
+            e1.synchronize()
+            if rep:
+                best = min(best, e0.elapsed_time(e1))
+        return best
+
+    def synth(n, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        t = torch.randint(0, 2 ** 62, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+        t[:, 3] &= (1 << 60) - 1
+        return t
+
+    # the integer ceiling everything multiplier-bound is scored against
+    g_mul = {}
+    for name, field, variant in (("fr_full", 0, 0), ("fr_challenge125", 0, 1), ("fq_full", 1, 0)):
+        v = ctypes.c_double()
+        sess.check(sess.lib.jb_diag_mul_throughput(sess.h, field, variant, 2000, 148 * 8, ctypes.byref(v)))
+        g_mul[name] = v.value
+    out["montgomery_products_per_s"] = {k: v * 1e9 for k, v in g_mul.items()}
+
+    # ---- bind_kernel, 2^24 (Polynomial::bind_with_order) -----------------------------------------
+    n = 1 << 24
+    src = synth(n, 0xB1D)
+    binds = []
+    for order, oname in ((LOW_TO_HIGH, "l2h"), (HIGH_TO_LOW, "h2l")):
+        for ch, cname in ((rand_challenge(5), "challenge125"), (F.to_limbs(F.R_MOD - 12345), "full254")):
+            def setup():
+                buf = src.clone()
+                return buf, Polynomial.wrap_device(sess, buf.data_ptr(), n)
+            ms = timed(lambda a: a[1].bind_with_order(ch, order), setup)
+            gbs = 48 * n / (ms * 1e-3) / 1e9
+            binds.append({"order": oname, "scalar": cname, "ms": ms, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak_hbm})
+    out["bind_kernel_2^24"] = {"algorithmic_bytes": 48 * n, "bound": "hbm", "peak": peak_hbm, "runs": binds}
+    del src
+
+    # ---- eq_stream_kernel (EqPolynomial::evals): 32 B written per output -------------------------
+    eqs = []
+    for lg in (22, 26):
+        for cname in ("challenge125", "full254"):
+            r = np.stack([rand_challenge(9 + i) if cname == "challenge125" else F.to_limbs((0x1234567 + i) * 0x9E3779B97F4A7C15 % F.R_MOD)
+                          for i in range(lg)])
+            ms = timed(lambda a: EqPolynomial.evals(sess, r).free())
+            gbs = 32 * (1 << lg) / (ms * 1e-3) / 1e9
+            ceiling = (g_mul["fr_challenge125"] if cname == "challenge125" else g_mul["fr_full"]) * 32  # GB/s if 1 product/output
+            eqs.append({"log_n": lg, "point": cname, "ms": ms, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak_hbm,
+                        "integer_ceiling_gb_per_s": ceiling, "frac_of_integer_ceiling": gbs / ceiling})
+    out["eq_stream_kernel"] = {"algorithmic_bytes_per_output": 32, "bound": "hbm (125-bit point) / integer pipe (254-bit point: one product per output)",
+                               "peak": peak_hbm, "runs": eqs}
+
+    # ---- G1 MSM: whole call + the bucket accumulation kernel (integer-bound) ---------------------
+    G = np.concatenate([F.to_limbs(1, F.Q_MOD), F.to_limbs(2, F.Q_MOD)])
+    msms = []
+    for lg in (20, 24):
+        nn = 1 << lg
+        rng = np.random.Generator(np.random.PCG64(0x5CA1A2 + lg))
+        sc = rng.integers(0, 1 << 64, size=(nn, 4), dtype=np.uint64)
+        sc[:, 3] &= np.uint64(((1 << 64) - 1) >> 3)
+        tab = Polynomial.new(sess, sc)
+        bases = G1Bases.generate_multiples(sess, G, nn)
+        # closed form (bases (i + 1) G): msm(s) == (sum_i s_i (i + 1)) G, checked on the host with one scalar multiplication
+        for label in ("plain_srs", "precomputed_srs"):
+            if label == "precomputed_srs":
+                try:
+                    bases.precompute()
+                except Exception as e:  # 12 x the SRS in HBM: report, do not fail the bench
+                    msms.append({"log_n": lg, "srs": label, "skipped": str(e)})
+                    continue
+            sess.timing_enable(True, min_items=1)
+            sess.timing_collect()
+            ms = timed(lambda a: bases.msm(tab), reps=3)
+            acc = [t for t in sess.timing_collect() if t["kind"] == "msm_accumulate"]
+            sess.timing_enable(False)
+            acc_ms = min(t["ms"] for t in acc) if acc else None
+            c_bits = acc[0]["m"] if acc else None
+            windows = -(-254 // c_bits) if c_bits else None
+            adds = nn * windows if windows else None
+            row = {"log_n": lg, "srs": label, "ms": ms, "terms_per_s": nn / (ms * 1e-3), "window_bits": c_bits, "windows": windows,
+                   "accumulate_kernel_ms": acc_ms}
+            if acc_ms:
+                rate = adds / (acc_ms * 1e-3)
+                ceiling = g_mul["fq_full"] * 1e9 / 10.0
+                row.update(bucket_adds_per_s=rate, integer_ceiling_adds_per_s=ceiling, frac_of_integer_ceiling=rate / ceiling,
+                           hbm_gb_per_s=(adds * 68) / (acc_ms * 1e-3) / 1e9, frac_of_hbm_peak=(adds * 68) / (acc_ms * 1e-3) / 1e9 / peak_hbm)
+            msms.append(row)
+        bases.free()
+        tab.free()
+    out["msm_g1"] = {"bound": "integer pipe (10 Fq products per mixed XYZZ bucket addition); 68 B gathered per addition",
+                     "runs": msms}
+
+    # ---- HyperKZG open, ell = 22 (precomputed SRS) ----------------------------------------------
+    ell = 22
+    nn = 1 << ell
+    bases = G1Bases.generate_multiples(sess, G, nn)
+    bases.precompute()
+    poly = Polynomial.new(sess, rand_limbs(1, nn))
+    point = np.stack([rand_challenge(7 + i) for i in range(ell)])
+    tc = timed(lambda a: HyperKZG.commit(bases, poly), reps=3)
+    to = timed(lambda a: HyperKZG.open(bases, poly, point, lambda c: 12345, lambda v: 6789), reps=3)
+    out["hyperkzg_ell22"] = {"commit_ms": tc, "open_ms": to, "srs": "precomputed windows + small-MSM table",
+                             "bound": "integer pipe (MSMs)", "note": "ell - 1 folds, ell - 1 + 3 MSMs, 3 Horner scans, two transcript callbacks"}
+    bases.free()
+    poly.free()
+
+    # ---- split-eq (Gruen) member, 2^22, m = 2 (degree 3) ----------------------------------------
+    lg = 22
+    nn = 1 << lg
+    tabs = [synth(nn, 0xE0 + j) for j in range(2)]
+    w = np.stack([rand_challenge(100 + i) for i in range(lg)])
+    eqp = EqPolynomial.evals(sess, w)
+    from jolt_b200 import ProductMember
+    probe_bufs = [t.clone() for t in tabs]
+    probe = ProductMember(sess, [eqp] + [Polynomial.wrap_device(sess, t.data_ptr(), nn) for t in probe_bufs], LOW_TO_HIGH)
+    ev = probe.prove_round_evals(None, 0)
+    claim = (ev[0] + ev[1]) % F.R_MOD
+    probe.close()
+    del probe_bufs
+
+    def se_setup():
+        bufs = [t.clone() for t in tabs]
+        return bufs, EqProductMember(sess, [Polynomial.wrap_device(sess, b.data_ptr(), nn) for b in bufs], w)
+
+    def se_run(a):
+        jolt_b200.prove_batch_native([BatchMember(claim, 1, lg, 0)], [a[1]], lg, 3, claim, seed=9, raw=True)
+        a[1].close()
+    import jolt_b200
+    ms = timed(se_run, se_setup, reps=3)
+    alg = 2 * 96 * nn  # two witness tables bound over the whole sumcheck (~96 N bytes each); no eq table is streamed
+    out["split_eq_member_2^22_m2"] = {"ms": ms, "algorithmic_bytes": alg, "gb_per_s": alg / (ms * 1e-3) / 1e9,
+                                      "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak_hbm, "bound": "hbm nominal; latency (22 round trips) in practice"}
+    del flush
     return out
 
 
@@ -325,10 +491,12 @@ def run_ours(args):
     base = [synth(0xB200 + 16 * rank + j) for j in range(m)]
     # the input claim (known from the previous protocol stage in a real proof): sum_x prod_j f_j(x)
     if world == 1:
-        probe = ProductMember(sess, [Polynomial.wrap_device(sess, b.clone().data_ptr(), n) for b in base], order)
+        probe_bufs = [b.clone() for b in base]  # (kept alive: a wrapped table borrows the tensor's memory)
+        probe = ProductMember(sess, [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in probe_bufs], order)
         ev = probe.prove_round_evals(None, 0)
         claim = (ev[0] + ev[1]) % F.R_MOD
         probe.close()
+        del probe_bufs
     else:
         claim = sharded_claim(sess, [Polynomial.wrap_device(sess, b.data_ptr(), n) for b in base], dist)
     desc = [BatchMember(claim, 1, args.log_n, 0)]
@@ -508,6 +676,8 @@ def run_ours(args):
                                    "note": "secondary: u64 columns promoted on the device (jb_table_upload_small), not the headline workload"}
     if world == 1 and not args.no_msm:
         line["msm"] = msm_section(sess, args.msm_log_n, not args.no_cpu_baseline)
+    if world == 1 and not args.no_kernels:
+        line["kernels"] = kernels_section(sess, peak, not args.no_cpu_baseline)
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
         reps = 2

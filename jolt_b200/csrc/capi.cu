@@ -336,7 +336,11 @@ int jb_table_upload(jb_ctx* c, const uint64_t* limbs, size_t len, jb_table* out)
     if (st != JB_OK) return st;
     Guard g(c);
     Table& t = c->tables[*out];
-    return c->check(cudaMemcpyAsync(t.buf, limbs, len * 32, cudaMemcpyHostToDevice, c->stream), "table upload");
+    st = c->check(cudaMemcpyAsync(t.buf, limbs, len * 32, cudaMemcpyHostToDevice, c->stream), "table upload");
+    // the host buffer is borrowed for the duration of the call only: with pinned / registered memory the copy is
+    // truly asynchronous, so wait for it (pageable memory is staged before cudaMemcpyAsync returns anyway)
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "table upload sync");
+    return st;
 }
 
 int jb_table_wrap_device(jb_ctx* c, void* dptr, size_t len, jb_table* out) {

@@ -13,6 +13,7 @@
 #include <string>
 
 #include "ctx.hpp"
+#include "poly_kernels.cuh"
 
 namespace {
 
@@ -137,9 +138,12 @@ int jb_comm_p2p_handle(jb_ctx* c, uint8_t out[64]) {
     if (!c || !out) return JB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);
     cudaSetDevice(c->device);
+    if (c->world > 16 || c->rank >= 16) return c->fail(JB_ERR_UNSUPPORTED, "p2p: at most 16 ranks (the NCCL path stays)");
+    c->quiesce_resident(true);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!c->xch_peer[c->rank]) {
         void* p = nullptr;
+        static_assert(jb::XCH_BYTES <= 65536, "exchange buffer too small");
         if (cudaMalloc(&p, 65536) != cudaSuccess) return c->fail(JB_ERR_OOM, "p2p: exchange buffer");
         cudaMemset(p, 0, 65536);
         cudaDeviceSynchronize();
@@ -187,7 +191,7 @@ int jb_comm_destroy(jb_ctx* c) {
         if (a) a->CommDestroy((ncclComm_t)c->nccl_comm);
         c->nccl_comm = nullptr;
     }
-    if (c->xch_ready || c->xch_peer[c->rank]) {
+    if (c->world <= 16 && c->rank < 16 && (c->xch_ready || c->xch_peer[c->rank])) {
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
         for (int g = 0; g < 16; ++g) {

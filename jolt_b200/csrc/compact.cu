@@ -101,6 +101,8 @@ int jb_table_upload_small(jb_ctx* c, const void* values, size_t len, int kind, j
     const size_t bytes = len * (size_t)small_kind_bytes(kind);
     st = c->dev_alloc(&d_vals, bytes);
     if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_vals, values, bytes, cudaMemcpyHostToDevice, c->stream), "upload_small H2D");
+    // (the caller's buffer is only borrowed for the call: a pinned source makes the copy truly asynchronous)
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "upload_small sync");
     if (st == JB_OK) {
         promote_small_kernel<<<grid_for(c, len), 256, 0, c->stream>>>(d_vals, len, kind, t.buf);
         c->launches++;
@@ -136,6 +138,8 @@ int jb_table_bind_small(jb_ctx* c, const void* values, size_t len, int kind, con
     const size_t bytes = len * (size_t)small_kind_bytes(kind);
     st = c->dev_alloc(&d_vals, bytes);
     if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_vals, values, bytes, cudaMemcpyHostToDevice, c->stream), "bind_small H2D");
+    // (the caller's buffer is only borrowed for the call: a pinned source makes the copy truly asynchronous)
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "bind_small sync");
     if (st == JB_OK) {
         if (order == JB_HIGH_TO_LOW)
             bind_small_kernel<ORDER_HIGH_TO_LOW><<<grid_for(c, half), 256, 0, c->stream>>>(d_vals, half, kind, s, t.buf);

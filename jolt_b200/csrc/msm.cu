@@ -645,6 +645,10 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     const uint64_t* d_gather = use_small ? srs.pre_small + 8 * offset : use_big ? srs.pre + 8 * offset : d_bases;
     const int Weff = shared ? 1 : p.W;  // bucket sets
     const size_t nb = (size_t)Weff * p.B;
+    // bucket offsets, task offsets, the scatter cursor and the histogram are 32-bit: W * n sorted entries must stay
+    // below 2^32 (n ~ 2^28 with 16 windows would wrap the exclusive scan and read wrong ranges - silently)
+    if ((size_t)p.W * n >= ((size_t)1 << 32) || nb + ((size_t)p.W * n) / MSM_CHUNK + 1 >= ((size_t)1 << 32))
+        return c->fail(JB_ERR_UNSUPPORTED, "msm: windows x terms must be < 2^32 (split the call)");
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
     const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
     uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr;
