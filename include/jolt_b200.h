@@ -151,7 +151,8 @@ int jb_member_final_evals(jb_member* mem, uint64_t* out_m_elems);
  * (crates/jolt-poly/src/split_eq.rs:10-447): each round's sweep is weighted by E_out (x) E_in over the
  * not-yet-current variables (two ~sqrt(N) tables), the current variable's linear factor and the hint
  * s(0)+s(1) = previous_claim complete the round polynomial on the host (gruen_poly_from_evals, :404-437).
- * w = nvars elements, w[0] <-> most significant index bit; LowToHigh binding; m in 1..3; the running claim
+ * w = nvars elements, w[0] <-> most significant index bit; both binding orders (LowToHigh: prefix tables
+ * evals_cached, split_eq.rs:208-232; HighToLow: suffix tables evals_cached_rev, :233-257); m in 1..3; the running claim
  * is mandatory in prove_round. Round polynomials equal those of the (m+1)-table product member over the
  * materialised eq table. jb_eq_member_scalar returns scale * eq(w, r) after the rounds. */
 int jb_eq_member_create(jb_ctx* ctx, const jb_table* tables, size_t m, const uint64_t* w, size_t nvars,
@@ -295,6 +296,17 @@ int jb_msm_g1_small(jb_ctx* ctx, jb_srs bases, size_t offset, const void* scalar
                     uint64_t out_xyz[12]);
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
+
+/* Batch affine addition: batch_g1_additions_multi_affine (crates/jolt-crypto/src/ec/bn254/batch_addition.rs:53-150),
+ * the one-hot / binary column path of Dory's tier-1 commitments (crates/jolt-dory/src/streaming.rs:68,128,152,201).
+ * Set s is indices[set_offsets[s] .. set_offsets[s + 1]) into `bases`; out_xy receives one AFFINE point per set
+ * (8 limbs, identity = zeros for an empty set; a singleton is its base). Every level halves the sets by pairwise
+ * affine additions that share batch inversions. Precondition as in the reference: the two points of a pair have
+ * distinct x (no repeated or opposite points); a violating pair yields the reference's unchecked garbage for that
+ * pair only (zero denominators are skipped by the batch inversion, as ark_ff::batch_inversion does).
+ * Indices out of bounds -> JB_ERR_INVALID (the reference documents them as a precondition). */
+int jb_g1_batch_add(jb_ctx* ctx, jb_srs bases, const uint64_t* set_offsets, const uint32_t* indices, size_t nsets,
+                    uint64_t* out_xy);
 
 /* Multi-GPU MSM: this rank's share of the terms (its own srs handle and host scalars); one
  * all-gather of the G partial points (96 B each) and a local sum give every rank the same total.

@@ -91,6 +91,7 @@ SIGNATURES = {
                                              ctypes.POINTER(ctypes.c_double), c_size_t, ctypes.POINTER(c_size_t)]),
     "jb_diag_mul_throughput": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.POINTER(ctypes.c_double)]),
+    "jb_g1_batch_add": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_u64p, ctypes.POINTER(ctypes.c_uint32), c_size_t, c_u64p]),
     "jb_msm_g1_sharded": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_u64p, c_size_t, c_u64p]),
     "jb_msm_g1_device": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_void_p, c_size_t, c_u64p]),
     "jb_hyperkzg_open": (ctypes.c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint64, c_u64p, c_size_t, c_void_p, c_void_p,

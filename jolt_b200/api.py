@@ -445,16 +445,16 @@ class RoundScheduler:
 class EqProductMember(ProductMember):
     """ProveRounds member for sum_x eq(w, x) * prod_j f_j(x) (degree m + 1) with the eq polynomial kept
     split (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): no eq table is materialised,
-    bound or streamed. `w_limbs`: n elements, w[0] <-> MSB; LowToHigh binding."""
+    bound or streamed. `w_limbs`: n elements, w[0] <-> MSB; both binding orders (split_eq.rs:208-257)."""
 
-    def __init__(self, session: Session, polys: list[Polynomial], w_limbs, scale=None):
+    def __init__(self, session: Session, polys: list[Polynomial], w_limbs, scale=None, order: int = LOW_TO_HIGH):
         self.s = session
         handles = np.array([p.handle for p in polys], dtype=np.uint64)
         w = np.ascontiguousarray(w_limbs, dtype=np.uint64).reshape(-1, 4)
         sc = None if scale is None else _limbs(scale)
         h = ctypes.c_void_p()
         session.check(session.lib.jb_eq_member_create(session.h, _p(handles), len(polys), _p(w), w.shape[0],
-                                                      _p(sc) if sc is not None else None, LOW_TO_HIGH, ctypes.byref(h)))
+                                                      _p(sc) if sc is not None else None, order, ctypes.byref(h)))
         for p in polys:
             p.handle = 0
         self.h = h
@@ -687,6 +687,19 @@ class G1Bases:
         self.s.check(self.s.lib.jb_msm_g1_small(self.s.h, self.handle, offset,
                                                 a.ctypes.data_as(ctypes.c_void_p) if n else None, n, k, _p(out)))
         return out
+
+    def batch_add(self, index_sets) -> np.ndarray:
+        """batch_g1_additions_multi_affine (crates/jolt-crypto/src/ec/bn254/batch_addition.rs:53-150): one affine
+        sum (8 limbs; zeros = identity) per index set. Precondition: no pair of equal / opposite points."""
+        offs = np.zeros(len(index_sets) + 1, dtype=np.uint64)
+        for i, st in enumerate(index_sets):
+            offs[i + 1] = offs[i] + len(st)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(st, dtype=np.uint32) for st in index_sets]) if len(index_sets) and offs[-1]
+                                    else np.zeros(0, dtype=np.uint32))
+        out = np.zeros((max(len(index_sets), 1), 8), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_g1_batch_add(self.s.h, self.handle, _p(offs), flat.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                len(index_sets), _p(out)))
+        return out[: len(index_sets)]
 
     def msm_sharded(self, scalars, offset: int = 0) -> np.ndarray:
         """This rank's share of a term-partitioned MSM; every rank gets the same total (jb_msm_g1_sharded)."""

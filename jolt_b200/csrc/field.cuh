@@ -557,4 +557,13 @@ __device__ __forceinline__ void st_elem(uint64_t* base, size_t idx, const F& x) 
                  : "memory");
 }
 
+// Streaming store (evict-first): for tables that are written once and not read again by the same kernel.
+template <class F>
+__device__ __forceinline__ void st_elem_cs(uint64_t* base, size_t idx, const F& x) {
+    uint32_t* p = reinterpret_cast<uint32_t*>(base) + idx * 8;
+    asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x.v[0]), "r"(x.v[1]),
+                 "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7])
+                 : "memory");
+}
+
 }  // namespace jb

@@ -64,10 +64,10 @@ int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar&
     return launch_fused_mb<M, P, ORDER, BIND, HI4, SKIP1, 256, 2>(c, tp, pairs, s, out);
 }
 
-// weighted (split-eq) passes: LowToHigh, s(1) from the claim, 256 x 2
-template <int M, bool BIND, bool HI4>
+// weighted (split-eq) passes: s(1) from the claim, 256 x 2
+template <int M, int ORDER, bool BIND, bool HI4>
 int launch_weighted(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, RoundOut out) {
-    auto kernel = fused_round_kernel<M, 1, ORDER_LOW_TO_HIGH, BIND, HI4, true, 256, 2, true>;
+    auto kernel = fused_round_kernel<M, 1, ORDER, BIND, HI4, true, 256, 2, true>;
     constexpr size_t smem = FusedShape<M, true>::smem_bytes(256);
     static int per_sm = [&] {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -90,19 +90,24 @@ int launch_weighted(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScal
     return c->check(cudaGetLastError(), "fused_round_kernel (weighted) launch");
 }
 
-template <int M>
+template <int M, int ORDER>
 int dispatch_weighted1(jb_ctx* c, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
                        const RoundOut& out) {
-    if (!bind) return launch_weighted<M, false, false>(c, tp, pairs, s, out);
-    return hi4 ? launch_weighted<M, true, true>(c, tp, pairs, s, out) : launch_weighted<M, true, false>(c, tp, pairs, s, out);
+    if (!bind) return launch_weighted<M, ORDER, false, false>(c, tp, pairs, s, out);
+    return hi4 ? launch_weighted<M, ORDER, true, true>(c, tp, pairs, s, out)
+               : launch_weighted<M, ORDER, true, false>(c, tp, pairs, s, out);
 }
 
-int dispatch_weighted(jb_ctx* c, int m, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
+int dispatch_weighted(jb_ctx* c, int m, int order, const TablePtrs& tp, size_t pairs, bool bind, bool hi4, const BindScalar& s,
                       const RoundOut& out) {
+    const bool l2h = order == JB_LOW_TO_HIGH;
     switch (m) {
-        case 1: return dispatch_weighted1<1>(c, tp, pairs, bind, hi4, s, out);
-        case 2: return dispatch_weighted1<2>(c, tp, pairs, bind, hi4, s, out);
-        case 3: return dispatch_weighted1<3>(c, tp, pairs, bind, hi4, s, out);
+        case 1: return l2h ? dispatch_weighted1<1, ORDER_LOW_TO_HIGH>(c, tp, pairs, bind, hi4, s, out)
+                           : dispatch_weighted1<1, ORDER_HIGH_TO_LOW>(c, tp, pairs, bind, hi4, s, out);
+        case 2: return l2h ? dispatch_weighted1<2, ORDER_LOW_TO_HIGH>(c, tp, pairs, bind, hi4, s, out)
+                           : dispatch_weighted1<2, ORDER_HIGH_TO_LOW>(c, tp, pairs, bind, hi4, s, out);
+        case 3: return l2h ? dispatch_weighted1<3, ORDER_LOW_TO_HIGH>(c, tp, pairs, bind, hi4, s, out)
+                           : dispatch_weighted1<3, ORDER_HIGH_TO_LOW>(c, tp, pairs, bind, hi4, s, out);
         default: return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
     }
 }
@@ -283,7 +288,7 @@ static int member_round(jb_member* mem, const uint64_t* bind, bool skip1, void* 
         tp.e_out = eqr->e_out;
         tp.e_in = eqr->e_in;
         tp.in_bits = eqr->in_bits;
-        st = dispatch_weighted(c, mem->m, tp, pairs, do_bind, hi4, s, ro);
+        st = dispatch_weighted(c, mem->m, mem->order, tp, pairs, do_bind, hi4, s, ro);
     } else {
         st = dispatch_fused(c, mem->m, mem->terms, mem->order, skip1, tp, pairs, do_bind, hi4, s, ro);
     }
@@ -568,21 +573,38 @@ static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
     if (!claim) return c->fail(JB_ERR_INVALID, "eq member: the running claim is required (Gruen hint s(0)+s(1))");
     const size_t n = mem->eq_n, M = (size_t)mem->m;
     if (round >= n) return c->fail(JB_ERR_INVALID, "prove_round: member is fully bound");
+    const bool l2h = mem->order == JB_LOW_TO_HIGH;
     if (bind) {
         if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
-        eq_absorb_bind(mem, n - round, bind);  // the previous round's variable
+        eq_absorb_bind(mem, l2h ? n - round : round - 1, bind);  // the previous round's variable
     }
-    const size_t cur = n - round;  // unbound variables including the current one (index cur - 1, LowToHigh)
-    const size_t head = cur - 1;
-    const size_t out_bits = head < mem->eq_split ? head : mem->eq_split;
-    const size_t in_bits = head - out_bits;
     EqRound er;
-    er.e_out = mem->eq_tabs + 4 * (((size_t)1 << out_bits) - 1);
-    er.e_in = mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << in_bits) - 1);
-    er.in_bits = (int)in_bits;
+    size_t cur_var;
+    if (l2h) {
+        const size_t cur = n - round;  // unbound variables including the current one (index cur - 1)
+        const size_t head = cur - 1;
+        const size_t out_bits = head < mem->eq_split ? head : mem->eq_split;
+        const size_t in_bits = head - out_bits;
+        er.e_out = mem->eq_tabs + 4 * (((size_t)1 << out_bits) - 1);
+        er.e_in = mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << in_bits) - 1);
+        er.in_bits = (int)in_bits;
+        cur_var = cur - 1;
+    } else {
+        // HighToLow (split_eq.rs:233-257): the current variable is w[round]; the remaining ones w[round + 1 .. n)
+        // are the pair index MSB-first: the unbound suffix of in_point = w[1 .. 1 + s) on top of out_point =
+        // w[1 + s .. n) (evals_cached_rev: suffix tables), then suffixes of out_point alone
+        const size_t sp = mem->eq_split;  // s = |in_point|
+        const size_t nlo = n - 1 - sp;    // |out_point|
+        const size_t hi_k = round < sp ? round : sp;          // hi table: eq(w[1 + hi_k .. 1 + s))
+        const size_t lo_k = round < sp ? 0 : round - sp;      // lo table: eq(w[1 + s + lo_k .. n))
+        er.e_out = mem->eq_tabs + 4 * mem->eq_hi_off[hi_k];
+        er.e_in = mem->eq_tabs + 4 * mem->eq_lo_off[lo_k];
+        er.in_bits = (int)(nlo - lo_k);
+        cur_var = round;
+    }
     // the current variable's linear factor l(t) = l0 + t (l1 - l0) is known before the pass runs
     const HostFr scalar = HostFr::from_limbs(mem->eq_scalar);
-    const HostFr wc = HostFr::from_limbs(mem->eq_w.data() + 4 * (cur - 1));
+    const HostFr wc = HostFr::from_limbs(mem->eq_w.data() + 4 * cur_var);
     const HostFr l1 = scalar * wc, l0 = scalar - l1;
     if (l1.is_zero()) return c->fail(JB_ERR_INVALID, "eq member: current eq evaluation at one must be invertible");
     int st = member_round(mem, bind, true, nullptr, &er);
@@ -617,7 +639,7 @@ static int eq_prove_round(jb_member* mem, const uint64_t* bind, size_t round, co
 int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint64_t* w, size_t nvars,
                         const uint64_t* scale_or_null, int order, jb_member** out) {
     if (!c || !handles || !w || !out) return JB_ERR_INVALID;
-    if (order != JB_LOW_TO_HIGH) return c->fail(JB_ERR_UNSUPPORTED, "eq member: LowToHigh binding only");
+    if (order != JB_LOW_TO_HIGH && order != JB_HIGH_TO_LOW) return c->fail(JB_ERR_INVALID, "eq member: unknown binding order");
     if (m < 1 || m > 3) return c->fail(JB_ERR_UNSUPPORTED, "eq member: m must be 1..3");
     for (size_t i = 0; i < nvars; ++i)
         if (!canonical_fr(w + 4 * i)) return c->fail(JB_ERR_INVALID, "eq member: point limbs not canonical");
@@ -638,16 +660,38 @@ int jb_eq_member_create(jb_ctx* c, const jb_table* handles, size_t m, const uint
     mem->eq_w.assign(w, w + 4 * nvars);
     HostFr sc = scale_or_null ? HostFr::from_limbs(scale_or_null) : HostFr::one();
     sc.store(mem->eq_scalar);
-    // prefix tables (EqPolynomial::evals_cached, eq.rs:322-340): Eo[k] over w[0..k), Ei[k] over w[split..split+k)
-    const size_t split = mem->eq_split, nin = nvars - 1 - (split < nvars - 1 ? split : nvars - 1);
-    const size_t out_max = split < nvars - 1 ? split : nvars - 1;
-    mem->eq_in_base = ((size_t)2 << out_max) - 1;
-    const size_t total = mem->eq_in_base + ((size_t)2 << nin) - 1;
-    st = c->dev_alloc((void**)&mem->eq_tabs, total * 32);
-    for (size_t k = 0; k <= out_max && st == JB_OK; ++k)
-        st = eq_build(c, w, k, nullptr, mem->eq_tabs + 4 * (((size_t)1 << k) - 1));
-    for (size_t k = 0; k <= nin && st == JB_OK; ++k)
-        st = eq_build(c, w + 4 * split, k, nullptr, mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << k) - 1));
+    if (order == JB_LOW_TO_HIGH) {
+        // prefix tables (EqPolynomial::evals_cached, eq.rs:322-340): Eo[k] over w[0..k), Ei[k] over w[split..split+k)
+        const size_t split = mem->eq_split, nin = nvars - 1 - (split < nvars - 1 ? split : nvars - 1);
+        const size_t out_max = split < nvars - 1 ? split : nvars - 1;
+        mem->eq_in_base = ((size_t)2 << out_max) - 1;
+        const size_t total = mem->eq_in_base + ((size_t)2 << nin) - 1;
+        st = c->dev_alloc((void**)&mem->eq_tabs, total * 32);
+        for (size_t k = 0; k <= out_max && st == JB_OK; ++k)
+            st = eq_build(c, w, k, nullptr, mem->eq_tabs + 4 * (((size_t)1 << k) - 1));
+        for (size_t k = 0; k <= nin && st == JB_OK; ++k)
+            st = eq_build(c, w + 4 * split, k, nullptr, mem->eq_tabs + 4 * (mem->eq_in_base + ((size_t)1 << k) - 1));
+    } else {
+        // HighToLow (split_eq.rs:233-257): tail = w[1..], in_point = tail[..s], out_point = tail[s..] with
+        // s = min(n / 2, n - 1); suffix tables (evals_cached_rev): hi[k] = eq(w[1 + k .. 1 + s)), lo[j] = eq(w[1 + s + j .. n))
+        const size_t sp = mem->eq_split < nvars - 1 ? mem->eq_split : nvars - 1;
+        mem->eq_split = sp;
+        const size_t nlo = nvars - 1 - sp;
+        size_t total = 0;
+        for (size_t k = 0; k <= sp; ++k) {
+            mem->eq_hi_off.push_back(total);
+            total += (size_t)1 << (sp - k);
+        }
+        for (size_t j = 0; j <= nlo; ++j) {
+            mem->eq_lo_off.push_back(total);
+            total += (size_t)1 << (nlo - j);
+        }
+        st = c->dev_alloc((void**)&mem->eq_tabs, total * 32);
+        for (size_t k = 0; k <= sp && st == JB_OK; ++k)
+            st = eq_build(c, w + 4 * (1 + k), sp - k, nullptr, mem->eq_tabs + 4 * mem->eq_hi_off[k]);
+        for (size_t j = 0; j <= nlo && st == JB_OK; ++j)
+            st = eq_build(c, w + 4 * (1 + sp + j), nlo - j, nullptr, mem->eq_tabs + 4 * mem->eq_lo_off[j]);
+    }
     }  // the context lock is released before the member is torn down (jb_member_destroy takes it)
     if (st != JB_OK) {
         jb_member_destroy(mem);
@@ -921,8 +965,9 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     if (!canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "finish_rounds: challenge limbs not canonical");
     if (mem->eq) {
         size_t var = 0;
-        for (size_t l = mem->len; l > 2; l >>= 1) ++var;  // index of the variable being bound (LowToHigh)
-        eq_absorb_bind(mem, var, bind);
+        for (size_t l = mem->len; l > 2; l >>= 1) ++var;  // unbound variables besides the one being bound
+        // LowToHigh binds w[var] (the most significant unbound one is w[0]); HighToLow binds w[n - 1 - var]
+        eq_absorb_bind(mem, mem->order == JB_LOW_TO_HIGH ? var : mem->eq_n - 1 - var, bind);
     }
     if (mem->run) {
         // the terminal bind is one more mailbox command; a fully bound member gets its values back with the

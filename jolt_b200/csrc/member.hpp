@@ -77,6 +77,7 @@ struct jb_member {
     uint64_t eq_scalar[4] = {0, 0, 0, 0};
     uint64_t* eq_tabs = nullptr;       // prefix tables Eo[k] (k <= split) then Ei[k] (k <= n-1-split), table k at 2^k - 1
     size_t eq_in_base = 0;             // element offset of the Ei family
+    std::vector<size_t> eq_hi_off, eq_lo_off;  // HighToLow: element offsets of the suffix tables (see jb_eq_member_create)
     // resident service (resident.cuh): the launched kernel that serves this member's rounds from a mailbox
     ResidentRun* run = nullptr;
     int run_idx = 0;

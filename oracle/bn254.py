@@ -481,6 +481,32 @@ def g1_msm_pippenger(bases, scalars, c: int | None = None):
     return total
 
 
+def batch_g1_additions_multi_affine(bases, indices_sets, q: int = Q_MOD):
+    """crates/jolt-crypto/src/ec/bn254/batch_addition.rs:53-150: one affine sum per index set. Every level pairs
+    neighbours (2j, 2j + 1) of each working set, all pairs of a level share one batch inversion (ark_ff's
+    batch_inversion leaves zero elements zero, :101-105), lambda = (y2 - y1) inv, x3 = lambda^2 - x1 - x2,
+    y3 = lambda (x1 - x3) - y1 (:121-125), an odd last element moves up unchanged (:136-140). Points are (x, y)
+    integer pairs; the identity (empty set, :69-70) is None. The distinct-x precondition is NOT checked, as in the
+    reference: a violating pair gets inv = 0 and an off-curve result."""
+    work = [[None] if not idx else [bases[i] for i in idx] for idx in indices_sets]
+    while any(len(w) >= 2 for w in work):
+        nxt = []
+        for w in work:
+            row = []
+            for j in range(len(w) // 2):
+                (x1, y1), (x2, y2) = w[2 * j], w[2 * j + 1]
+                d = (x2 - x1) % q
+                inv = pow(d, -1, q) if d else 0
+                lam = (y2 - y1) * inv % q
+                x3 = (lam * lam - x1 - x2) % q
+                row.append((x3, (lam * (x1 - x3) - y1) % q))
+            if len(w) % 2:
+                row.append(w[-1])
+            nxt.append(row)
+        work = nxt
+    return [w[0] for w in work]
+
+
 # --------------------------------------------------------------------------- #
 # HyperKZG prover side (crates/jolt-hyperkzg/src/scheme.rs:54-158, kzg.rs:15-126)
 # --------------------------------------------------------------------------- #

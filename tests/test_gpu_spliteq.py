@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 import jolt_b200
-from jolt_b200 import BatchMember, EqPolynomial, EqProductMember, LOW_TO_HIGH, Polynomial, ProductMember, UnivariatePoly
+from jolt_b200 import (BatchMember, EqPolynomial, EqProductMember, HIGH_TO_LOW, LOW_TO_HIGH, Polynomial, ProductMember,
+                       UnivariatePoly)
 from jolt_b200 import field as F
 from oracle import bn254 as O
 from oracle import coracle as C
@@ -21,14 +22,15 @@ def sess():
     s.close()
 
 
+@pytest.mark.parametrize("order", [LOW_TO_HIGH, HIGH_TO_LOW])
 @pytest.mark.parametrize("m", [1, 2, 3])
-@pytest.mark.parametrize("n", [1, 2, 5, 9])
-def test_eq_member_lockstep_vs_oracle(sess, m, n):
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 9, 12])
+def test_eq_member_lockstep_vs_oracle(sess, m, n, order):
     tabs = [O.random_fr(300 + 10 * m + j, 1 << n) for j in range(m)]
     w = O.random_fr(77 + n, n)
     eq_tab = O.eq_evals(w)                                    # r[0] <-> MSB (eq.rs:218-219)
-    ref = O.ProductMember([eq_tab] + tabs, O.LOW_TO_HIGH)
-    gpu = EqProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs], C.ints_to_mont(w))
+    ref = O.ProductMember([eq_tab] + tabs, order)
+    gpu = EqProductMember(sess, [Polynomial.from_ints(sess, t) for t in tabs], C.ints_to_mont(w), order=order)
     assert gpu.num_rounds() == n and gpu.degree() == m + 1
     claim = sum(eq_tab[i] * int(np.prod([t[i] for t in tabs], dtype=object)) for i in range(1 << n)) % O.R_MOD
     ch = O.random_fr(5, n)
@@ -43,7 +45,7 @@ def test_eq_member_lockstep_vs_oracle(sess, m, n):
     gpu.finish_rounds(bind)
     fe = ref.final_evals()
     assert gpu.final_evals() == fe[1:]
-    assert gpu.eq_scalar() == fe[0]                          # eq(w, r) with the LowToHigh challenge order
+    assert gpu.eq_scalar() == fe[0]                          # eq(w, r) with the order's challenge-to-variable map
     assert gpu.eq_scalar() * int(np.prod(gpu.final_evals(), dtype=object)) % O.R_MOD == claim
 
 

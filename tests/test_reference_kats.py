@@ -110,3 +110,22 @@ def test_g1_published_alt_bn128_vectors():
     for k, want in ((2, two_g), (3, three_g)):
         xy, inf = C.g1_msm_naive(g_limbs, C.ints_to_mont([k]))
         assert not inf and (O.from_mont_limbs(xy[:4], O.Q_MOD), O.from_mont_limbs(xy[4:], O.Q_MOD)) == want
+
+
+def test_batch_addition_restatement_matches_group_sums_and_reference_edge_cases():
+    """crates/jolt-crypto/src/ec/bn254/batch_addition.rs:160-240 replayed on the oracle restatement: empty set ->
+    identity, singleton -> the base, a pair -> the group sum, random unique-index sets -> the projective sums."""
+    import random
+    # "random" points as in the reference's test (G1Affine::rand): structured multiples k G would let partial sums
+    # collide (2G + 3G meets 5G) and trip the distinct-x precondition
+    pts = [O.g1_scalar_mul((1, 2), k) for k in O.random_fr(77, 40)]
+    res = O.batch_g1_additions_multi_affine(pts, [[], [2], [0, 3]])
+    assert res[0] is None and res[1] == pts[2] and res[2] == O.g1_add(pts[0], pts[3])
+    assert O.batch_g1_additions_multi_affine(pts, []) == []
+    rnd = random.Random(5)
+    sets = [rnd.sample(range(40), rnd.randint(1, 17)) for _ in range(6)]
+    for got, st in zip(O.batch_g1_additions_multi_affine(pts, sets), sets):
+        acc = None
+        for i in st:
+            acc = O.g1_add(acc, pts[i])
+        assert got == acc and O.g1_is_on_curve(got)
