@@ -452,22 +452,42 @@ static int run_round(jb_ctx* c, ResidentRun* run, RunItem* items, int n, const u
     if (st != JB_OK) return st;
     uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
     ResConsumed info[RES_MAX_MEMBERS];
-    while (resident_inflight(run) > 1) {  // the previous command's answer: it carries this round's lookahead
+    bool lost = false;
+    while (!lost && resident_inflight(run) > 1) {  // the previous command's answer: it carries this round's lookahead
         st = resident_consume(run, out, info);
-        if (st != JB_OK) return st;
-        for (int i = 0; i < rn; ++i) harvest_lookahead(mems[i], info[i], out + (size_t)i * RES_SLOT_U64);
+        if (st == JB_RES_LOST) lost = true;
+        else if (st != JB_OK) return st;
+        else for (int i = 0; i < rn; ++i) harvest_lookahead(mems[i], info[i], out + (size_t)i * RES_SLOT_U64);
     }
     uint64_t vals[RES_MAX_MEMBERS][JB_MAX_EVALS * 4];
     bool hit[RES_MAX_MEMBERS], need_now = false;
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n && !lost; ++i) {
         jb_member* m = items[i].mem;
         hit[i] = c->lookahead && items[i].bind && m->look_ok && m->look_round == items[i].round && m->m == 2;
         if (hit[i]) lookahead_values(m, items[i].bind, vals[i]);
         else need_now = true;
     }
-    if (need_now) {
+    if (need_now && !lost) {
         st = resident_consume(run, out, info);  // (cannot release the run: the members of this round are not fully bound)
+        if (st == JB_RES_LOST) lost = true;
+        else if (st != JB_OK) return st;
+    }
+    if (lost) {
+        // the kernel gave up waiting (the host was held up): replay the unexecuted binds with launches and compute
+        // this round's sums with one eval-only launch per member - the proof is unchanged, only slower
+        st = resident_recover(run);
         if (st != JB_OK) return st;
+        for (int i = 0; i < n; ++i) {
+            jb_member* m = items[i].mem;
+            st = member_round(m, nullptr, true, nullptr);
+            if (st == JB_OK) st = wait_round_result0(c);
+            if (st == JB_OK) st = assemble_evals(c, m->m, true, c->h_result, items[i].claim, items[i].round, items[i].out_evals);
+            if (st != JB_OK) return st;
+            m->rounds_done++;
+        }
+        return JB_OK;
+    }
+    if (need_now) {
         for (int i = 0; i < n; ++i)
             if (!hit[i]) {
                 const int idx = items[i].mem->run_idx;
@@ -506,6 +526,7 @@ static int resident_member_final(jb_member* mem, const uint64_t* bind) {
     unsigned actions[RES_MAX_MEMBERS] = {0};
     actions[mem->run_idx] = RES_ACT_FINAL;
     int st = resident_round(mem->run, actions, bind, false, nullptr);
+    if (st == JB_RES_LOST) return resident_recover(mem->run);  // (replays the terminal bind with a launch)
     if (st != JB_OK && mem->run) resident_end(mem->run, true);
     return st;
 }
@@ -1175,10 +1196,14 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
                 int st = JB_OK;
                 while (st == JB_OK && resident_inflight(m->run) > 0) st = resident_consume(m->run, nullptr, nullptr);
                 if (st == JB_OK) st = resident_post(m->run, actions, bind, false);
+                if (st == JB_RES_LOST) st = resident_recover(m->run);  // back to launches (below)
+                else if (st != JB_OK) return st;
+                else {
+                    m->look_ok = false;
+                    via[i] = VIA_RUN;
+                    continue;
+                }
                 if (st != JB_OK) return st;
-                m->look_ok = false;
-                via[i] = VIA_RUN;
-                continue;
             }
         }
         if (m->run) resident_end(m->run, true);
@@ -1194,7 +1219,12 @@ int jb_scheduler_prove_round(jb_scheduler* s, const jb_round_work* work, size_t 
             uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
             ResConsumed info[RES_MAX_MEMBERS];
             st = resident_consume(m->run, out, info);
-            if (st == JB_OK) {
+            if (st == JB_RES_LOST) {  // recover (replays this round's bind), then an eval-only launch
+                st = resident_recover(m->run);
+                if (st == JB_OK) st = member_round(m, nullptr, true, nullptr);
+                if (st == JB_OK) st = wait_round_result0(c);
+                if (st == JB_OK) st = assemble_evals(c, m->m, true, c->h_result, w.claim, w.round, out_evals + i * JB_MAX_EVALS * 4);
+            } else if (st == JB_OK) {
                 uint64_t vals[JB_MAX_EVALS * 4];
                 answer_values(m, info[0], out, vals);
                 st = assemble_evals(c, m->m, true, vals, w.claim, w.round, out_evals + i * JB_MAX_EVALS * 4);
@@ -1230,7 +1260,8 @@ int jb_scheduler_finish_rounds(jb_scheduler* s, const jb_finish_work* work, size
         if (one_run && run) {
             unsigned actions[RES_MAX_MEMBERS] = {0};
             for (size_t i = 0; i < n_work; ++i) actions[s->members[work[i].member]->run_idx] = RES_ACT_FINAL;
-            return resident_round(run, actions, work[0].bind, false, nullptr);
+            int st = resident_round(run, actions, work[0].bind, false, nullptr);
+            return st == JB_RES_LOST ? resident_recover(run) : st;
         }
     }
     for (size_t i = 0; i < n_work; ++i) {

@@ -118,6 +118,7 @@ struct ResidentRun {
     jb_member* mem[jb::RES_MAX_MEMBERS] = {nullptr};
     unsigned grid = 0;
     ResConsumed ring[2][jb::RES_MAX_MEMBERS];  // what command s (slot s & 1) asked of every member
+    uint64_t ring_challenge[2][4];             // ... and the challenge it carried (to replay it if the kernel is lost)
     struct RoundInfo { int kind; uint64_t items; int m; };
     RoundInfo info[64];                       // what command s (< 64) asked for, for the device-timed pass log
     uint64_t host_post[64], host_recv[64];    // CLOCK_MONOTONIC ns (diagnostics)
@@ -134,6 +135,14 @@ struct ResidentRun {
 int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange);
 int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info);
 int resident_inflight(const ResidentRun* run);
+// resident_consume returns JB_RES_LOST when the kernel gave up waiting for commands (the host was held up for
+// ~10 s: a debugger, a tool patching a module, an absorb callback that blocks) and exited WITHOUT executing the
+// commands still in flight. The tables are consistent at the last executed round. resident_recover then replays
+// the unexecuted commands' binds with ordinary launches (the host's view of the tables is exact again), releases the
+// run and marks its members for one launch per round; the caller recomputes the current round's sums with an
+// eval-only launch. A member never fails because its resident kernel went away.
+constexpr int JB_RES_LOST = -1000;
+int resident_recover(ResidentRun* run);
 int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out);
 int resident_run_size(const ResidentRun* run);
 // Stops the kernel (if it still runs), orders the context's stream after it and detaches the members.

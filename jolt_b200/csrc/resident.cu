@@ -230,7 +230,7 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_len, bool 
     std::memset(run->mb, 0, sizeof(ResMailbox));
     args.mb = (ResMailbox*)run->res.mb_dev;
     args.st = (ResState*)run->res.d_state;
-    args.timeout_cycles = 20000000000LL;  // ~10 s of SM clocks without a command: give the SMs back
+    args.timeout_cycles = c->resident_timeout_cycles;  // ~10 s of SM clocks without a command: give the SMs back
     args.world = c->world;
     args.rank = c->rank;
     for (int g = 0; g < 16; ++g) args.peer[g] = c->xch_peer[g];
@@ -296,7 +296,10 @@ int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* cha
         }
     }
     line->cmd = cmd;
-    if (challenge) std::memcpy((void*)line->challenge, challenge, 32);
+    if (challenge) {
+        std::memcpy((void*)line->challenge, challenge, 32);
+        std::memcpy(run->ring_challenge[seq & 1], challenge, 32);
+    }
     run->seq = seq;
     if (seq <= 64) {
         run->info[seq - 1] = ri;
@@ -317,8 +320,8 @@ int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info) {
     if (seq <= 64) run->host_recv[seq - 1] = now_ns();
     if (mb->ans[seq & 1].status != 0) {
         run->kernel_live = false;
-        return c->fail(JB_ERR_CUDA, mb->ans[seq & 1].status == 2 ? "peer exchange timed out (a rank did not arrive)"
-                                                                 : "resident kernel aborted (timeout)");
+        if (mb->ans[seq & 1].status == 2) return c->fail(JB_ERR_CUDA, "peer exchange timed out (a rank did not arrive)");
+        return JB_RES_LOST;  // the kernel stopped waiting for commands: nothing from `seq` on was executed
     }
     run->consumed = seq;
     const uint64_t* result = mb->result[seq & 1];
@@ -341,13 +344,52 @@ int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info) {
     return JB_OK;
 }
 
+int resident_recover(ResidentRun* run) {
+    jb_ctx* c = run->c;
+    run->kernel_live = false;
+    cudaStreamSynchronize(run->res.stream);  // the kernel has exited (it answered the lost command with status 1)
+    const uint64_t first = run->consumed + 1, last = run->seq;
+    // the host's view ran ahead of the device by the unexecuted commands: step it back ...
+    for (uint64_t q = last; q >= first; --q) {
+        const ResConsumed* slot = run->ring[q & 1];
+        for (int i = 0; i < run->n; ++i) {
+            if (slot[i].act != RES_ACT_BIND_EVAL && slot[i].act != RES_ACT_FINAL) continue;
+            jb_member* m = run->mem[i];
+            m->len *= 2;
+            for (auto& t : m->tables) {
+                if (m->order == JB_LOW_TO_HIGH) t.swap_buffers();
+                t.len = m->len;
+            }
+        }
+    }
+    // ... and replay their binds, in order, with ordinary launches
+    int st = JB_OK;
+    cudaEventRecord(run->res.event, run->res.stream);
+    cudaStreamWaitEvent(c->stream, run->res.event, 0);
+    for (uint64_t q = first; q <= last && st == JB_OK; ++q) {
+        const ResConsumed* slot = run->ring[q & 1];
+        for (int i = 0; i < run->n && st == JB_OK; ++i) {
+            if (slot[i].act != RES_ACT_BIND_EVAL && slot[i].act != RES_ACT_FINAL) continue;
+            jb_member* m = run->mem[i];
+            for (auto& t : m->tables) {
+                st = bind_table(c, t, run->ring_challenge[q & 1], m->order);
+                if (st != JB_OK) break;
+            }
+            if (st == JB_OK) m->len /= 2;
+        }
+    }
+    for (int i = 0; i < run->n; ++i) run->mem[i]->look_ok = false;
+    run->consumed = run->seq;
+    release_run(run, true);
+    return st;
+}
+
 int resident_round(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, uint64_t* out) {
     int st = JB_OK;
     while (st == JB_OK && run->consumed < run->seq) st = resident_consume(run, nullptr, nullptr);  // (never releases: a
-    if (st != JB_OK) return st;                                                                     //  round is still to come)
-    st = resident_post(run, actions, challenge, exchange);
-    if (st != JB_OK) return st;
-    return resident_consume(run, out, nullptr);
+    if (st == JB_OK) st = resident_post(run, actions, challenge, exchange);                         //  round is still to come)
+    if (st == JB_OK) st = resident_consume(run, out, nullptr);
+    return st;  // JB_RES_LOST: the caller recovers (resident_recover) and redoes the round with launches
 }
 
 void resident_end(ResidentRun* run, bool mark_no_resident) {
@@ -358,7 +400,12 @@ void resident_end(ResidentRun* run, bool mark_no_resident) {
         const bool last = run->consumed + 1 == run->seq;
         bool done = last;
         for (int i = 0; i < run->n && done; ++i) done = run->mem[i]->len < 2;
-        if (resident_consume(run, nullptr, nullptr) != JB_OK) break;
+        const int cs = resident_consume(run, nullptr, nullptr);
+        if (cs == JB_RES_LOST) {
+            resident_recover(run);  // replays the unexecuted binds and releases the run
+            return;
+        }
+        if (cs != JB_OK) break;
         if (done) {  // that consume released the run (every member fully bound)
             (void)c;
             return;

@@ -127,6 +127,38 @@ def test_resident_run_survives_interleaved_context_work(sess):
     assert prove(False) == prove(True)
 
 
+def test_lost_resident_kernel_is_recovered_with_launches(sess):
+    """a resident kernel that stops waiting for commands (the host was held up - here a 3 ms device
+    timeout and a host that sleeps) must not fail the member: the unexecuted binds are replayed with launches, the
+    round is recomputed, and the proof is the oracle's, both in thin (lookahead) and in generic rounds."""
+    import time
+    os.environ["JB_RESIDENT_TIMEOUT_S"] = "0.003"
+    try:
+        s2 = jolt_b200.Session(0)
+    finally:
+        del os.environ["JB_RESIDENT_TIMEOUT_S"]
+    for n, order, naps in ((9, LOW_TO_HIGH, (2, 5)), (9, HIGH_TO_LOW, (1, 2, 7)), (18, LOW_TO_HIGH, (1, 9, 16))):
+        tabs = [rand_limbs(0x7E57 + j, 1 << n) for j in range(2)]
+        gpu = ProductMember(s2, [Polynomial.new(s2, t) for t in tabs], order)
+        cur = [t.copy() for t in tabs]
+        bind, thr = None, C.max_threads()
+        for rnd in range(n):
+            if bind is not None:
+                cur = [C.bind(t, bind, order, thr) for t in cur]
+            want = C.mont_to_ints(C.product_round_evals(cur, 2, order, thr))
+            if rnd in naps:
+                time.sleep(0.05)      # far beyond the kernel's patience: it exits, possibly with commands in flight
+            got = gpu.prove_round_evals(bind, rnd, (want[0] + want[1]) % O.R_MOD)
+            assert got == want, f"n={n} round {rnd}"
+            bind = rand_challenge(4000 + rnd)
+        cur = [C.bind(t, bind, order, thr) for t in cur]
+        time.sleep(0.05)
+        gpu.finish_rounds(bind)
+        assert gpu.final_evals() == [C.mont_to_ints(t)[0] for t in cur]
+        gpu.close()
+    s2.close()
+
+
 # ---- sum of products: IncClaimReduction -------------------------------------------------------------------
 def inc_fixture(n, seed):
     pts = [O.synthetic_point(n, s) for s in (3, 5, 7, 11)]          # inc_claim_reduction.rs:236-241
