@@ -198,6 +198,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
     if (const char* ml = std::getenv("JB_RESIDENT_MAX_LOG")) c->resident_max_log = std::atoi(ml);
     if (const char* ts = std::getenv("JB_RESIDENT_TIMEOUT_S")) c->resident_timeout_cycles = (long long)(std::atof(ts) * 1.9e9);
+    if (std::getenv("JB_EVAL_TMA")) c->eval_tma = true;
     if (std::getenv("JB_NO_LOOKAHEAD")) c->lookahead = false;
     if (const char* es = std::getenv("JB_EQ_STORE")) c->eq_store_mode = std::atoi(es);
     if (const char* el = std::getenv("JB_EQ_LAYOUT")) c->eq_layout = std::atoi(el);  // diagnostics: every round waits for its own answer

@@ -143,9 +143,10 @@ int jb_comm_p2p_handle(jb_ctx* c, uint8_t out[64]) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     if (!c->xch_peer[c->rank]) {
         void* p = nullptr;
-        static_assert(jb::XCH_BYTES <= 65536, "exchange buffer too small");
-        if (cudaMalloc(&p, 65536) != cudaSuccess) return c->fail(JB_ERR_OOM, "p2p: exchange buffer");
-        cudaMemset(p, 0, 65536);
+        static_assert(jb::XCH_BYTES <= jb::XCH_ARENA_OFFSET, "exchange area too small");
+        // exchange slots + flags, then the gather arena (two halves)
+        if (cudaMalloc(&p, jb::XCH_TOTAL_BYTES) != cudaSuccess) return c->fail(JB_ERR_OOM, "p2p: exchange buffer");
+        cudaMemset(p, 0, jb::XCH_ARENA_OFFSET);
         cudaDeviceSynchronize();
         c->xch_peer[c->rank] = (uint64_t*)p;
     }

@@ -80,6 +80,7 @@ struct jb_ctx {
     std::vector<TailRes> tail_pool;
     uint64_t diag_wait_ns = 0, diag_waits = 0;  // host time spent waiting for round results
     bool use_tail = true;           // resident kernel service (off under profilers / JB_NO_TAIL: one launch per round)
+    bool eval_tma = false;          // A/B: TMA-staged variant of the degree-2 eval-only sweep (JB_EVAL_TMA=1)
     int eq_layout = 0;              // eq stream kernel: 0 = a warp writes 1 KiB runs (a thread's outputs 8 KiB apart), 1 = a thread's 8 outputs consecutive
     int eq_store_mode = -1;         // eq table stores: -1 auto, 0 default caching, 1 streaming (evict-first)
     long long resident_timeout_cycles = 20000000000LL;  // a resident kernel gives its SMs back after this long without a command
@@ -113,6 +114,7 @@ struct jb_ctx {
     uint64_t* xch_peer[16] = {nullptr};
     bool xch_ready = false;
     uint64_t xch_seq = 0;
+    uint64_t gather_seq = 0;  // gathers through the arena that follows the exchange area (parity = arena half)
     int comm_allreduce_lanes(uint64_t* d_lanes_buf, size_t n_u64);
     int comm_allgather(const uint64_t* d_send, uint64_t* d_recv, size_t n_u64_per_rank);
     int publish_lanes(const uint64_t* d_lanes_buf, int n_u64);

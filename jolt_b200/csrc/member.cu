@@ -15,6 +15,7 @@
 #include "member.hpp"
 #include "resident.cuh"
 #include "sumcheck_host.hpp"
+#include "tma_ab.cuh"
 
 using namespace jb;
 using namespace jbi;
@@ -54,8 +55,36 @@ int launch_fused_mb(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScal
     return c->check(cudaGetLastError(), "fused_round_kernel launch");
 }
 
+// A/B (JB_EVAL_TMA=1): the degree-2 eval-only sweep with its evaluation blocks staged by the TMA unit (tma_ab.cuh)
+template <int ORDER>
+int launch_eval2_tma(jb_ctx* c, const TablePtrs& tp, size_t pairs, RoundOut out) {
+    auto kernel = eval2_tma_kernel<ORDER>;
+    constexpr size_t smem = TmaShape::smem_bytes;
+    static int per_sm = [&] {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        return nb;
+    }();
+    size_t need = (pairs + TMA_TILE - 1) / TMA_TILE;
+    size_t resident = (size_t)c->sm_count * per_sm;
+    size_t grid = need < resident ? need : resident;
+    if (grid < 1) grid = 1;
+    int st = c->ensure_partial(grid * 2);
+    if (st != JB_OK) return st;
+    out.partial = c->d_partial;
+    int tix = c->timing_begin(2, pairs, 2);
+    kernel<<<(unsigned)grid, TMA_THREADS, smem, c->stream>>>(tp, pairs, out);
+    c->timing_end(tix);
+    c->launches++;
+    return c->check(cudaGetLastError(), "eval2_tma_kernel launch");
+}
+
 template <int M, int P, int ORDER, bool BIND, bool HI4, bool SKIP1>
 int launch_fused(jb_ctx* c, const TablePtrs& tp, size_t pairs, const BindScalar& s, const RoundOut& out) {
+    if constexpr (M == 2 && P == 1 && !BIND && SKIP1) {
+        if (c->eval_tma && pairs >= 4096) return launch_eval2_tma<ORDER>(c, tp, pairs, out);
+    }
     // occupancy shapes (tuning knob JB_FUSED_SHAPE): 0 = 256 threads x 2 blocks (128 registers),
     // 1 = 128 threads x 5 blocks (<= 102 registers, 20 warps/SM)
     if constexpr (M == 2 && P == 1) {
@@ -442,13 +471,14 @@ struct RunItem {
 // One round of `n` members of one run: ONE mailbox command. Members whose previous answer carried lookahead sums
 // are answered at once from those (their command stays in flight: the device's bind + next sums overlap the
 // caller's Fiat-Shamir step); the others wait for this command's own answer.
-static int run_round(jb_ctx* c, ResidentRun* run, RunItem* items, int n, const uint64_t* shared_bind, bool exchange) {
+static int run_round(jb_ctx* c, ResidentRun* run, RunItem* items, int n, const uint64_t* shared_bind, bool exchange,
+                     bool gather = false) {
     unsigned actions[RES_MAX_MEMBERS] = {0};
     for (int i = 0; i < n; ++i) actions[items[i].mem->run_idx] = items[i].bind ? RES_ACT_BIND_EVAL : RES_ACT_EVAL;
     jb_member* mems[RES_MAX_MEMBERS];
     const int rn = run->n;
     for (int i = 0; i < rn; ++i) mems[i] = run->mem[i];
-    int st = resident_post(run, actions, shared_bind, exchange);
+    int st = resident_post(run, actions, shared_bind, exchange, gather);
     if (st != JB_OK) return st;
     uint64_t out[RES_MAX_MEMBERS * RES_SLOT_U64];
     ResConsumed info[RES_MAX_MEMBERS];
@@ -507,7 +537,7 @@ static int run_round(jb_ctx* c, ResidentRun* run, RunItem* items, int n, const u
 // This round of one member through its resident kernel (starting one if the member is eligible). Returns
 // JB_ERR_UNSUPPORTED if the member is not served by a run: the caller launches instead.
 static int resident_member_prove(jb_member* mem, const uint64_t* bind, const uint64_t* claim, size_t round, bool exchange,
-                                 uint64_t* out_evals) {
+                                 uint64_t* out_evals, bool gather = false) {
     jb_ctx* c = mem->ctx;
     if (!mem->run) {
         if (!resident_eligible(mem)) return JB_ERR_UNSUPPORTED;
@@ -516,7 +546,7 @@ static int resident_member_prove(jb_member* mem, const uint64_t* bind, const uin
         if (st != JB_OK) return st;
     }
     RunItem it{mem, bind, claim, round, out_evals};
-    int st = run_round(c, mem->run, &it, 1, bind, exchange);
+    int st = run_round(c, mem->run, &it, 1, bind, exchange, gather);
     if (st != JB_OK && mem->run) resident_end(mem->run, true);
     return st;
 }
@@ -787,6 +817,22 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
         Guard g(c, true);
         if (round != mem->rounds_done) return c->fail(JB_ERR_INVALID, "prove_round: round index out of sequence");
         if (bind && !canonical_fr(bind)) return c->fail(JB_ERR_INVALID, "prove_round: challenge limbs not canonical");
+        if (mem->gathered) {
+            // gathered inside the resident kernel: an ordinary member from here on
+            if (bind && mem->len < 4) return c->fail(JB_ERR_INVALID, "prove_round: no round left after this bind (use finish_rounds)");
+            const bool skip1 = claim != nullptr && !c->verify_rounds;
+            int st = JB_ERR_UNSUPPORTED;
+            if (skip1) {
+                st = resident_member_prove(mem, bind, claim, round, false, out_evals);
+                if (st == JB_OK) mem->rounds_done--;
+                if (st != JB_ERR_UNSUPPORTED) return st;
+            }
+            before_launch(mem);
+            st = member_round(mem, bind, skip1, nullptr);
+            if (st == JB_OK) st = wait_round_result0(c);
+            if (st != JB_OK) return st;
+            return assemble_evals(c, mem->m, skip1, c->h_result, claim, round, out_evals);
+        }
         if (!mem->tail) {
             const size_t len_after = bind ? mem->len / 2 : mem->len;
             if (len_after > mem->gather_len) {
@@ -820,8 +866,22 @@ static int sharded_prove_round(jb_member* mem, const uint64_t* bind, size_t roun
                 if (st != JB_OK) return st;
                 return assemble_evals(c, mem->m, skip1, vals, claim, round, out_evals);
             }
-            // the shard is small: stop the resident kernel (its tables are consistent at a round boundary),
-            // apply the pending bind, gather, continue on the tail
+            // the shard is small. If its resident kernel is alive and the arena holds the gathered tables, the
+            // kernel itself gathers: it binds, writes the bound shard into every rank's arena over NVLink, waits for
+            // the peers' shards and sweeps the gathered tables - no kernel exit, no NCCL call; from here on this
+            // member proves its remaining rounds un-sharded (identically on every rank)
+            const bool skip1g = claim != nullptr && !c->verify_rounds;
+            if (bind && skip1g && mem->run && len_after == mem->gather_len && resident_gather_fits(c, mem, len_after) &&
+                !std::getenv("JB_NCCL_GATHER")) {
+                int st = resident_member_prove(mem, bind, claim, round, false, out_evals, true);
+                if (st == JB_OK) {
+                    mem->rounds_done--;  // (the caller counts sharded rounds)
+                    mem->gathered = true;
+                }
+                return st;
+            }
+            // otherwise: stop the resident kernel (its tables are consistent at a round boundary),
+            // apply the pending bind, gather with NCCL, continue on the tail
             if (mem->run) resident_end(mem->run, false);
             c->quiesce_resident(false);
             if (bind) {
@@ -977,7 +1037,7 @@ int jb_member_export_table(jb_member* mem, size_t j, void* device_dst, size_t ca
 int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
     if (!mem || !bind) return JB_ERR_INVALID;
     jb_ctx* c = mem->ctx;
-    if (mem->sharded) {
+    if (mem->sharded && !mem->gathered) {
         if (!mem->tail) return c->fail(JB_ERR_INVALID, "finish_rounds: sharded member has not reached its tail");
         return jb_member_finish_rounds(mem->tail, bind);
     }
@@ -1007,7 +1067,7 @@ int jb_member_finish_rounds(jb_member* mem, const uint64_t bind[4]) {
 int jb_member_final_evals(jb_member* mem, uint64_t* out) {
     if (!mem || !out) return JB_ERR_INVALID;
     jb_ctx* c = mem->ctx;
-    if (mem->sharded) {
+    if (mem->sharded && !mem->gathered) {
         if (!mem->tail) return c->fail(JB_ERR_INVALID, "NotFullyBound (sharded member before its tail)");
         return jb_member_final_evals(mem->tail, out);
     }

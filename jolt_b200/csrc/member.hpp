@@ -67,6 +67,7 @@ struct jb_member {
     bool sharded = false;
     size_t gather_len = 0;
     jb_member* tail = nullptr;
+    bool gathered = false;  // the shards were gathered inside the resident kernel: the member continues un-sharded
     // split-eq member (GruenSplitEqPolynomial, crates/jolt-poly/src/split_eq.rs:159-447): the relation is
     // sum_x eq(w, x) prod_j f_j(x); eq is never materialised - per round the sweep is weighted by
     // E_out (x) E_in over the not-yet-current variables and the current variable's linear factor
@@ -119,6 +120,8 @@ struct ResidentRun {
     unsigned grid = 0;
     ResConsumed ring[2][jb::RES_MAX_MEMBERS];  // what command s (slot s & 1) asked of every member
     uint64_t ring_challenge[2][4];             // ... and the challenge it carried (to replay it if the kernel is lost)
+    bool ring_gather[2] = {false, false};      // ... and whether it was a gather (not replayable)
+    std::vector<Table> deferred;               // shard buffers a gather made obsolete: freed when the run ends
     struct RoundInfo { int kind; uint64_t items; int m; };
     RoundInfo info[64];                       // what command s (< 64) asked for, for the device-timed pass log
     uint64_t host_post[64], host_recv[64];    // CLOCK_MONOTONIC ns (diagnostics)
@@ -132,7 +135,10 @@ struct ResidentRun {
 // member (lanes, see resident.cuh; with `exchange` member 0's lanes are all-reduced over the ranks), `info` what
 // the command had asked. The run is released when every member is fully bound and nothing is in flight (the run
 // pointer is dead after that: check mem->run). round = drain + post + consume.
-int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange);
+// gather (single-member run of an index-sharded member, action BIND_EVAL): bind, scatter the bound shard into every
+// rank's arena and sweep the gathered tables; afterwards the member's tables ARE its arena views (len x world).
+int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, bool gather = false);
+bool resident_gather_fits(const jb_ctx* c, const jb_member* mem, uint64_t shard_len_after_bind);
 int resident_consume(ResidentRun* run, uint64_t* out, ResConsumed* info);
 int resident_inflight(const ResidentRun* run);
 // resident_consume returns JB_RES_LOST when the kernel gave up waiting for commands (the host was held up for

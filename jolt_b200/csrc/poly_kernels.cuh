@@ -129,7 +129,15 @@ struct RoundOut {
 };
 constexpr int XCH_SLOT_U64 = 136;                // u64 lanes per (parity, source) slot (a thin round: 8 sums x 17 lanes)
 constexpr int XCH_FLAG_BASE = 2 * 16 * XCH_SLOT_U64;  // flags[parity][source] follow the slots
-constexpr size_t XCH_BYTES = (size_t)(XCH_FLAG_BASE + 2 * 16) * 8;
+constexpr int XCH_GFLAG_BASE = XCH_FLAG_BASE + 2 * 16;  // gather barrier flags [parity][source]
+constexpr size_t XCH_BYTES = (size_t)(XCH_GFLAG_BASE + 2 * 16) * 8;
+// The same IPC allocation continues with the GATHER ARENA: once a sharded member's shards are short, every rank
+// writes its bound shard straight into every peer's arena (NVLink stores from inside the resident kernel) and all
+// ranks finish the remaining rounds on the gathered tables - no kernel exit, no NCCL all-gather. Two halves
+// (parity of the context's gather count): a rank can be at most one gather ahead of a peer.
+constexpr size_t XCH_ARENA_OFFSET = 65536;                   // bytes from the start of the allocation
+constexpr size_t XCH_ARENA_HALF = (size_t)16 << 20;          // bytes per parity half
+constexpr size_t XCH_TOTAL_BYTES = XCH_ARENA_OFFSET + 2 * XCH_ARENA_HALF;
 
 template <class F>
 __device__ __forceinline__ F ld_elem_cg(const uint64_t* base, size_t idx) {

@@ -132,6 +132,7 @@ void release_run(ResidentRun* run, bool mark_no_resident) {
     // later work on the context's stream is ordered after the kernel's exit
     cudaEventRecord(run->res.event, run->res.stream);
     cudaStreamWaitEvent(c->stream, run->res.event, 0);
+    for (auto& t : run->deferred) c->release(t);
     c->tail_pool.push_back(run->res);
     for (int i = 0; i < run->n; ++i) {
         if (run->mem[i]) {
@@ -259,7 +260,13 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_len, bool 
 
 int resident_inflight(const ResidentRun* run) { return run ? (int)(run->seq - run->consumed) : 0; }
 
-int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange) {
+bool resident_gather_fits(const jb_ctx* c, const jb_member* mem, uint64_t np) {
+    // per table: the gathered table (world x np) and its ping-pong partner (half of it)
+    const uint64_t glen = np * (uint64_t)c->world;
+    return c->xch_ready && c->world <= 16 && (uint64_t)mem->ntables() * (glen + glen / 2) * 32 <= XCH_ARENA_HALF;
+}
+
+int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* challenge, bool exchange, bool gather) {
     jb_ctx* c = run->c;
     if (!run->kernel_live) return c->fail(JB_ERR_INVALID, "resident run is not live");
     if (run->seq - run->consumed >= 2) return c->fail(JB_ERR_INVALID, "resident run: two commands already in flight");
@@ -271,7 +278,13 @@ int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* cha
         cmd |= RES_FLAG_EXCHANGE;
         line->xseq = ++c->xch_seq;
     }
+    if (gather) {
+        if (run->n != 1 || (actions[0] & 0xf) != RES_ACT_BIND_EVAL || exchange) return c->fail(JB_ERR_INVALID, "resident gather: one member, one bind");
+        cmd |= RES_FLAG_GATHER;
+        line->xseq = ++c->gather_seq;
+    }
     ResConsumed* slot = run->ring[seq & 1];
+    run->ring_gather[seq & 1] = gather;
     ResidentRun::RoundInfo ri{-1, 0, 0};
     for (int i = 0; i < run->n; ++i) {
         jb_member* m = run->mem[i];
@@ -279,6 +292,28 @@ int resident_post(ResidentRun* run, const unsigned* actions, const uint64_t* cha
         cmd |= (uint64_t)a << (16 + 4 * i);
         slot[i].act = a;
         slot[i].round = m->rounds_done;
+        if (gather) {
+            // the member leaves its shard for the gathered tables in this rank's arena (views, not owned)
+            const uint64_t np = m->len / 2, glen = np * (uint64_t)c->world;
+            uint64_t* arena = c->xch_peer[c->rank] + (XCH_ARENA_OFFSET + (size_t)(c->gather_seq & 1) * XCH_ARENA_HALF) / 8;
+            const int T = m->ntables();
+            for (int j = 0; j < T; ++j) {
+                Table& t = m->tables[j];
+                run->deferred.push_back(t);  // (the kernel still reads the shard while it executes this command)
+                t.buf = arena + (size_t)j * glen * 4;
+                t.alt = arena + (size_t)T * glen * 4 + (size_t)j * (glen / 2) * 4;
+                t.cap = t.len = glen;
+                t.alt_cap = glen / 2;
+                t.buf_owned = t.alt_owned = false;
+            }
+            m->len = glen;
+            slot[i].nprime = glen;
+            slot[i].thin = res_is_thin(m->m, glen);
+            ri.kind = 0;
+            ri.items += glen / 2;
+            ri.m = T;
+            continue;
+        }
         slot[i].nprime = a == RES_ACT_BIND_EVAL ? m->len / 2 : m->len;
         slot[i].thin = (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) && res_is_thin(m->m, slot[i].nprime);
         if (a == RES_ACT_EVAL || a == RES_ACT_BIND_EVAL) {
@@ -349,6 +384,11 @@ int resident_recover(ResidentRun* run) {
     run->kernel_live = false;
     cudaStreamSynchronize(run->res.stream);  // the kernel has exited (it answered the lost command with status 1)
     const uint64_t first = run->consumed + 1, last = run->seq;
+    for (uint64_t q = first; q <= last; ++q)
+        if (run->ring_gather[q & 1]) {
+            release_run(run, true);
+            return c->fail(JB_ERR_CUDA, "resident kernel lost during a cross-rank gather (not replayable)");
+        }
     // the host's view ran ahead of the device by the unexecuted commands: step it back ...
     for (uint64_t q = last; q >= first; --q) {
         const ResConsumed* slot = run->ring[q & 1];

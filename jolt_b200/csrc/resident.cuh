@@ -50,6 +50,9 @@ constexpr int RES_SLOT_U64 = 136;
 enum : unsigned { RES_ACT_NONE = 0, RES_ACT_EVAL = 1, RES_ACT_BIND_EVAL = 2, RES_ACT_FINAL = 3 };
 enum : uint64_t { RES_OP_ROUND = 1, RES_OP_ABORT = 2 };
 constexpr uint64_t RES_FLAG_EXCHANGE = 1ull << 8;  // member 0's sums are all-reduced over peer memory
+// member 0 (index-sharded): bind, then write the bound shard into EVERY rank's gather arena, wait for the peers'
+// shards, and sweep the GATHERED tables (G x the shard) - the member continues un-sharded, in the same kernel
+constexpr uint64_t RES_FLAG_GATHER = 1ull << 9;
 
 // The mailbox is a ring of TWO commands / answers (command s uses slot s & 1): with lookahead the host posts
 // command s + 1 while the answer to command s is still on its way.
@@ -92,7 +95,10 @@ struct alignas(128) ResState {
     // commands in flight block 0 may SEE command s + 1 before round s is complete: it re-publishes it only after
     // done == s, so no block can miss (or tear) a command and no RED of round s + 1 lands in round s's lanes.
     uint64_t done;
-    uint64_t pad3[15];
+    uint64_t bar_epoch;          // in-command grid barrier (gather): arrivals in bar_count, release by epoch
+    unsigned int bar_count;
+    unsigned int pad3a;
+    uint64_t pad3[13];
     uint64_t lanes[RES_MAX_MEMBERS * RES_SLOT_U64];  // zero between rounds
 };
 
@@ -400,9 +406,81 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
         }
         const bool hi4 = (s_line[2] | s_line[3]) == 0;  // 125-bit challenge [0,0,lo,hi]: 4-row product
 
+        unsigned eff_actions = actions;  // what the member loop below executes (a gather turns its bind into an eval)
+        if (cmdw & RES_FLAG_GATHER) {
+            // ---- bind member 0's shard and scatter it into every rank's arena --------------------------------
+            const int G = a.world, par = (int)(xseq & 1);
+            const uint64_t len = s_len[0], np = len / 2;      // np = this rank's bound shard
+            const uint64_t glen = np * (uint64_t)G;           // the gathered table
+            const ResShape sh = res_shape(np, live);
+            if (b < sh.nblk && tid < (int)sh.tpb) {
+                for (uint64_t i = (uint64_t)b * sh.tpb + tid; i < np; i += (uint64_t)sh.nblk * sh.tpb) {
+                    // LowToHigh shards are contiguous blocks of the global table, HighToLow shards are strided
+                    const uint64_t gpos = ORDER == ORDER_LOW_TO_HIGH ? (uint64_t)a.rank * np + i : i * (uint64_t)G + a.rank;
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        const uint64_t* in = s_cur[0][j];
+                        const Fr lo = ld_elem_rw<Fr>(in, ORDER == ORDER_HIGH_TO_LOW ? i : 2 * i);
+                        const Fr hi = ld_elem_rw<Fr>(in, ORDER == ORDER_HIGH_TO_LOW ? i + np : 2 * i + 1);
+                        const Fr o = hi4 ? bind_pair<true>(lo, hi, sc) : bind_pair<false>(lo, hi, sc);
+                        for (int g = 0; g < G; ++g)
+                            st_elem(a.peer[g] + (XCH_ARENA_OFFSET + (size_t)par * XCH_ARENA_HALF) / 8 + (size_t)j * glen * 4, gpos, o);
+                    }
+                }
+            }
+            // ---- grid barrier; its last arriver also waits for every peer's shard ------------------------------
+            __syncthreads();
+            if (tid == 0) {
+                bool ok = true;
+                if (live > 1) {
+                    __threadfence_system();
+                    const uint64_t epoch = ld_acquire_gpu(&a.st->bar_epoch);
+                    if (atomicAdd(&a.st->bar_count, 1u) == live - 1) {
+                        a.st->bar_count = 0;
+                        __threadfence_system();  // every block's peer stores (ordered before its arrival) before the flags
+                        for (int g = 0; g < G; ++g) *(volatile uint64_t*)(a.peer[g] + XCH_GFLAG_BASE + par * 16 + a.rank) = xseq;
+                        const long long t0 = clock64();
+                        uint64_t* mine = a.peer[a.rank];
+                        for (int src = 0; src < G && ok; ++src)
+                            while (*(volatile uint64_t*)(mine + XCH_GFLAG_BASE + par * 16 + src) != xseq)
+                                if (clock64() - t0 > a.timeout_cycles) {
+                                    ok = false;
+                                    break;
+                                }
+                        __threadfence_system();
+                        st_release_gpu(&a.st->bar_epoch, epoch + 1 + (ok ? 0 : (1ull << 32)));
+                    } else {
+                        const long long t0 = clock64();
+                        while ((uint32_t)ld_acquire_gpu(&a.st->bar_epoch) == (uint32_t)epoch)
+                            if (clock64() - t0 > a.timeout_cycles) break;
+                    }
+                } else {
+                    __threadfence_system();
+                    for (int g = 0; g < G; ++g) *(volatile uint64_t*)(a.peer[g] + XCH_GFLAG_BASE + par * 16 + a.rank) = xseq;
+                    const long long t0 = clock64();
+                    uint64_t* mine = a.peer[a.rank];
+                    for (int src = 0; src < G && ok; ++src)
+                        while (*(volatile uint64_t*)(mine + XCH_GFLAG_BASE + par * 16 + src) != xseq)
+                            if (clock64() - t0 > a.timeout_cycles) {
+                                ok = false;
+                                break;
+                            }
+                    __threadfence_system();
+                }
+                // the member continues on the gathered tables (and their ping-pong partners) in THIS rank's arena
+                uint64_t* arena = a.peer[a.rank] + (XCH_ARENA_OFFSET + (size_t)par * XCH_ARENA_HALF) / 8;
+                for (int j = 0; j < T; ++j) {
+                    s_cur[0][j] = arena + (size_t)j * glen * 4;
+                    s_oth[0][j] = arena + (size_t)T * glen * 4 + (size_t)j * (glen / 2) * 4;
+                }
+                s_len[0] = glen;
+            }
+            __syncthreads();
+            eff_actions = (actions & ~0xfu) | RES_ACT_EVAL;
+        }
         // ---- this block's share of every active member's pass -------------------------------------------
         for (int m = 0; m < NM; ++m) {
-            const unsigned act = (actions >> (4 * m)) & 0xf;
+            const unsigned act = (eff_actions >> (4 * m)) & 0xf;
             if (act == RES_ACT_NONE) continue;
             const uint64_t len = s_len[m];
             if (act == RES_ACT_FINAL) {  // terminal bind: no sweep
@@ -474,7 +552,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
         if (tid == 0) {
             unsigned ln = 0;
             for (int m = 0; m < NM; ++m) {
-                const unsigned act = (actions >> (4 * m)) & 0xf;
+                const unsigned act = (eff_actions >> (4 * m)) & 0xf;
                 if (act == RES_ACT_BIND_EVAL || act == RES_ACT_FINAL) {
                     if (ORDER == ORDER_LOW_TO_HIGH) {
 #pragma unroll
@@ -491,7 +569,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 const unsigned need = res_need_blocks(D, P, s_len[m], grid);
                 ln = need > ln ? need : ln;
             }
-            s_live_next = ln;
+            s_live_next = ln < live ? ln : live;  // (a gather enlarges the tables; blocks that have left stay gone)
             if (live > 1) {
                 __threadfence();
                 const unsigned ticket = atomicAdd(&a.st->ticket, 1u);
