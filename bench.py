@@ -118,6 +118,10 @@ class ClockSampler:
                 pass
             time.sleep(0.002)
 
+    def restart(self):
+        """forget what was sampled so far (the timed region starts now)"""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
         if self.thread is None:
@@ -502,6 +506,10 @@ def run_ours(args):
     desc = [BatchMember(claim, 1, args.log_n, 0)]
     copies = [[b.clone() for b in base] for _ in range(K + W)]
     torch.cuda.synchronize()
+    # the NVML sampler thread starts BEFORE the warm-up (its initialisation takes tens of ms: started between the
+    # barrier and the first event it made rank 0 late and every other rank's first exchange wait for it, inside their
+    # timed region); its samples are discarded at the start of the timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for w in range(W):
         one_step(copies[w], 7)
     if dist:
@@ -509,7 +517,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     sess.timing_enable(True, min_items=1 << (args.log_n - 3))
     launches0 = sess.launch_count
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.restart()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     t0 = time.perf_counter()

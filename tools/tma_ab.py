@@ -18,6 +18,8 @@ try:
     peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
 except Exception:
     pass
+stream = torch.cuda.Stream()      # the session runs on torch's current stream: the L2 flush is ordered before each pass
+torch.cuda.set_stream(stream)
 g = torch.Generator(device="cuda").manual_seed(1)
 tabs = []
 for j in range(2):
@@ -32,7 +34,7 @@ for variant in ("ldg", "tma"):
         os.environ["JB_EVAL_TMA"] = "1"
     else:
         os.environ.pop("JB_EVAL_TMA", None)
-    sess = jolt_b200.Session(0)
+    sess = jolt_b200.Session(0, cuda_stream=stream.cuda_stream)
     for order, oname in ((LOW_TO_HIGH, "l2h"), (HIGH_TO_LOW, "h2l")):
         probe = ProductMember(sess, [Polynomial.wrap_device(sess, t.data_ptr(), n) for t in tabs], order)
         ev = probe.prove_round_evals(None, 0)       # all points, no claim: the reference value
