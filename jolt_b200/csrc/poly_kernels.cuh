@@ -525,234 +525,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) fused_round_kernel(TablePtrs tp, 
     round_epilogue<K>(acc, dsm + FusedShape<D, SKIP1>::acc_words(BLOCK), out);
 }
 
-// ---- persistent tail: the last rounds of a member without a launch per round -------------------------
-// Once a member's tables are short, a sumcheck round costs a kernel launch (~5 us) plus the drain of a
-// mostly idle GPU, several times the arithmetic. This kernel is launched ONCE when the tables drop to
-// TAIL_MAX_LEN entries and then serves every remaining round from a mailbox in host-mapped pinned
-// memory: thread 0 polls `cmd_seq`, the block binds + sweeps the (L2-resident) tables, thread 0 writes
-// the K round values and raises `res_seq`. The Fiat-Shamir round trip becomes two PCIe hops and a few
-// microseconds of arithmetic. One block, 512 threads, its own stream (other members' launches are not
-// queued behind it). Values are identical to the streaming kernel's (same evaluation set, exact sums).
-struct alignas(64) TailMailbox {
-    // line 0 (64 B), host -> device. The host writes cmd/challenge first and cmd_seq last; the device
-    // reads the whole line with ONE coalesced 64-byte request (a single PCIe read, a coherent snapshot
-    // of the cache line), so a snapshot that shows the new sequence number also shows its payload.
-    volatile uint64_t cmd_seq;   // sequence number of the posted command
-    uint64_t cmd;                // TAIL_CMD_* | (skip1 << 8)
-    uint64_t challenge[4];       // Montgomery limbs of the bind scalar
-    uint64_t pad0[2];
-    // line 1.., device -> host
-    volatile uint64_t res_seq;   // sequence number of the completed command
-    uint64_t status;             // 0 ok, 1 timeout/abort
-    uint64_t pad1[6];
-    uint64_t result[8 * 4];      // K canonical elements
-};
-enum : uint64_t { TAIL_CMD_BIND_ROUND = 1, TAIL_CMD_EVAL_ROUND = 2, TAIL_CMD_FINAL_BIND = 3, TAIL_CMD_ABORT = 4 };
-constexpr size_t TAIL_MAX_LEN = 8192;  // enter the tail when a table has <= this many entries
-
-struct TailTables {
-    uint64_t* buf[4];
-    uint64_t* alt[4];  // LowToHigh ping-pong partner (>= len/2 entries)
-    size_t len;
-};
-
-template <int M, int ORDER>
-__global__ void __launch_bounds__(512) tail_rounds_kernel(TailTables tt, TailMailbox* mb, long long timeout_cycles) {
-    __shared__ uint32_t red[32 * (M + 1) * 8];
-    __shared__ uint64_t s_cmd;
-    __shared__ uint32_t s_ch[8];
-    const int tid = threadIdx.x;
-    uint64_t* cur[M];
-    uint64_t* oth[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-        cur[j] = tt.buf[j];
-        oth[j] = tt.alt[j];
-    }
-    size_t len = tt.len;
-    uint64_t seq = 0;
-    while (true) {
-        if (tid < 32) {  // warp 0 polls the command line
-            const long long t0 = clock64();
-            const volatile uint64_t* line = reinterpret_cast<const volatile uint64_t*>(mb);
-            uint64_t v = 0;
-            bool got = false;
-            while (true) {
-                if (tid < 8) v = line[tid];
-                const uint64_t sq = __shfl_sync(0xffffffffu, v, 0);
-                if (sq == seq + 1) {
-                    got = true;
-                    break;
-                }
-                const int expired = __shfl_sync(0xffffffffu, (int)(clock64() - t0 > timeout_cycles), 0);
-                if (expired) break;  // host went away: give the SM back
-                __nanosleep(32);
-            }
-            if (tid == 1) s_cmd = got ? v : (uint64_t)TAIL_CMD_ABORT;
-            if (got && tid >= 2 && tid < 6) {
-                s_ch[2 * (tid - 2)] = (uint32_t)v;
-                s_ch[2 * (tid - 2) + 1] = (uint32_t)(v >> 32);
-            }
-        }
-        __syncthreads();
-        ++seq;
-        const uint64_t cmd = s_cmd & 0xff;
-        const bool skip1 = ((s_cmd >> 8) & 1) != 0;
-        if (cmd == TAIL_CMD_ABORT) {
-            if (tid == 0) {
-                mb->status = 1;
-                __threadfence_system();
-                mb->res_seq = seq;
-            }
-            return;
-        }
-        Fr sv;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sv.v[i] = s_ch[i];
-        const bool hi4 = (sv.v[0] | sv.v[1] | sv.v[2] | sv.v[3]) == 0;  // 125-bit challenge [0,0,lo,hi]: 4-row product
-        auto bind1 = [&](const Fr& lo_, const Fr& hi_) {
-            Fr d = fp_sub_lazy(hi_, lo_);
-            Fr m = hi4 ? fp_mul_hi4(d, sv.v + 4) : fp_mul(d, sv);
-            return fp_add(lo_, m);
-        };
-        if (cmd == TAIL_CMD_FINAL_BIND) {
-            const size_t half = len / 2;
-            for (size_t i = tid; i < half; i += blockDim.x) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    Fr lo = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? i : 2 * i);
-                    Fr hi = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? i + half : 2 * i + 1);
-                    Fr out = bind1(lo, hi);
-                    st_elem(ORDER == ORDER_HIGH_TO_LOW ? cur[j] : oth[j], i, out);
-                }
-            }
-            __syncthreads();
-            // leave the result in the member's primary buffer whatever the ping-pong parity
-            if (ORDER == ORDER_LOW_TO_HIGH) {
-                for (size_t i = tid; i < half; i += blockDim.x)
-#pragma unroll
-                    for (int j = 0; j < M; ++j)
-                        if (oth[j] != tt.buf[j]) st_elem(tt.buf[j], i, ld_elem_rw<Fr>(oth[j], i));
-            } else {
-                for (size_t i = tid; i < half; i += blockDim.x)
-#pragma unroll
-                    for (int j = 0; j < M; ++j)
-                        if (cur[j] != tt.buf[j]) st_elem(tt.buf[j], i, ld_elem_rw<Fr>(cur[j], i));
-            }
-            __syncthreads();
-            if (tid == 0) {
-                if (half == 1) {  // fully bound: hand the M final values back with the acknowledgement
-#pragma unroll
-                    for (int j = 0; j < M; ++j) {
-                        Fr v = ld_elem_rw<Fr>(tt.buf[j], 0);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w)
-                            mb->result[j * 4 + w] = (uint64_t)v.v[2 * w] | ((uint64_t)v.v[2 * w + 1] << 32);
-                    }
-                }
-                mb->status = 0;
-                __threadfence_system();
-                mb->res_seq = seq;
-            }
-            return;
-        }
-        const bool bind = cmd == TAIL_CMD_BIND_ROUND;
-        const size_t blen = bind ? len / 2 : len;  // length swept this round
-        const size_t pairs = blen / 2;
-        constexpr int KMAX = M + 1;
-        Fr acc[KMAX];
-#pragma unroll
-        for (int e = 0; e < KMAX; ++e) acc[e] = Fr::zero();
-        for (size_t y = tid; y < pairs; y += blockDim.x) {
-            Fr lo[M], hi[M];
-#pragma unroll
-            for (int j = 0; j < M; ++j) {
-                if (bind) {
-                    if (ORDER == ORDER_HIGH_TO_LOW) {
-                        Fr a = ld_elem_rw<Fr>(cur[j], y), c = ld_elem_rw<Fr>(cur[j], y + 2 * pairs);
-                        Fr b = ld_elem_rw<Fr>(cur[j], y + pairs), d = ld_elem_rw<Fr>(cur[j], y + 3 * pairs);
-                        lo[j] = bind1(a, c);
-                        hi[j] = bind1(b, d);
-                        st_elem(cur[j], y, lo[j]);
-                        st_elem(cur[j], y + pairs, hi[j]);
-                    } else {
-                        Fr a = ld_elem_rw<Fr>(cur[j], 4 * y), b = ld_elem_rw<Fr>(cur[j], 4 * y + 1);
-                        Fr c = ld_elem_rw<Fr>(cur[j], 4 * y + 2), d = ld_elem_rw<Fr>(cur[j], 4 * y + 3);
-                        lo[j] = bind1(a, b);
-                        hi[j] = bind1(c, d);
-                        st_elem(oth[j], 2 * y, lo[j]);
-                        st_elem(oth[j], 2 * y + 1, hi[j]);
-                    }
-                } else {
-                    lo[j] = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? y : 2 * y);
-                    hi[j] = ld_elem_rw<Fr>(cur[j], ORDER == ORDER_HIGH_TO_LOW ? y + pairs : 2 * y + 1);
-                }
-            }
-            // same evaluation set and order as fused_round_kernel: s(0), [s(1)], s(2..M-1), s(inf)
-            int e = 0;
-            {
-                Fr prod = lo[0];
-#pragma unroll
-                for (int j = 1; j < M; ++j) prod = fp_mul(prod, lo[j]);
-                acc[e] = fp_add(acc[e], prod);
-                ++e;
-            }
-            if (!skip1) {
-                Fr prod = hi[0];
-#pragma unroll
-                for (int j = 1; j < M; ++j) prod = fp_mul(prod, hi[j]);
-                acc[e] = fp_add(acc[e], prod);
-                ++e;
-            }
-            if (M >= 2) {
-                Fr dlt[M], c2[M];
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    dlt[j] = fp_sub(hi[j], lo[j]);
-                    c2[j] = hi[j];
-                }
-#pragma unroll
-                for (int t = 2; t < M; ++t) {
-#pragma unroll
-                    for (int j = 0; j < M; ++j) c2[j] = fp_add(c2[j], dlt[j]);
-                    Fr prod = c2[0];
-#pragma unroll
-                    for (int j = 1; j < M; ++j) prod = fp_mul(prod, c2[j]);
-                    acc[e] = fp_add(acc[e], prod);
-                    ++e;
-                }
-                Fr prod = dlt[0];
-#pragma unroll
-                for (int j = 1; j < M; ++j) prod = fp_mul(prod, dlt[j]);
-                acc[e] = fp_add(acc[e], prod);
-            }
-        }
-        block_sum<KMAX>(acc, red);
-        if (tid == 0) {
-            const int K = (M == 1) ? (skip1 ? 1 : 2) : (skip1 ? M : M + 1);
-            for (int t = 0; t < K; ++t)
-#pragma unroll
-                for (int w = 0; w < 4; ++w)
-                    mb->result[t * 4 + w] = (uint64_t)acc[t].v[2 * w] | ((uint64_t)acc[t].v[2 * w + 1] << 32);
-            mb->status = 0;
-            __threadfence_system();
-            mb->res_seq = seq;
-        }
-        if (bind) {
-            if (ORDER == ORDER_LOW_TO_HIGH) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    uint64_t* t = cur[j];
-                    cur[j] = oth[j];
-                    oth[j] = t;
-                }
-            }
-            len = blen;
-        }
-        __syncthreads();  // the round's stores are visible to the whole block before the next round reads them
-    }
-}
-
 // ---- eq-table expansion --------------------------------------------------------------------
 // table[x] = scale * prod_i (r_i if bit_i(x) else 1 - r_i), bit_i(x) = bit (n-1-i) of x.
 // One block expands EQ_BLOCK_VARS trailing variables from one prefix value:
