@@ -297,7 +297,7 @@ def kernels_section(sess, peak_hbm: float, with_cpu: bool):
     out = {"timing": "CUDA events on the launching stream, best of 5 after 1 warm-up, 512 MiB L2 flush between repetitions"}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
-    def timed(fn, setup=None, reps=5):
+    def timed(fn, setup=None, reps=5, teardown=None):
         best = 1e30
         for rep in range(reps + 1):
             arg = setup() if setup else None
@@ -309,6 +309,8 @@ def kernels_section(sess, peak_hbm: float, with_cpu: bool):
             e1.synchronize()
             if rep:
                 best = min(best, e0.elapsed_time(e1))
+            if teardown:  # hand the tables back: the next repetition's device allocations come out of the pool
+                teardown(arg)
         return best
 
     def synth(n, seed):
@@ -334,7 +336,7 @@ def kernels_section(sess, peak_hbm: float, with_cpu: bool):
             def setup():
                 buf = src.clone()
                 return buf, Polynomial.wrap_device(sess, buf.data_ptr(), n)
-            ms = timed(lambda a: a[1].bind_with_order(ch, order), setup)
+            ms = timed(lambda a: a[1].bind_with_order(ch, order), setup, teardown=lambda a: a[1].free())
             gbs = 48 * n / (ms * 1e-3) / 1e9
             binds.append({"order": oname, "scalar": cname, "ms": ms, "gb_per_s": gbs, "frac_of_hbm_peak": gbs / peak_hbm})
     out["bind_kernel_2^24"] = {"algorithmic_bytes": 48 * n, "bound": "hbm", "peak": peak_hbm, "runs": binds}

@@ -197,6 +197,7 @@ static int ctx_create_impl(int device, bool borrow, void* cuda_stream, jb_ctx** 
     if (const char* sh = std::getenv("JB_FUSED_SHAPE")) c->fused_shape = std::atoi(sh);  // tuning knob
     if (std::getenv("JB_NO_TAIL")) c->use_tail = false;  // diagnostics: one launch per round all the way down
     if (const char* ml = std::getenv("JB_RESIDENT_MAX_LOG")) c->resident_max_log = std::atoi(ml);
+    if (const char* sp = std::getenv("JB_STATIC_PCT")) c->resident_static_pct = std::max(0, std::min(100, std::atoi(sp)));
     if (const char* ts = std::getenv("JB_RESIDENT_TIMEOUT_S")) c->resident_timeout_cycles = (long long)(std::atof(ts) * 1.9e9);
     if (std::getenv("JB_EVAL_TMA")) c->eval_tma = true;
     if (std::getenv("JB_NO_LOOKAHEAD")) c->lookahead = false;

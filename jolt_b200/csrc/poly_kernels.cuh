@@ -250,6 +250,11 @@ struct TablePtrs {
     const uint64_t* e_out;
     const uint64_t* e_in;
     int in_bits;
+    // DYN passes (resident kernel): pair indices below static_end are laid out statically (grid-stride); the rest
+    // is handed out 32 indices at a time, one warp per claim, from the counter *work (zero at the start of a pass).
+    // static_end is a multiple of the grid stride; SIZE_MAX = everything static.
+    unsigned int* work;
+    size_t static_end;
 };
 
 // Fused pass for a sum-of-products member  sum_x sum_{k<P} prod_{j<D} f_{kD+j}(x)  (degree D, T = D*P tables;
@@ -294,7 +299,11 @@ __device__ __forceinline__ Fr ld_tab(const uint64_t* base, size_t idx) {
 // RAW (D > 1): skip the block's Montgomery reduction and leave the K x 17 integer column sums (u64) in the scratch
 // area dsm + acc_words - the resident kernel ships them to the host, which does the O(K) serial reduction far
 // faster than one GPU lane can (acc[] is then not written).
-template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, bool WEIGHTED, bool NC, bool RAW = false>
+// DYN: the tail of the index range is claimed dynamically (TablePtrs::work / static_end): the SMs do not all
+// stream at the same rate (measured: the slowest block of a 2^21-pair pass arrives ~20 % after the fastest), and
+// a round ends when the LAST block arrives - blocks that are ahead take more of the tail.
+template <int D, int P, int ORDER, bool BIND, bool HI4, bool SKIP1, int BLOCK, bool WEIGHTED, bool NC, bool RAW = false,
+          bool DYN = false>
 __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, const BindScalar& s, uint32_t* dsm,
                                            size_t first, size_t stride, Fr (&acc)[FusedShape<D, SKIP1>::K]) {
     constexpr int K = FusedShape<D, SKIP1>::K;
@@ -318,9 +327,29 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
     // behind the previous iteration's arithmetic instead of behind other warps - there are only 16 per SM.
     // (ptxas sinks the L2 prefetch below to the end of the loop body, so on its own it buys no lead time.)
     constexpr bool PIPE = !BIND && P == 1 && (D == 1 || (D == 2 && SKIP1));
+    // The index sequence of a thread: first, first + stride, ... while below S (static part), then warp-wide claims.
+    const size_t S = DYN ? tp.static_end : (size_t)0;
+    bool dyn = false;
+    auto claim = [&]() -> size_t {  // warp-uniform: every lane of the warp is in the loop or none is
+        unsigned c = 0;
+        if ((tid & 31) == 0) c = atomicAdd(tp.work, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        return S + (size_t)c * 32 + (tid & 31);
+    };
+    auto advance = [&](size_t prev) -> size_t {
+        if (!DYN) return prev + stride;
+        if (!dyn && prev + stride < S) return prev + stride;  // (uniform over the grid: S is a multiple of stride)
+        dyn = true;
+        return claim();
+    };
+    size_t ystart = first;
+    if (DYN && first >= S && first < pairs) {  // (no static part at all)
+        dyn = true;
+        ystart = claim();
+    }
     Fr nlo[PIPE ? D : 1], nhi[PIPE ? D : 1];
     if (PIPE) {
-        const size_t y0 = first;
+        const size_t y0 = ystart;
         if (y0 < pairs) {
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -334,11 +363,11 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
             }
         }
     }
-    for (size_t y = first; y < pairs; y += stride) {
-        // prefetch the lines of a later iteration into L2 (ncu: long-scoreboard was the top stall)
-        const size_t yp = y + (PIPE ? 2 : 1) * stride;
-        if (yp < pairs) {
-            const size_t yn = yp;
+    // Two indices of lookahead: y1 is the next iteration's, y2 the one after. Eval-only passes load y1 into registers
+    // and prefetch y2's lines into L2; bind passes prefetch y1's lines (ptxas sinks that prefetch to the end of the
+    // loop body; prefetching y2 there instead measured 8-13 % SLOWER on the 2^20..2^21-pair rounds, r02 probe).
+    auto prefetch_pair = [&](size_t yn) {
+        if (yn < pairs) {
 #pragma unroll
             for (int j = 0; j < T; ++j) {
                 if (ORDER == ORDER_HIGH_TO_LOW) {
@@ -353,6 +382,12 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
                 }
             }
         }
+    };
+    size_t y1 = (ystart < pairs) ? advance(ystart) : pairs;
+    for (size_t y = ystart; y < pairs;) {
+        const size_t ynext = y1;
+        const size_t y2 = (y1 < pairs) ? advance(y1) : pairs;
+        prefetch_pair(PIPE ? y2 : y1);
         Fr wgt;
         if (WEIGHTED) {
             const size_t mask = ((size_t)1 << tp.in_bits) - 1;
@@ -367,7 +402,7 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
                     lo[j] = nlo[j];
                     hi[j] = nhi[j];
                 }
-                const size_t yn = y + stride;
+                const size_t yn = ynext;
                 if (yn < pairs) {
 #pragma unroll
                     for (int j = 0; j < D; ++j) {
@@ -466,6 +501,8 @@ __device__ __forceinline__ void fused_pass(const TablePtrs& tp, size_t pairs, co
                 }
             }
         }
+        y = y1;
+        y1 = y2;
     }
     if (D == 1) {
 #pragma unroll

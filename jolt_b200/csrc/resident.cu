@@ -231,7 +231,8 @@ int resident_begin(jb_ctx* c, jb_member** mems, int n, uint64_t first_len, bool 
     std::memset(run->mb, 0, sizeof(ResMailbox));
     args.mb = (ResMailbox*)run->res.mb_dev;
     args.st = (ResState*)run->res.d_state;
-    args.timeout_cycles = c->resident_timeout_cycles;  // ~10 s of SM clocks without a command: give the SMs back
+    args.timeout_cycles = c->resident_timeout_cycles;
+    args.static_pct = c->resident_static_pct;  // ~10 s of SM clocks without a command: give the SMs back
     args.world = c->world;
     args.rank = c->rank;
     for (int g = 0; g < 16; ++g) args.peer[g] = c->xch_peer[g];

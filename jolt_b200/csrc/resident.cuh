@@ -41,7 +41,7 @@ constexpr int RES_BLOCK = 256;
 constexpr size_t RES_SMALL_LEN = 8192;  // tables this short need few blocks: such runs coexist with other work
 // Degree-2 rounds with at most this many pair indices run as THIN passes (thin_pass below): latency-shaped, and
 // they also return the lookahead sums that let the host answer the NEXT round without waiting for the device.
-constexpr uint64_t RES_THIN_PAIRS = 1ull << 16;
+constexpr uint64_t RES_THIN_PAIRS = 1ull << 17;  // (2^17: the first thin round costs what the generic pass costs there, and one more round is pipelined)
 // mailbox / accumulator words per member: a thin round returns 8 sums x 17 lanes; a generic round K <= 4 values
 // x 17 lanes (products) or x 8 lanes (D = 1); a terminal bind the T final values x 4 limbs
 constexpr int RES_SLOT_U64 = 136;
@@ -100,6 +100,8 @@ struct alignas(128) ResState {
     unsigned int pad3a;
     uint64_t pad3[13];
     uint64_t lanes[RES_MAX_MEMBERS * RES_SLOT_U64];  // zero between rounds
+    // dynamic-tail claim counters of the big passes, one 128-byte line per member; zero between rounds
+    unsigned int work[RES_MAX_MEMBERS * 32];
 };
 
 struct ResMemberArg {
@@ -114,6 +116,7 @@ struct ResArgs {
     ResMailbox* mb;     // host-mapped
     ResState* st;       // device
     long long timeout_cycles;
+    int static_pct;     // big passes: this share of the pair range is laid out statically, the rest is claimed (100 = off)
     // peer exchange (world > 1): exchange buffer of every rank as mapped in THIS process
     uint64_t* peer[16];
     int world, rank;
@@ -168,7 +171,7 @@ __device__ __noinline__ void resident_pass(const TablePtrs tp, size_t pairs, con
                                            size_t stride, uint64_t* g_lanes, uint64_t* s_dst) {
     constexpr int K = D;
     Fr acc[K];
-    fused_pass<D, P, ORDER, BIND, HI4, true, RES_BLOCK, false, false, (D > 1)>(tp, pairs, sc, dsm, first, stride, acc);
+    fused_pass<D, P, ORDER, BIND, HI4, true, RES_BLOCK, false, false, (D > 1), true>(tp, pairs, sc, dsm, first, stride, acc);
     const int tid = threadIdx.x;
     if (D > 1) {
         const uint64_t* colsum = reinterpret_cast<const uint64_t*>(dsm + FusedShape<D, true>::acc_words(RES_BLOCK));
@@ -516,6 +519,8 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                     }
                     tp.e_out = tp.e_in = nullptr;
                     tp.in_bits = 0;
+                    tp.work = nullptr;
+                    tp.static_end = ~(size_t)0;
                     uint64_t* gl = a.st->lanes + m * RES_SLOT_U64;
                     uint64_t* sl = live == 1 ? s_lanes + m * RES_SLOT_U64 : nullptr;
                     if (bind) thin_pass<P, ORDER, true>(tp, nprime, sc, hi4, dsm, b, nb, gl, sl);
@@ -536,6 +541,11 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                 // threads beyond this round's width have no pair (they still take part in the block reduction)
                 const size_t first = tid < (int)sh.tpb ? (size_t)b * sh.tpb + tid : (size_t)pairs;
                 const size_t stride = (size_t)sh.nblk * sh.tpb;
+                // passes of >= 2 full sweeps of the grid: the tail of the range is claimed warp by warp
+                tp.work = a.st->work + m * 32;
+                tp.static_end = ~(size_t)0;
+                if (a.static_pct < 100 && live > 1 && sh.tpb == RES_BLOCK && (size_t)pairs >= 2 * stride)
+                    tp.static_end = ((size_t)pairs / 100 * (size_t)a.static_pct / stride) * stride;
                 uint64_t* gl = a.st->lanes + m * RES_SLOT_U64;
                 uint64_t* sl = live == 1 ? s_lanes + m * RES_SLOT_U64 : nullptr;
                 if (!bind)
@@ -600,6 +610,7 @@ __global__ void __launch_bounds__(RES_BLOCK, 2) resident_rounds_kernel(const __g
                         a.st->lanes[idx] = 0;  // back to zero for the next round
                     }
                 }
+                if (tid < NM) a.st->work[tid * 32] = 0;
                 __syncthreads();
             }
             uint64_t status = 0;
