@@ -58,8 +58,19 @@ typedef enum jb_scalar_kind {
     JB_SCALAR_U64 = 4,
     JB_SCALAR_U128 = 5,
     JB_SCALAR_I64 = 6,
-    JB_SCALAR_I128 = 7
+    JB_SCALAR_I128 = 7,
+    JB_SCALAR_S64 = 8,  /* array of jb_s64 */
+    JB_SCALAR_S128 = 9  /* array of jb_s128 */
 } jb_scalar_kind;
+
+/* Sign-magnitude integers: jolt_field::signed::S64 / S128 = SignedBigInt<1> / SignedBigInt<2>
+ * { magnitude: Limbs<N>, is_positive: bool } (crates/jolt-field/src/signed.rs:25-32), the scalars of the legacy
+ * msm_s64 / msm_s128 (crates/jolt-prover-legacy/src/msm/mod.rs:140-158) and of MultilinearPolynomial::S128Scalars
+ * (poly/multilinear_polynomial.rs:33). The Rust struct is not repr(C); these are the records the adapter passes
+ * (a #[repr(C)] mirror; on x86-64 / aarch64 rustc lays SignedBigInt<N> out exactly like this). Field value:
+ * +-magnitude mod r; "zero is not canonicalized" (signed.rs:16-17): a zero magnitude with either sign is 0. */
+typedef struct jb_s64 { uint64_t magnitude; uint8_t is_positive; uint8_t pad[7]; } jb_s64;       /* 16 bytes */
+typedef struct jb_s128 { uint64_t magnitude[2]; uint8_t is_positive; uint8_t pad[7]; } jb_s128;  /* 24 bytes */
 
 typedef struct jb_ctx jb_ctx;       /* ~ ProofSession: device pools + stream */
 typedef struct jb_member jb_member; /* ~ Box<dyn SumcheckKernel>: a ProveRounds member on device */
@@ -286,7 +297,7 @@ int jb_srs_free(jb_ctx* ctx, jb_srs s);
  * normalisation is needed (or paid for) at the boundary. n == 0 -> identity (group_laws.rs:143-146);
  * offset + n > srs length -> JB_ERR_LENGTH (the reference panics, mod.rs:200-204). */
 int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars, size_t n, uint64_t out_xyz[12]);
-/* Small-scalar MSM: VariableBaseMSM::msm_u8/u16/u32/u64/u128/i64/i128 and the U8Scalars..I64Scalars arms of
+/* Small-scalar MSM: VariableBaseMSM::msm_u8/u16/u32/u64/u128/i64/i128/s64/s128 and the U8Scalars..I64Scalars arms of
  * VariableBaseMSM::msm (crates/jolt-prover-legacy/src/msm/mod.rs:27-150; msm_binary = JB_SCALAR_U8 with
  * values 0/1). `scalars`: host array of n primitive integers of `kind` (not JB_SCALAR_FR). Only
  * ceil(bits / c) windows are formed and the window is sized for the width (one 9-bit window for u8, five
@@ -294,6 +305,24 @@ int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars,
  * every point in one bucket) are cut into up to 16384 chunks per bucket. Same result conventions as jb_msm_g1. */
 int jb_msm_g1_small(jb_ctx* ctx, jb_srs bases, size_t offset, const void* scalars, size_t n, int kind,
                     uint64_t out_xyz[12]);
+/* VariableBaseMSM::batch_msm and batch_msm_univariate (crates/jolt-prover-legacy/src/msm/mod.rs:160-181): `count` MSMs,
+ * MSM k over the PREFIX bases[0 .. lens[k]) with the host column scalars[k] of kind kinds[k] (JB_SCALAR_FR = 4 x u64
+ * Montgomery limbs per entry: the LargeScalars arm / UniPoly coefficients; otherwise a primitive column as for
+ * jb_msm_g1_small). out_xyz: count x 12 limbs. The reference runs them on a Rayon pool; here they are enqueued back to
+ * back on the context's stream (each one already fills the device). Any lens[k] > srs length -> JB_ERR_LENGTH before
+ * anything runs (the reference panics in the worker, mod.rs:166). */
+int jb_msm_g1_batch(jb_ctx* ctx, jb_srs bases, size_t count, const void* const* scalars, const size_t* lens,
+                    const int* kinds, uint64_t* out_xyz);
+/* Row-batched MSM: `rows` MSMs of `row_width` terms each against the SAME bases[0 .. row_width), scalars row-major
+ * (row r = scalars[r * row_width ..), kind as above, JB_SCALAR_FR allowed) - the tier-1 row commitments of a Dory
+ * matrix commitment: DoryScheme::feed / feed_u64 / feed_i128 push one row MSM per chunk and feed_i128_rows_with maps
+ * msm_i128 over the windows of a batch on a Rayon pool (crates/jolt-dory/src/streaming.rs:53-70, 113-152, 154-201).
+ * Here all the rows go through ONE pass of the pipeline: digits, one scan, one scatter and one bucket accumulation
+ * over (row, bucket) sets of 8-bit shared windows (the 2^(8w) * P_i table of the first row_width bases is built on
+ * first use and kept with the SRS handle), so a 4096 x 4096 matrix costs one launch sequence, not 4096.
+ * out_xyz: rows x 12 limbs (Jacobian, conventions of jb_msm_g1). row_width > srs length -> JB_ERR_LENGTH. */
+int jb_msm_g1_rows(jb_ctx* ctx, jb_srs bases, const void* scalars, size_t rows, size_t row_width, int kind,
+                   uint64_t* out_xyz);
 /* Same with the scalars already on the device (a table, e.g. a folded HyperKZG polynomial). */
 int jb_msm_g1_table(jb_ctx* ctx, jb_srs bases, size_t offset, jb_table scalars, size_t n, uint64_t out_xyz[12]);
 

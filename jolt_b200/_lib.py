@@ -83,6 +83,9 @@ SIGNATURES = {
     "jb_srs_free": (ctypes.c_int, [c_void_p, ctypes.c_uint64]),
     "jb_msm_g1": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_u64p, c_size_t, c_u64p]),
     "jb_msm_g1_small": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, c_void_p, c_size_t, ctypes.c_int, c_u64p]),
+    "jb_msm_g1_batch": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t),
+                                        ctypes.POINTER(ctypes.c_int), c_u64p]),
+    "jb_msm_g1_rows": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_size_t, c_size_t, ctypes.c_int, c_u64p]),
     "jb_msm_g1_table": (ctypes.c_int, [c_void_p, ctypes.c_uint64, c_size_t, ctypes.c_uint64, c_size_t, c_u64p]),
     "jb_ctx_diag": (ctypes.c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "jb_ctx_run_log": (ctypes.c_int, [c_void_p, c_u64p, c_size_t, ctypes.POINTER(c_size_t)]),

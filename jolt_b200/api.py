@@ -105,7 +105,7 @@ class Session:
 
 
 # jb_scalar_kind (include/jolt_b200.h): compact-table / small-scalar encodings
-SCALAR_KINDS = {"fr": 0, "u8": 1, "u16": 2, "u32": 3, "u64": 4, "u128": 5, "i64": 6, "i128": 7}
+SCALAR_KINDS = {"fr": 0, "u8": 1, "u16": 2, "u32": 3, "u64": 4, "u128": 5, "i64": 6, "i128": 7, "s64": 8, "s128": 9}
 _DTYPE_KIND = {np.dtype(np.uint8): "u8", np.dtype(np.bool_): "u8", np.dtype(np.uint16): "u16",
                np.dtype(np.uint32): "u32", np.dtype(np.uint64): "u64", np.dtype(np.int64): "i64"}
 
@@ -113,7 +113,21 @@ _DTYPE_KIND = {np.dtype(np.uint8): "u8", np.dtype(np.bool_): "u8", np.dtype(np.u
 def small_scalars(values, kind: str | None = None) -> tuple[np.ndarray, int, int]:
     """(contiguous byte-exact array, jb_scalar_kind, n) for a primitive integer column. `values`: a numpy
     array of dtype bool/u8/u16/u32/u64/i64, or - for the 128-bit kinds - a sequence of Python ints with
-    `kind` = "u128" / "i128" (stored as 16 little-endian bytes each, two's complement)."""
+    `kind` = "u128" / "i128" (stored as 16 little-endian bytes each, two's complement). The sign-magnitude kinds
+    "s64" / "s128" (jolt_field::signed::S64 / S128, crates/jolt-field/src/signed.rs:25-32) take a sequence of
+    (magnitude, is_positive) tuples or of Python ints (sign taken from the int; (0, False) is the reference's -0)
+    and are stored as jb_s64 / jb_s128 records: N u64 magnitude limbs, then the sign byte, padded to 8."""
+    if kind in ("s64", "s128"):
+        limbs = 1 if kind == "s64" else 2
+        rec = np.zeros((len(values), limbs + 1), dtype=np.uint64)
+        for i, v in enumerate(values):
+            mag, pos = (abs(int(v)), int(v) >= 0) if not isinstance(v, (tuple, list)) else (int(v[0]), bool(v[1]))
+            if not 0 <= mag < 1 << (64 * limbs):
+                raise ValueError(f"{kind} magnitude out of range")
+            for j in range(limbs):
+                rec[i, j] = (mag >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+            rec[i, limbs] = 1 if pos else 0  # little-endian: the sign byte is the first byte of the last word
+        return rec, SCALAR_KINDS[kind], len(values)
     if kind in ("u128", "i128"):
         ints = [int(v) for v in values]
         lo_hi = np.empty((len(ints), 2), dtype=np.uint64)
@@ -686,6 +700,45 @@ class G1Bases:
         out = np.zeros(12, dtype=np.uint64)
         self.s.check(self.s.lib.jb_msm_g1_small(self.s.h, self.handle, offset,
                                                 a.ctypes.data_as(ctypes.c_void_p) if n else None, n, k, _p(out)))
+        return out
+
+    def batch_msm(self, columns) -> np.ndarray:
+        """VariableBaseMSM::batch_msm / batch_msm_univariate (crates/jolt-prover-legacy/src/msm/mod.rs:160-181): one MSM
+        per column against the PREFIX bases[..len(column)] of this base set. A column is (n, 4) Montgomery limbs
+        (LargeScalars / UniPoly coefficients), a numpy integer array, or a (values, kind) pair as in small_scalars.
+        Returns (len(columns), 12) Jacobian limbs."""
+        keep, ptrs, lens, kinds = [], [], [], []
+        for col in columns:
+            if isinstance(col, tuple):
+                a, k, n = small_scalars(col[0], col[1])
+            elif isinstance(col, np.ndarray) and col.dtype == np.uint64 and col.ndim == 2 and col.shape[1] == 4:
+                a, k, n = np.ascontiguousarray(col), SCALAR_KINDS["fr"], col.shape[0]
+            else:
+                a, k, n = small_scalars(col)
+            keep.append(a)
+            ptrs.append(a.ctypes.data if n else 0)
+            lens.append(n)
+            kinds.append(k)
+        m = len(columns)
+        out = np.zeros((max(m, 1), 12), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_msm_g1_batch(self.s.h, self.handle, m, (ctypes.c_void_p * max(m, 1))(*ptrs),
+                                                (ctypes.c_size_t * max(m, 1))(*lens), (ctypes.c_int * max(m, 1))(*kinds), _p(out)))
+        return out[:m]
+
+    def msm_rows(self, values, rows: int, kind: str | None = None) -> np.ndarray:
+        """Row-batched MSM (jb_msm_g1_rows): `values` is a row-major matrix of `rows` rows (a flat column as in
+        small_scalars, or (rows * w, 4) Montgomery limbs with kind="fr"); every row is an MSM against bases[..w] -
+        Dory's tier-1 row commitments (crates/jolt-dory/src/streaming.rs:53-201). Returns (rows, 12) Jacobian limbs."""
+        if kind == "fr":
+            a = np.ascontiguousarray(values, dtype=np.uint64).reshape(-1, 4)
+            k, n = SCALAR_KINDS["fr"], a.shape[0]
+        else:
+            a, k, n = small_scalars(values, kind)
+        if rows <= 0 or n % rows:
+            raise ValueError("msm_rows: the number of scalars must be a multiple of rows")
+        out = np.zeros((rows, 12), dtype=np.uint64)
+        self.s.check(self.s.lib.jb_msm_g1_rows(self.s.h, self.handle, a.ctypes.data_as(ctypes.c_void_p) if n else None,
+                                               rows, n // rows, k, _p(out)))
         return out
 
     def batch_add(self, index_sets) -> np.ndarray:

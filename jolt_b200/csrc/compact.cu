@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) bind_small_kernel(const void* values, siz
     }
 }
 
-int valid_kind(int kind) { return kind >= SK_U8 && kind <= SK_I128; }
+int valid_kind(int kind) { return kind >= SK_U8 && kind <= SK_LAST; }
 
 int grid_for(jb_ctx* c, size_t items) {
     size_t need = (items + 255) / 256;

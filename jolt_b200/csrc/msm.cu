@@ -102,9 +102,12 @@ MsmPlan plan_for(size_t n, int bits = 254) {
 // as called from crates/jolt-prover-legacy/src/msm/mod.rs:27-150).
 // AGG: equal slots within a warp are counted by ONE atomic (match.any) - witness columns are skewed
 // (binary, one-hot, constants: millions of points in one bucket), and same-address atomics serialise.
+// row_w: 0 for one MSM over n terms; otherwise the n terms are n / row_w ROWS of row_w scalars, every row against the
+// same bases[0 .. row_w) and with its own (shared-window) bucket set: slot = row * B + bucket (jb_msm_g1_rows).
 template <bool AGG>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, int kind, const uint64_t* bases, size_t n, int c,
-                                                         int W, int B, int shared, uint32_t* digits, unsigned int* hist) {
+                                                         int W, int B, int shared, uint32_t* digits, unsigned int* hist,
+                                                         size_t row_w) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     if (!AGG && !valid) return;
@@ -118,8 +121,10 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, in
             if (ld_small(scalars, i, kind, k.v)) flip = 0x80000000u;
         }
         // identity bases contribute nothing
-        skip = ld_elem<Fq>(bases, 2 * i).is_zero() && ld_elem<Fq>(bases, 2 * i + 1).is_zero();
+        const size_t bi = row_w ? i % row_w : i;
+        skip = ld_elem<Fq>(bases, 2 * bi).is_zero() && ld_elem<Fq>(bases, 2 * bi + 1).is_zero();
     }
+    const size_t row_slot = row_w && valid ? (i / row_w) * (size_t)B : 0;
     uint32_t carry = 0;
     const uint32_t mask = (1u << c) - 1u;
     const int lane = threadIdx.x & 31;
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, in
         if (skip) enc = 0;
         if (enc) enc ^= flip;
         if (valid) digits[(size_t)w * n + i] = enc;
-        const size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
+        const size_t slot = (shared ? row_slot : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
         if (AGG) {
             const unsigned m = __ballot_sync(0xffffffffu, enc != 0);
             if (enc) {
@@ -276,11 +281,84 @@ __global__ void __launch_bounds__(1024) msm_scan_apply_kernel(unsigned int* offs
         }
 }
 
-// task -> bucket map (a bucket writes its <= 64 task slots)
-__global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* toff, size_t nbuckets, uint32_t* task_bucket) {
-    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nbuckets) return;
-    for (unsigned t = toff[b]; t < toff[b + 1]; ++t) task_bucket[t] = (uint32_t)b;
+// task -> bucket map (a bucket writes its <= 64 task slots) AND the order in which the accumulation walks the tasks:
+// by chunk length, longest first (a counting sort on min(len, 255)). One thread owns one task, so a warp is as slow
+// as its longest chunk: in bucket order the lengths of neighbouring tasks are Poisson-distributed (2^20 terms with a
+// 20-bit window: mean 26, the longest of 32 is ~41 - a third of the lanes idle); in length order every warp walks
+// equal chunks and the long ones start first.
+constexpr int MSM_LEN_BINS = 256;
+__device__ __forceinline__ int task_len_bin(unsigned cnt, unsigned maxq) {
+    const unsigned len = chunk_len(cnt, maxq);
+    return MSM_LEN_BINS - 1 - (int)(len < (unsigned)(MSM_LEN_BINS - 1) ? len : (unsigned)(MSM_LEN_BINS - 1));
+}
+// among the lanes of the warp with the same bin: q summed over the lower lanes (pre), over all of them (tot), and the
+// first lane with q > 0 (first; -1 if none). Uniform loop: every lane of the warp takes part.
+__device__ __forceinline__ void warp_bin_group(int bin, unsigned q, unsigned& pre, unsigned& tot, int& first) {
+    const int lane = threadIdx.x & 31;
+    pre = 0;
+    tot = 0;
+    first = -1;
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) {
+        const unsigned v = __shfl_sync(0xffffffffu, q, l);
+        const int bl = __shfl_sync(0xffffffffu, bin, l);
+        if (bl == bin && v) {
+            if (l < lane) pre += v;
+            tot += v;
+            if (first < 0) first = l;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) msm_len_hist_kernel(const unsigned int* offsets, const unsigned int* toff, size_t nbuckets,
+                                                           unsigned maxq, unsigned int* len_hist) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = b < nbuckets;
+    const unsigned cnt = valid ? offsets[b + 1] - offsets[b] : 0u;
+    const unsigned q = valid ? toff[b + 1] - toff[b] : 0u;
+    const int bin = task_len_bin(cnt, maxq);
+    unsigned pre, tot;
+    int first;
+    warp_bin_group(bin, q, pre, tot, first);
+    if (q && first == (int)(threadIdx.x & 31)) atomicAdd(&len_hist[bin], tot);
+}
+// len_hist: [0, 256) task counts per bin (read), [256, 512) cursors (zero on entry)
+__global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* offsets, const unsigned int* toff, size_t nbuckets,
+                                                        unsigned maxq, unsigned int* len_hist, uint32_t* task_bucket,
+                                                        uint32_t* order) {
+    __shared__ unsigned int bin_start[MSM_LEN_BINS];
+    {   // exclusive scan of the 256 bin counts (Hillis-Steele in shared memory)
+        __shared__ unsigned int tmp[MSM_LEN_BINS];
+        const int k = threadIdx.x;
+        unsigned v = len_hist[k];
+        tmp[k] = v;
+        __syncthreads();
+        for (int off = 1; off < MSM_LEN_BINS; off <<= 1) {
+            const unsigned add = k >= off ? tmp[k - off] : 0u;
+            __syncthreads();
+            tmp[k] += add;
+            __syncthreads();
+        }
+        bin_start[k] = tmp[k] - v;
+        __syncthreads();
+    }
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = b < nbuckets;
+    const unsigned cnt = valid ? offsets[b + 1] - offsets[b] : 0u;
+    const unsigned t0 = valid ? toff[b] : 0u;
+    const unsigned q = valid ? toff[b + 1] - t0 : 0u;
+    const int bin = task_len_bin(cnt, maxq);
+    unsigned pre, tot;
+    int first;
+    warp_bin_group(bin, q, pre, tot, first);
+    unsigned base = 0;
+    if (q && first == (int)(threadIdx.x & 31)) base = atomicAdd(&len_hist[MSM_LEN_BINS + bin], tot);
+    base = __shfl_sync(0xffffffffu, base, first < 0 ? 0 : first);
+    if (!q) return;
+    const unsigned pos = bin_start[bin] + base + pre;
+    for (unsigned j = 0; j < q; ++j) {
+        task_bucket[t0 + j] = (uint32_t)b;
+        order[pos + j] = t0 + j;
+    }
 }
 
 // ---- 3. scatter -----------------------------------------------------------------------------------
@@ -289,14 +367,16 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* toff
 template <bool AGG>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B, int shared,
                                                           size_t stride, const unsigned int* offsets, unsigned int* cursor,
-                                                          uint32_t* sorted) {
+                                                          uint32_t* sorted, size_t row_w) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     if (!AGG && !valid) return;
     const int lane = threadIdx.x & 31;
+    const size_t row_slot = row_w && valid ? (i / row_w) * (size_t)B : 0;
+    const size_t col = row_w ? i % row_w : i;  // index into the bases / a table row
     for (int w = 0; w < W; ++w) {
         uint32_t enc = valid ? digits[(size_t)w * n + i] : 0u;
-        const size_t slot = (shared ? 0 : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
+        const size_t slot = (shared ? row_slot : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
         unsigned int pos;
         if (AGG) {
             // one atomic per distinct slot in the warp; lanes take consecutive positions in lane order
@@ -312,7 +392,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
             if (!enc) continue;
             pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
         }
-        sorted[pos] = (uint32_t)(shared ? (size_t)w * stride + i : i) | (enc & 0x80000000u);
+        sorted[pos] = (uint32_t)(shared ? (size_t)w * stride + col : col) | (enc & 0x80000000u);
     }
 }
 
@@ -321,10 +401,12 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
 //         and are folded by msm_combine_kernel. --------------------------------------------------------
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bases, const uint32_t* sorted,
                                                              const unsigned int* offsets, const unsigned int* toff,
-                                                             const uint32_t* task_bucket, size_t nbuckets,
-                                                             uint64_t* buckets, uint64_t* partial, unsigned maxq) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= toff[nbuckets]) return;
+                                                             const uint32_t* task_bucket, const uint32_t* order,
+                                                             size_t nbuckets, uint64_t* buckets, uint64_t* partial,
+                                                             unsigned maxq) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= toff[nbuckets]) return;
+    const size_t t = order[k];  // tasks in length order (msm_tasks_kernel)
     const uint32_t b = task_bucket[t];
     const unsigned int base = offsets[b], cnt = offsets[b + 1] - base;
     const unsigned int len = chunk_len(cnt, maxq), j = (unsigned int)t - toff[b];
@@ -505,6 +587,71 @@ __global__ void __launch_bounds__(32) msm_final_kernel(const uint64_t* win, int 
     }
 }
 
+// rows mode: every bucket set is one row's MSM; win[r] (XYZZ) -> Jacobian, one thread per row
+__global__ void __launch_bounds__(128) msm_rows_out_kernel(const uint64_t* win, size_t rows, uint64_t* out_xyz) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const XYZZ acc = ld_xyzz(win, r);
+    Fq X = Fq::one(), Y = Fq::one(), Z = Fq::zero();
+    if (!acc.is_inf()) {
+        Fq zzz2 = fp_sqr(acc.zzz);
+        Fq zz2 = fp_sqr(acc.zz);
+        X = fp_mul(fp_mul(acc.x, acc.zz), zzz2);
+        Y = fp_mul(fp_mul(acc.y, fp_mul(zz2, acc.zz)), zzz2);
+        Z = fp_mul(acc.zz, acc.zzz);
+    }
+    st_elem(out_xyz, 3 * r, X);
+    st_elem(out_xyz, 3 * r + 1, Y);
+    st_elem(out_xyz, 3 * r + 2, Z);
+}
+
+// ---- binary columns: msm_binary (the `all(s <= 1)` arm of VariableBaseMSM::msm / msm_u8,
+//      crates/jolt-prover-legacy/src/msm/mod.rs:35-47, 96-106). The result is the plain sum of the selected bases: no
+//      digits, no sort - every thread walks its own 16-flag groups and adds the selected bases into ONE XYZZ
+//      accumulator (complete mixed additions: repeated / opposite bases are handled), then the existing tree folds
+//      the per-thread partials. ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) u8_max_kernel(const uint8_t* v, size_t n, unsigned int* out_max) {
+    const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int m = 0;
+    const size_t groups = n / 16;
+    for (size_t g = t; g < groups; g += T) {
+        const uint4 q = ((const uint4*)v)[g];
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
+    }
+    for (size_t i = groups * 16 + t; i < n; i += T) m = __vmaxu4(m, (unsigned int)v[i]);
+    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out_max, m);
+}
+
+__global__ void __launch_bounds__(128) msm_select_sum_kernel(const uint8_t* flags, const uint64_t* bases, size_t n,
+                                                             uint64_t* partial) {
+    const size_t T = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ acc = XYZZ::inf();
+    const size_t groups = (n + 15) / 16;
+    for (size_t g = t; g < groups; g += T) {
+        const size_t i0 = g * 16;
+        uint32_t mask = 0;
+        if (i0 + 16 <= n) {
+            const uint4 q = ((const uint4*)flags)[g];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mask |= ((w[k] & 1u) | ((w[k] >> 7) & 2u) | ((w[k] >> 14) & 4u) | ((w[k] >> 21) & 8u)) << (4 * k);
+        } else {
+            for (size_t i = i0; i < n; ++i) mask |= (uint32_t)(flags[i] & 1u) << (i - i0);
+        }
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const Fq px = ld_elem<Fq>(bases, 2 * (i0 + j)), py = ld_elem<Fq>(bases, 2 * (i0 + j) + 1);
+            if (px.is_zero() && py.is_zero()) continue;  // identity base
+            xyzz_add_affine(acc, px, py, false);
+        }
+    }
+    st_xyzz(partial, t, acc);
+}
+
 // ---- SRS helpers ------------------------------------------------------------------------------------------
 // Jacobian (X, Y, Z) -> affine (x, y) = (X/Z^2, Y/Z^3); Z == 0 -> identity (0, 0). One inversion per thread.
 __global__ void __launch_bounds__(128) jacobian_to_affine_kernel(const uint64_t* xyz, size_t n, uint64_t* xy) {
@@ -628,22 +775,27 @@ bool canonical_q(const uint64_t* a) {
 using Guard = CtxGuard;
 
 // `srs`: the resident bases; terms are bases[offset .. offset + n).
-int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, size_t n, uint64_t out_xyz[12],
-               int kind = SK_FR) {
+// rows > 1 (jb_msm_g1_rows): n = rows * row_w terms, row r = scalars[r * row_w ..) against bases[0 .. row_w); the
+// small table (8-bit shared windows) must cover row_w; out_xyz receives rows x 12 limbs.
+int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, size_t n, uint64_t* out_xyz,
+               int kind = SK_FR, size_t rows = 1) {
     const int bits = small_kind_bits(kind);
-    const unsigned maxq = kind == SK_FR ? MSM_MAX_CHUNKS : MSM_MAX_CHUNKS_SMALL;
+    const bool by_rows = rows > 1;
+    const size_t row_w = by_rows ? n / rows : 0;
+    // (a row's bucket holds at most row_w * W points: 64 chunks bound the walk without the block-per-bucket pass)
+    const unsigned maxq = (kind == SK_FR || by_rows) ? MSM_MAX_CHUNKS : MSM_MAX_CHUNKS_SMALL;
     // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
     // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
     // Small MSMs (the tail of HyperKZG's intermediate commitments, verifier-sized MSMs) use a second, tiny
     // table with 8-bit windows over the first bases: 128 buckets, no doubling chain - latency, not work.
-    const bool use_small = srs.pre_small != nullptr && n <= 4096 && offset + n <= srs.pre_small_len;
+    const bool use_small = by_rows || (srs.pre_small != nullptr && n <= 4096 && offset + n <= srs.pre_small_len);
     const bool use_big = !use_small && srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
     const bool shared = use_small || use_big;
     const MsmPlan p = use_small ? plan_with(8, bits) : use_big ? plan_with(srs.pre_c, bits) : plan_for(n, bits);
     const size_t pre_stride = use_small ? srs.pre_small_len : srs.n;       // row w starts at w * stride
     const uint64_t* d_bases = srs.xy + 8 * offset;                          // digits: identity test, per-window path: gather
     const uint64_t* d_gather = use_small ? srs.pre_small + 8 * offset : use_big ? srs.pre + 8 * offset : d_bases;
-    const int Weff = shared ? 1 : p.W;  // bucket sets
+    const int Weff = by_rows ? (int)rows : shared ? 1 : p.W;  // bucket sets
     const size_t nb = (size_t)Weff * p.B;
     // bucket offsets, task offsets, the scatter cursor and the histogram are 32-bit: W * n sorted entries must stay
     // below 2^32 (n ~ 2^28 with 16 windows would wrap the exclusive scan and read wrong ranges - silently)
@@ -651,7 +803,8 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
         return c->fail(JB_ERR_UNSUPPORTED, "msm: windows x terms must be < 2^32 (split the call)");
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
     const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
-    uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr;
+    uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr, *order = nullptr;
+    unsigned int* len_hist = nullptr;
     unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr, *block_sums = nullptr;
     const unsigned scan_blocks = (unsigned)((nb + SCAN_PER_BLOCK - 1) / SCAN_PER_BLOCK);  // <= 512 (c <= 22)
     uint64_t *buckets = nullptr, *partial = nullptr, *seg = nullptr, *win = nullptr, *d_out = nullptr;
@@ -664,32 +817,37 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     if (st == JB_OK) st = c->dev_alloc((void**)&toff, (nb + 1) * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&block_sums, 2 * 1024 * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&task_bucket, max_tasks * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&order, max_tasks * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&len_hist, 2 * MSM_LEN_BINS * 4);
+    if (st == JB_OK) st = c->check(cudaMemsetAsync(len_hist, 0, 2 * MSM_LEN_BINS * 4, c->stream), "msm memset");
     if (st == JB_OK) st = c->dev_alloc((void**)&buckets, nb * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&partial, max_tasks * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&seg, (size_t)Weff * p.T * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&win, (size_t)Weff * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&tree_a, tree_pts * 128);
     if (st == JB_OK) st = c->dev_alloc((void**)&tree_b, tree_pts * 128);
-    if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96 * rows);
     if (st == JB_OK) st = c->check(cudaMemsetAsync(hist, 0, nb * 4, c->stream), "msm memset");
     if (st == JB_OK) {
         unsigned g = (unsigned)((n + 255) / 256);
         const bool agg = kind != SK_FR;
         if (agg)
-            msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
+            msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
         else
-            msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist);
+            msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
         if (agg)
-            msm_scatter_kernel<true><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
+            msm_scatter_kernel<true><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w);
         else
-            msm_scatter_kernel<false><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted);
-        msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(toff, nb, task_bucket);
+            msm_scatter_kernel<false><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w);
+        msm_len_hist_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist);
+        msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist, task_bucket, order);
+        c->launches++;
         int tix = c->timing_begin(4, n, p.c);
         msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
-                                                                                      task_bucket, nb, buckets, partial, maxq);
+                                                                                      task_bucket, order, nb, buckets, partial, maxq);
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
         if (maxq > MSM_MAX_CHUNKS) {
@@ -715,16 +873,24 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
                 c->launches++;
             }
         }
-        msm_final_kernel<<<1, 32, 0, c->stream>>>(win, Weff, d_out);
+        if (by_rows) msm_rows_out_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, c->stream>>>(win, rows, d_out);
+        else msm_final_kernel<<<1, 32, 0, c->stream>>>(win, Weff, d_out);
         c->launches += 10;
         st = c->check(cudaGetLastError(), "msm kernels");
     }
-    if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
-    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm sync");
-    if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
+    if (by_rows) {
+        if (st == JB_OK) st = c->check(cudaMemcpyAsync(out_xyz, d_out, 96 * rows, cudaMemcpyDeviceToHost, c->stream), "msm rows D2H");
+        if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm sync");
+    } else {
+        if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
+        if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm sync");
+        if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
+    }
     c->dev_free(digits);
     c->dev_free(sorted);
     c->dev_free(task_bucket);
+    c->dev_free(order);
+    c->dev_free(len_hist);
     c->dev_free(hist);
     c->dev_free(offsets);
     c->dev_free(toff);
@@ -733,6 +899,64 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     c->dev_free(partial);
     c->dev_free(seg);
     c->dev_free(win);
+    c->dev_free(tree_a);
+    c->dev_free(tree_b);
+    c->dev_free(d_out);
+    return st;
+}
+
+// The small-MSM table: 8-bit shared windows (2^(8 w) * P_i, 32 rows) over the first bases - at least `want` of them,
+// by default the first <= 2^15 (<= 66 MiB). Serves MSMs of <= 4096 terms (the tail of a HyperKZG open) and the
+// row-batched MSMs of jb_msm_g1_rows.
+int build_small_table(jb_ctx* c, Srs& s, size_t want) {
+    const MsmPlan ps = plan_with(8);
+    size_t small_len = s.n < ((size_t)1 << 15) ? s.n : ((size_t)1 << 15);
+    if (want > small_len) small_len = want;
+    if (small_len > s.n) small_len = s.n;
+    if (s.pre_small && s.pre_small_len >= small_len) return JB_OK;
+    uint64_t* tab = nullptr;
+    int st = c->dev_alloc((void**)&tab, (size_t)ps.W * small_len * 64);
+    if (st != JB_OK) return st;
+    precompute_windows_kernel<<<(unsigned)((small_len + 127) / 128), 128, 0, c->stream>>>(s.xy, small_len, ps.c, ps.W, tab);
+    c->launches++;
+    st = c->check(cudaGetLastError(), "precompute_windows (small) launch");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "precompute sync");
+    if (st != JB_OK) {
+        c->dev_free(tab);
+        return st;
+    }
+    if (s.pre_small) c->dev_free(s.pre_small);
+    s.pre_small = tab;
+    s.pre_small_len = small_len;
+    return JB_OK;
+}
+
+void identity_xyz(uint64_t out[12]);
+
+// msm_binary on the device: `d_flags` = n bytes (0 / 1) already resident. Returns the Jacobian sum of the selected bases.
+int msm_binary_device(jb_ctx* c, const Srs& srs, size_t offset, const uint8_t* d_flags, size_t n, uint64_t out_xyz[12]) {
+    const unsigned blocks = 148 * 8;  // 1184 blocks x 128 threads: every thread owns ~n / 2^17 groups
+    const size_t T = (size_t)blocks * 128;
+    uint64_t *partial = nullptr, *tree_a = nullptr, *tree_b = nullptr, *d_out = nullptr;
+    int st = c->dev_alloc((void**)&partial, T * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&tree_a, ((T + 2047) / 2048 + 1) * 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&tree_b, 128);
+    if (st == JB_OK) st = c->dev_alloc((void**)&d_out, 96);
+    if (st == JB_OK) {
+        int tix = c->timing_begin(4, n, 1);
+        msm_select_sum_kernel<<<blocks, 128, 0, c->stream>>>(d_flags, srs.xy + 8 * offset, n, partial);
+        c->timing_end(tix);
+        const int b1 = (int)((T + 2047) / 2048);
+        msm_tree_sum_kernel<<<dim3(b1, 1), 256, 0, c->stream>>>(partial, (int)T, tree_a);
+        msm_tree_sum_kernel<<<dim3(1, 1), 256, 0, c->stream>>>(tree_a, b1, tree_b);  // b1 = 74 <= 2048
+        msm_final_kernel<<<1, 32, 0, c->stream>>>(tree_b, 1, d_out);
+        c->launches += 4;
+        st = c->check(cudaGetLastError(), "msm_binary kernels");
+    }
+    if (st == JB_OK) st = c->check(cudaMemcpyAsync(c->h_small, d_out, 96, cudaMemcpyDeviceToHost, c->stream), "msm D2H");
+    if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm sync");
+    if (st == JB_OK) std::memcpy(out_xyz, c->h_small, 96);
+    c->dev_free(partial);
     c->dev_free(tree_a);
     c->dev_free(tree_b);
     c->dev_free(d_out);
@@ -858,22 +1082,7 @@ int jb_srs_precompute(jb_ctx* c, jb_srs h, int window_bits) {
     }
     s.pre_c = p.c;
     s.pre_W = p.W;
-    // the small-MSM table: 8-bit windows over the first <= 2^15 bases (<= 66 MiB)
-    const MsmPlan ps = plan_with(8);
-    const size_t small_len = s.n < ((size_t)1 << 15) ? s.n : ((size_t)1 << 15);
-    if (c->dev_alloc((void**)&s.pre_small, (size_t)ps.W * small_len * 64) == JB_OK) {
-        precompute_windows_kernel<<<(unsigned)((small_len + 127) / 128), 128, 0, c->stream>>>(s.xy, small_len, ps.c, ps.W, s.pre_small);
-        c->launches++;
-        if (c->check(cudaGetLastError(), "precompute_windows (small) launch") == JB_OK &&
-            c->check(cudaStreamSynchronize(c->stream), "precompute sync") == JB_OK) {
-            s.pre_small_len = small_len;
-        } else {
-            c->dev_free(s.pre_small);
-            s.pre_small = nullptr;
-        }
-    } else {
-        s.pre_small = nullptr;  // optional: the plain path stays
-    }
+    build_small_table(c, s, 0);  // optional: the plain path stays without it
     return JB_OK;
 }
 
@@ -931,7 +1140,7 @@ int jb_msm_g1(jb_ctx* c, jb_srs h, size_t offset, const uint64_t* scalars, size_
 
 int jb_msm_g1_small(jb_ctx* c, jb_srs h, size_t offset, const void* scalars, size_t n, int kind, uint64_t out_xyz[12]) {
     if (!c || !out_xyz || (n && !scalars)) return JB_ERR_INVALID;
-    if (kind < SK_U8 || kind > SK_I128) return c->fail(JB_ERR_INVALID, "msm_small: unknown scalar kind");
+    if (kind < SK_U8 || kind > SK_LAST) return c->fail(JB_ERR_INVALID, "msm_small: unknown scalar kind");
     Guard g(c);
     auto it = c->srs.find(h);
     if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
@@ -946,8 +1155,96 @@ int jb_msm_g1_small(jb_ctx* c, jb_srs h, size_t offset, const void* scalars, siz
     int st = c->dev_alloc(&d_s, bytes);
     if (st != JB_OK) return st;
     st = c->check(cudaMemcpyAsync(d_s, scalars, bytes, cudaMemcpyHostToDevice, c->stream), "msm small scalars H2D");
-    if (st == JB_OK) st = msm_device(c, it->second, offset, d_s, n, out_xyz, kind);
+    // The reference's dispatch for u8 / bool columns (msm/mod.rs:35-47, 96-106): all zero -> identity, all <= 1 ->
+    // msm_binary, else msm_u8. One pass over the bytes decides (the reference's par_iter().all()); below 2^14 terms
+    // the general path is launch-latency either way.
+    unsigned int vmax = 2;
+    if (st == JB_OK && kind == SK_U8 && n >= ((size_t)1 << 14)) {
+        unsigned int* d_max = nullptr;
+        st = c->dev_alloc((void**)&d_max, 4);
+        if (st == JB_OK) st = c->check(cudaMemsetAsync(d_max, 0, 4, c->stream), "msm max memset");
+        if (st == JB_OK) {
+            u8_max_kernel<<<148 * 4, 256, 0, c->stream>>>((const uint8_t*)d_s, n, d_max);
+            c->launches++;
+            st = c->check(cudaMemcpyAsync(c->h_small, d_max, 4, cudaMemcpyDeviceToHost, c->stream), "msm max D2H");
+        }
+        if (st == JB_OK) st = c->check(cudaStreamSynchronize(c->stream), "msm max sync");
+        if (st == JB_OK) std::memcpy(&vmax, c->h_small, 4);
+        if (d_max) c->dev_free(d_max);
+    }
+    if (st == JB_OK) {
+        if (vmax == 0) identity_xyz(out_xyz);
+        else if (vmax == 1) st = msm_binary_device(c, it->second, offset, (const uint8_t*)d_s, n, out_xyz);
+        else st = msm_device(c, it->second, offset, d_s, n, out_xyz, kind);
+    }
     c->dev_free(d_s);
+    return st;
+}
+
+int jb_msm_g1_batch(jb_ctx* c, jb_srs h, size_t count, const void* const* scalars, const size_t* lens, const int* kinds,
+                    uint64_t* out_xyz) {
+    if (!c || (count && (!scalars || !lens || !kinds || !out_xyz))) return JB_ERR_INVALID;
+    size_t srs_n = 0;
+    {
+        Guard g(c);
+        auto it = c->srs.find(h);
+        if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+        srs_n = it->second.n;
+        for (size_t k = 0; k < count; ++k) {
+            if (kinds[k] < SK_FR || kinds[k] > SK_LAST) return c->fail(JB_ERR_INVALID, "batch_msm: unknown scalar kind");
+            if (lens[k] > srs_n) return c->fail(JB_ERR_LENGTH, "batch_msm: a column is longer than the base set");
+            if (lens[k] && !scalars[k]) return c->fail(JB_ERR_INVALID, "batch_msm: null column");
+        }
+    }
+    for (size_t k = 0; k < count; ++k) {
+        const int st = kinds[k] == SK_FR ? jb_msm_g1(c, h, 0, (const uint64_t*)scalars[k], lens[k], out_xyz + 12 * k)
+                                         : jb_msm_g1_small(c, h, 0, scalars[k], lens[k], kinds[k], out_xyz + 12 * k);
+        if (st != JB_OK) return st;
+    }
+    return JB_OK;
+}
+
+int jb_msm_g1_rows(jb_ctx* c, jb_srs h, const void* scalars, size_t rows, size_t row_width, int kind, uint64_t* out_xyz) {
+    if (!c || (rows && row_width && (!scalars || !out_xyz)) || (rows && !out_xyz)) return JB_ERR_INVALID;
+    if (kind < SK_FR || kind > SK_LAST) return c->fail(JB_ERR_INVALID, "msm_rows: unknown scalar kind");
+    if (rows == 0) return JB_OK;
+    if (row_width == 0) {
+        for (size_t r = 0; r < rows; ++r) identity_xyz(out_xyz + 12 * r);
+        return JB_OK;
+    }
+    const size_t esz = kind == SK_FR ? 32 : (size_t)small_kind_bytes(kind);
+    if (rows == 1)
+        return kind == SK_FR ? jb_msm_g1(c, h, 0, (const uint64_t*)scalars, row_width, out_xyz)
+                             : jb_msm_g1_small(c, h, 0, scalars, row_width, kind, out_xyz);
+    Guard g(c);
+    auto it = c->srs.find(h);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    if (row_width > it->second.n) return c->fail(JB_ERR_LENGTH, "msm: bases/scalars length mismatch");
+    int st = build_small_table(c, it->second, row_width);
+    if (st != JB_OK) return st;
+    // rows per pass: 32-bit offsets (entries < 2^28 keeps the workspace near 2 GiB) and <= 4 Mi histogram counters
+    const MsmPlan p = plan_with(8, small_kind_bits(kind));
+    size_t per = ((size_t)1 << 28) / ((size_t)p.W * row_width);
+    if (per > 32768) per = 32768;
+    if (per < 2) per = 2;
+    if ((size_t)p.W * row_width * per >= ((size_t)1 << 31)) return c->fail(JB_ERR_UNSUPPORTED, "msm_rows: row too wide (use jb_msm_g1_batch)");
+    for (size_t r0 = 0; r0 < rows && st == JB_OK; r0 += per) {
+        size_t cnt = rows - r0 < per ? rows - r0 : per;
+        const char* src = (const char*)scalars + r0 * row_width * esz;
+        if (cnt == 1) {  // a lone last row: the single-MSM path (by_rows needs >= 2 rows)
+            void* d1 = nullptr;
+            st = c->dev_alloc(&d1, row_width * esz);
+            if (st == JB_OK) st = c->check(cudaMemcpyAsync(d1, src, row_width * esz, cudaMemcpyHostToDevice, c->stream), "msm rows H2D");
+            if (st == JB_OK) st = msm_device(c, it->second, 0, d1, row_width, out_xyz + 12 * r0, kind);
+            if (d1) c->dev_free(d1);
+            continue;
+        }
+        void* d_s = nullptr;
+        st = c->dev_alloc(&d_s, cnt * row_width * esz);
+        if (st == JB_OK) st = c->check(cudaMemcpyAsync(d_s, src, cnt * row_width * esz, cudaMemcpyHostToDevice, c->stream), "msm rows H2D");
+        if (st == JB_OK) st = msm_device(c, it->second, 0, d_s, cnt * row_width, out_xyz + 12 * r0, kind, cnt);
+        if (d_s) c->dev_free(d_s);
+    }
     return st;
 }
 

@@ -11,6 +11,13 @@ namespace jb {
 
 // numeric values of jb_scalar_kind (include/jolt_b200.h)
 constexpr int SK_FR = 0, SK_U8 = 1, SK_U16 = 2, SK_U32 = 3, SK_U64 = 4, SK_U128 = 5, SK_I64 = 6, SK_I128 = 7;
+// sign-magnitude integers: jolt_field::signed::{S64, S128} = SignedBigInt<1>, SignedBigInt<2>
+// (crates/jolt-field/src/signed.rs:25-32; legacy msm_s64 / msm_s128, crates/jolt-prover-legacy/src/msm/mod.rs:140-158;
+// MultilinearPolynomial::S128Scalars, poly/multilinear_polynomial.rs:33). Records of N u64 magnitude limbs followed by
+// one sign byte (is_positive), padded to a multiple of 8: jb_s64 = 16 bytes, jb_s128 = 24 bytes (include/jolt_b200.h).
+// "Zero is not canonicalized" (signed.rs:16-17): -0 is 0.
+constexpr int SK_S64 = 8, SK_S128 = 9;
+constexpr int SK_LAST = SK_S128;
 
 __host__ __device__ inline int small_kind_bytes(int kind) {
     switch (kind) {
@@ -19,6 +26,8 @@ __host__ __device__ inline int small_kind_bytes(int kind) {
         case SK_U32: return 4;
         case SK_U64: case SK_I64: return 8;
         case SK_U128: case SK_I128: return 16;
+        case SK_S64: return 16;   // record stride (8 magnitude + 1 sign + 7 padding)
+        case SK_S128: return 24;  // (16 magnitude + 1 sign + 7 padding)
         default: return 0;
     }
 }
@@ -29,8 +38,8 @@ __host__ __device__ inline int small_kind_bits(int kind) {
         case SK_U8: return 8;
         case SK_U16: return 16;
         case SK_U32: return 32;
-        case SK_U64: case SK_I64: return 64;
-        case SK_U128: case SK_I128: return 128;
+        case SK_U64: case SK_I64: case SK_S64: return 64;
+        case SK_U128: case SK_I128: case SK_S128: return 128;
         default: return 254;
     }
 }
@@ -64,8 +73,20 @@ __device__ __forceinline__ bool ld_small(const void* values, size_t i, int kind,
             }
             break;
         }
+        case SK_S64: {
+            lo = ((const uint64_t*)values)[2 * i];
+            neg = (((const uint64_t*)values)[2 * i + 1] & 0xffull) == 0;  // is_positive == false
+            break;
+        }
+        case SK_S128: {
+            lo = ((const uint64_t*)values)[3 * i];
+            hi = ((const uint64_t*)values)[3 * i + 1];
+            neg = (((const uint64_t*)values)[3 * i + 2] & 0xffull) == 0;
+            break;
+        }
         default: break;
     }
+    if ((lo | hi) == 0) neg = false;  // -0 (representable by the sign-magnitude kinds) is 0
     mag[0] = (uint32_t)lo;
     mag[1] = (uint32_t)(lo >> 32);
     mag[2] = (uint32_t)hi;

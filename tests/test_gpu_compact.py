@@ -1,7 +1,8 @@
 """Compact (primitive-integer) columns on the device vs the oracle.
   * promotion F::from(T)            crates/jolt-field/src/bn254/mod.rs:265-298 (from_u64/from_i64/from_u128/from_i128)
   * Polynomial<T>::bind_to_field    crates/jolt-poly/src/dense.rs:129-142 (test bind_matches_bind_to_field, :613-625)
-  * small-scalar MSMs               crates/jolt-prover-legacy/src/msm/mod.rs:27-150 (msm_u8 .. msm_i128, msm_binary)
+  * small-scalar MSMs               crates/jolt-prover-legacy/src/msm/mod.rs:27-158 (msm_u8 .. msm_i128, msm_s64 / msm_s128,
+                                    msm_binary), batch_msm / batch_msm_univariate :160-181
 Every result is compared bit-for-bit with the oracle applied to the promoted values (v mod r)."""
 import numpy as np
 import pytest
@@ -14,9 +15,11 @@ from oracle import coracle as C
 pytestmark = pytest.mark.gpu
 
 G = np.array(O.to_mont_limbs(1, O.Q_MOD) + O.to_mont_limbs(2, O.Q_MOD), dtype=np.uint64)
-KINDS = ["u8", "u16", "u32", "u64", "i64", "u128", "i128"]
+KINDS = ["u8", "u16", "u32", "u64", "i64", "u128", "i128", "s64", "s128"]
 RANGE = {"u8": (0, 1 << 8), "u16": (0, 1 << 16), "u32": (0, 1 << 32), "u64": (0, 1 << 64),
-         "i64": (-(1 << 63), 1 << 63), "u128": (0, 1 << 128), "i128": (-(1 << 127), 1 << 127)}
+         "i64": (-(1 << 63), 1 << 63), "u128": (0, 1 << 128), "i128": (-(1 << 127), 1 << 127),
+         # sign-magnitude (crates/jolt-field/src/signed.rs:25-32): the full unsigned magnitude with either sign
+         "s64": (-(1 << 64) + 1, 1 << 64), "s128": (-(1 << 128) + 1, 1 << 128)}
 DTYPE = {"u8": np.uint8, "u16": np.uint16, "u32": np.uint32, "u64": np.uint64, "i64": np.int64}
 
 
@@ -159,3 +162,84 @@ def test_msm_small_with_precomputed_srs_and_offsets(sess, srs_bases):
         want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
         assert g1_jacobian_to_affine(big.msm_small(a, kind=k)) == want, kind
     big.free()
+
+
+def test_sign_magnitude_negative_zero_and_extremes(sess, srs_bases):
+    # "Zero is not canonicalized: a zero magnitude may carry either sign" (crates/jolt-field/src/signed.rs:16-17;
+    # limbs_signed_differential.rs:239-240 builds both): -0 promotes to 0 and contributes nothing to an MSM
+    n = 8
+    m64, m128 = (1 << 64) - 1, (1 << 128) - 1
+    for kind, top in (("s64", m64), ("s128", m128)):
+        recs = [(0, False), (0, True), (1, False), (1, True), (top, False), (top, True), (5, False), (7, True)]
+        vals = [m if pos else -m for m, pos in recs]
+        p = Polynomial.from_small(sess, recs, kind)
+        assert p.to_ints() == [v % O.R_MOD for v in vals], kind
+        p.free()
+        bases = G1Bases.from_affine(sess, srs_bases[:n])
+        sc = C.ints_to_mont([v % O.R_MOD for v in vals])
+        want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, 1))
+        assert g1_jacobian_to_affine(bases.msm_small(recs, kind=kind)) == want, kind
+        bases.free()
+
+
+def test_batch_msm_matches_single_msms(sess, srs_bases):
+    # batch_msm: every column against the prefix bases[..len] (msm/mod.rs:160-168); batch_msm_univariate: field columns (:170-181)
+    n = 1 << 11
+    bases = G1Bases.from_affine(sess, srs_bases[:n])
+    rng = np.random.default_rng(21)
+    fr_col = C.ints_to_mont(O.random_fr(5, 700))
+    cols = [
+        rng.integers(0, 2, size=n).astype(np.uint8),          # binary -> msm_binary arm
+        np.zeros(300, dtype=np.uint8),                        # all zero -> identity
+        rng.integers(0, 1 << 16, size=1000).astype(np.uint16),
+        rng.integers(-(1 << 62), 1 << 62, size=n).astype(np.int64),
+        (column("s128", 513, 4), "s128"),
+        (column("i128", 64, 6), "i128"),
+        fr_col,                                               # LargeScalars / UniPoly coefficients
+        np.zeros(0, dtype=np.uint32),                         # empty column -> identity
+    ]
+    got = bases.batch_msm(cols)
+    assert got.shape == (len(cols), 12)
+    for j, col in enumerate(cols):
+        if isinstance(col, tuple):
+            vals = [int(v) for v in col[0]]
+        elif col.dtype == np.uint64 and col.ndim == 2:
+            vals = None
+        else:
+            vals = [int(v) for v in col]
+        sc = col if vals is None else C.ints_to_mont([v % O.R_MOD for v in vals])
+        m = len(sc)
+        want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:m], sc, 0, C.max_threads())) if m else None
+        assert g1_jacobian_to_affine(got[j]) == want, j
+    with pytest.raises(jolt_b200.JoltB200Error, match="longer than the base set"):
+        bases.batch_msm([np.zeros(n + 1, dtype=np.uint8)])
+    bases.free()
+
+
+@pytest.mark.parametrize("rows,width", [(2, 64), (5, 256), (37, 1 << 10), (3, 1 << 13)])
+def test_msm_rows_matches_row_msms(sess, srs_bases, rows, width):
+    # Dory tier-1: one MSM per matrix row against the same bases (crates/jolt-dory/src/streaming.rs:113-201)
+    bases = G1Bases.from_affine(sess, srs_bases[:width])
+    kinds = ["u64", "i128", "s64", "u8"] if width <= 1 << 10 else ["i64"]
+    for kind in kinds:
+        vals = column(kind, rows * width, 100 + rows)
+        if kind == "u8":   # one binary row, one zero row, one constant row (every point of the row in one bucket)
+            vals[:width] = [v & 1 for v in vals[:width]]
+            vals[width:2 * width] = [0] * width
+            if rows > 2:
+                vals[2 * width:3 * width] = [200] * width
+        a, k = as_input(kind, vals)
+        got = bases.msm_rows(a, rows, kind=k)
+        for r in range(rows):
+            sc = C.ints_to_mont([v % O.R_MOD for v in vals[r * width:(r + 1) * width]])
+            want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:width], sc, 0, C.max_threads()))
+            assert g1_jacobian_to_affine(got[r]) == want, (kind, r)
+    if width <= 256:   # field rows (DoryScheme::feed)
+        sc = C.ints_to_mont(O.random_fr(rows, rows * width))
+        got = bases.msm_rows(sc, rows, kind="fr")
+        for r in range(rows):
+            want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:width], sc[r * width:(r + 1) * width], 0, C.max_threads()))
+            assert g1_jacobian_to_affine(got[r]) == want, ("fr", r)
+    with pytest.raises(jolt_b200.JoltB200Error, match="length mismatch"):
+        bases.msm_rows(np.zeros(2 * (width + 1), dtype=np.uint8), 2)
+    bases.free()
