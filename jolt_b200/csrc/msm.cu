@@ -19,6 +19,7 @@
 // (mod.rs:205) becomes a one-time normalisation at upload.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,7 +31,17 @@ using namespace jb;
 
 namespace {
 
-constexpr int MSM_SEG = 16;  // buckets per reduction segment
+// buckets per reduction segment: one thread walks a segment (2 general additions per bucket, then [lo] * run by
+// double-and-add), so the segment kernel is a latency chain, not work: 8 instead of 16 buckets halves the chain.
+// JB_MSM_SEG overrides (A/B).
+int msm_seg_size() {
+    static const int v = [] {
+        const char* e = getenv("JB_MSM_SEG");
+        const int x = e ? atoi(e) : 8;
+        return x >= 2 && x <= 64 ? x : 8;
+    }();
+    return v;
+}
 
 struct MsmPlan {
     int c;        // window bits
@@ -46,7 +57,7 @@ MsmPlan plan_with(int c, int bits = 254) {
     p.W = (bits + c - 1) / c;
     if (bits - (p.W - 1) * c > c - 1) p.W += 1;  // top window: data < 2^(c-1), so data + carry <= 2^(c-1) = B
     p.B = 1 << (c - 1);
-    p.T = (p.B + MSM_SEG - 1) / MSM_SEG;
+    p.T = (p.B + msm_seg_size() - 1) / msm_seg_size();
     return p;
 }
 
@@ -367,16 +378,24 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* offs
 template <bool AGG>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B, int shared,
                                                           size_t stride, const unsigned int* offsets, unsigned int* cursor,
-                                                          uint32_t* sorted, size_t row_w) {
+                                                          uint32_t* sorted, size_t row_w, int mode, unsigned range_shift) {
+    // mode 0: every window in this thread. The positions are random within the destination, and a random 4-byte
+    // store dirties a 32-byte sector: once the destination (4 B x windows x terms) outgrows the L2, the scatter runs at
+    // the DRAM's sector rate (6.6 ms for 2^24 terms). So big MSMs order the work in TIME by destination region, one
+    // grid row (blockIdx.y) per region, so that the region being filled stays in the L2 until its sectors are complete:
+    // mode 1 (one bucket set per window): region = window; mode 2 (one shared bucket set): region = a bucket range
+    // (slot >> range_shift); every row re-reads the digits (coalesced, cheap) and keeps its own entries.
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     if (!AGG && !valid) return;
     const int lane = threadIdx.x & 31;
     const size_t row_slot = row_w && valid ? (i / row_w) * (size_t)B : 0;
     const size_t col = row_w ? i % row_w : i;  // index into the bases / a table row
-    for (int w = 0; w < W; ++w) {
+    const int w_lo = mode == 1 ? (int)blockIdx.y : 0, w_hi = mode == 1 ? (int)blockIdx.y + 1 : W;
+    for (int w = w_lo; w < w_hi; ++w) {
         uint32_t enc = valid ? digits[(size_t)w * n + i] : 0u;
         const size_t slot = (shared ? row_slot : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
+        if (mode == 2 && enc && (unsigned)(slot >> range_shift) != blockIdx.y) enc = 0;
         unsigned int pos;
         if (AGG) {
             // one atomic per distinct slot in the warp; lanes take consecutive positions in lane order
@@ -449,13 +468,13 @@ __global__ void __launch_bounds__(128) msm_combine_kernel(const unsigned int* to
 }
 
 // ---- 5. segment sums: G = sum_{b in segment} (b + 1) * B_b ---------------------------------------------
-__global__ void __launch_bounds__(128) msm_segment_kernel(const uint64_t* buckets, int W, int B, int T,
+__global__ void __launch_bounds__(128) msm_segment_kernel(const uint64_t* buckets, int W, int B, int T, int seg_size,
                                                           uint64_t* seg_out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)W * T) return;
     int w = (int)(t / T), seg = (int)(t % T);
-    int lo = seg * MSM_SEG;
-    int hi = lo + MSM_SEG < B ? lo + MSM_SEG : B;
+    int lo = seg * seg_size;
+    int hi = lo + seg_size < B ? lo + seg_size : B;
     XYZZ run = XYZZ::inf(), acc = XYZZ::inf();
     for (int b = hi - 1; b >= lo; --b) {
         XYZZ bk = ld_xyzz(buckets, (size_t)w * B + b);
@@ -838,10 +857,26 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
-        if (agg)
-            msm_scatter_kernel<true><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w);
-        else
-            msm_scatter_kernel<false><<<g, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w);
+        {   // scatter, ordered in time by destination region once the destination outgrows the L2 (see the kernel)
+            const size_t entries = (size_t)p.W * n;
+            int mode = 0, regions = 1;
+            unsigned range_shift = 0;
+            if (!by_rows && entries >= ((size_t)1 << 25)) {
+                if (!shared) {
+                    mode = 1;
+                    regions = p.W;
+                } else if (p.c - 1 >= 6) {
+                    mode = 2;
+                    regions = entries >= ((size_t)1 << 27) ? 8 : 4;
+                    range_shift = (unsigned)(p.c - 1) - (regions == 8 ? 3u : 2u);  // nb = 2^(c-1) buckets
+                }
+            }
+            const dim3 sg(g, (unsigned)regions);
+            if (agg)
+                msm_scatter_kernel<true><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, mode, range_shift);
+            else
+                msm_scatter_kernel<false><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, mode, range_shift);
+        }
         msm_len_hist_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist);
         msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist, task_bucket, order);
         c->launches++;
@@ -854,7 +889,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
             msm_combine_wide_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(toff, partial, buckets);
             c->launches++;
         }
-        msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, seg);
+        msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, msm_seg_size(), seg);
         {   // tree-sum the T segment points of every bucket set, ping-ponging between two scratch buffers
             const uint64_t* src = seg;
             int count = p.T;
