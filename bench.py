@@ -380,21 +380,42 @@ def kernels_section(sess, peak_hbm: float, with_cpu: bool):
             acc = [t for t in sess.timing_collect() if t["kind"] == "msm_accumulate"]
             sess.timing_enable(False)
             acc_ms = min(t["ms"] for t in acc) if acc else None
-            c_bits = acc[0]["m"] if acc else None
+            c_bits = acc[0]["m"] % 100 if acc else None
+            ba_levels = acc[0]["m"] // 100 if acc else 0   # batched-affine levels in front of the XYZZ accumulation
             windows = -(-254 // c_bits) if c_bits else None
             adds = nn * windows if windows else None
             row = {"log_n": lg, "srs": label, "ms": ms, "terms_per_s": nn / (ms * 1e-3), "window_bits": c_bits, "windows": windows,
-                   "accumulate_kernel_ms": acc_ms}
+                   "accumulate_kernel_ms": acc_ms, "batched_affine_levels": ba_levels}
             if acc_ms:
                 rate = adds / (acc_ms * 1e-3)
-                ceiling = g_mul["fq_full"] * 1e9 / 10.0
-                row.update(bucket_adds_per_s=rate, integer_ceiling_adds_per_s=ceiling, frac_of_integer_ceiling=rate / ceiling,
+                # Fq products per bucket addition: 10 for a mixed XYZZ addition; with L affine levels the share
+                # 1 - 2^-L of the additions costs ~6.3 (5M + 1S + the prefix / peel products of the shared inversion)
+                per_add = 10.0 if not ba_levels else 6.3 * (1 - 0.5 ** ba_levels) + 10.0 * 0.5 ** ba_levels
+                ceiling = g_mul["fq_full"] * 1e9 / per_add
+                row.update(bucket_adds_per_s=rate, fq_products_per_addition=per_add, integer_ceiling_adds_per_s=ceiling,
+                           frac_of_integer_ceiling=rate / ceiling,
                            hbm_gb_per_s=(adds * 68) / (acc_ms * 1e-3) / 1e9, frac_of_hbm_peak=(adds * 68) / (acc_ms * 1e-3) / 1e9 / peak_hbm)
             msms.append(row)
         bases.free()
         tab.free()
-    out["msm_g1"] = {"bound": "integer pipe (10 Fq products per mixed XYZZ bucket addition); 68 B gathered per addition",
-                     "runs": msms}
+    out["msm_g1"] = {"bound": "integer pipe (10 Fq products per mixed XYZZ bucket addition, ~6.3 per batched-affine addition); 68 B gathered per addition",
+                     "accumulate_kernel_ms": "batched-affine levels (if any) + the XYZZ accumulation kernel", "runs": msms}
+
+    # ---- row-batched small-scalar MSM (Dory tier-1 rows) and a binary column ---------------------
+    rows_n, row_w = 1024, 4096
+    bases = G1Bases.generate_multiples(sess, G, 1 << 22)
+    rngm = np.random.Generator(np.random.PCG64(0xD0))
+    mat = rngm.integers(0, 1 << 64, size=rows_n * row_w, dtype=np.uint64)
+    bases.msm_rows(mat, rows_n)  # builds the 8-bit window table of the first row_w bases once
+    t_rows = timed(lambda a: bases.msm_rows(mat, rows_n), reps=3)
+    t_loop = timed(lambda a: [bases.msm_small(mat[r * row_w:(r + 1) * row_w]) for r in range(16)], reps=2) / 16 * rows_n
+    bits = rngm.integers(0, 2, size=1 << 22, dtype=np.uint8)
+    bases.msm_small(bits)
+    t_bin = timed(lambda a: bases.msm_small(bits), reps=3)
+    out["msm_rows_u64_1024x4096"] = {"ms": t_rows, "terms_per_s": rows_n * row_w / (t_rows * 1e-3), "row_by_row_ms_extrapolated_from_16_rows": t_loop,
+                                     "note": "jb_msm_g1_rows: host scalars (H2D of 8 B/term inside), one pipeline pass over (row, bucket) sets"}
+    out["msm_binary_2^22"] = {"ms": t_bin, "terms_per_s": (1 << 22) / (t_bin * 1e-3), "note": "msm_binary arm: host flags (1 B/term H2D inside), select-sum kernel"}
+    bases.free()
 
     # ---- HyperKZG open, ell = 22 (precomputed SRS) ----------------------------------------------
     ell = 22

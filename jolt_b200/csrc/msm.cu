@@ -25,20 +25,22 @@
 
 #include "ctx.hpp"
 #include "ec.cuh"
+#include "msm_affine.cuh"
 #include "small_scalar.cuh"
 
 using namespace jb;
 
 namespace {
 
-// buckets per reduction segment: one thread walks a segment (2 general additions per bucket, then [lo] * run by
-// double-and-add), so the segment kernel is a latency chain, not work: 8 instead of 16 buckets halves the chain.
-// JB_MSM_SEG overrides (A/B).
+// buckets per reduction segment: one thread walks a segment (2 general additions per bucket) and then multiplies the
+// segment's plain sum by its first bucket number (double-and-add, ~330 products): the multiplication is per SEGMENT, so
+// short segments cost work (measured at 2^20 / 2^24 terms, precomputed SRS: 8 buckets 0.88 / 3.76 ms, 16 buckets
+// 0.55 / 2.38 ms). JB_MSM_SEG overrides (A/B).
 int msm_seg_size() {
     static const int v = [] {
         const char* e = getenv("JB_MSM_SEG");
-        const int x = e ? atoi(e) : 8;
-        return x >= 2 && x <= 64 ? x : 8;
+        const int x = e ? atoi(e) : 16;
+        return x >= 2 && x <= 256 ? x : 16;
     }();
     return v;
 }
@@ -233,17 +235,24 @@ __device__ __forceinline__ void block_exclusive_scan2(unsigned int& a, unsigned 
     __syncthreads();
 }
 
+// pad_shift = L > 0 (batched-affine levels, msm_affine.cuh): the point offsets are scanned over counts padded to a
+// multiple of 2^L and the tasks are planned over the ceil(cnt / 2^L) points a bucket has left after L halvings.
 __global__ void __launch_bounds__(1024) msm_scan_local_kernel(unsigned int* hist, unsigned int* offsets, unsigned int* toff,
-                                                              size_t total, unsigned int* block_sums, unsigned maxq) {
+                                                              size_t total, unsigned int* block_sums, unsigned maxq,
+                                                              unsigned pad_shift) {
     __shared__ unsigned int sm_a[32], sm_b[32];
     const size_t base = (size_t)blockIdx.x * SCAN_PER_BLOCK + (size_t)threadIdx.x * 4;
     unsigned int c[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if (base + k < total) c[k] = hist[base + k];
+    const unsigned pad_mask = (1u << pad_shift) - 1u;
     unsigned int q[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) q[k] = chunk_count(c[k], maxq);
+    for (int k = 0; k < 4; ++k) {
+        c[k] = (c[k] + pad_mask) & ~pad_mask;
+        q[k] = chunk_count(c[k] >> pad_shift, maxq);
+    }
     unsigned int sa = c[0] + c[1] + c[2] + c[3], sb = q[0] + q[1] + q[2] + q[3], ta, tb;
     block_exclusive_scan2(sa, sb, sm_a, sm_b, ta, tb);
 #pragma unroll
@@ -302,46 +311,33 @@ __device__ __forceinline__ int task_len_bin(unsigned cnt, unsigned maxq) {
     const unsigned len = chunk_len(cnt, maxq);
     return MSM_LEN_BINS - 1 - (int)(len < (unsigned)(MSM_LEN_BINS - 1) ? len : (unsigned)(MSM_LEN_BINS - 1));
 }
-// among the lanes of the warp with the same bin: q summed over the lower lanes (pre), over all of them (tot), and the
-// first lane with q > 0 (first; -1 if none). Uniform loop: every lane of the warp takes part.
-__device__ __forceinline__ void warp_bin_group(int bin, unsigned q, unsigned& pre, unsigned& tot, int& first) {
-    const int lane = threadIdx.x & 31;
-    pre = 0;
-    tot = 0;
-    first = -1;
-#pragma unroll 4
-    for (int l = 0; l < 32; ++l) {
-        const unsigned v = __shfl_sync(0xffffffffu, q, l);
-        const int bl = __shfl_sync(0xffffffffu, bin, l);
-        if (bl == bin && v) {
-            if (l < lane) pre += v;
-            tot += v;
-            if (first < 0) first = l;
-        }
-    }
-}
+// Both kernels run a fixed grid; block g owns the contiguous bucket range [g * per, (g + 1) * per) and counts in shared
+// memory, so the 256 global counters see one atomic per (block, non-empty bin) instead of one per warp and bin.
+constexpr int MSM_TASK_BLOCKS = 592;
 __global__ void __launch_bounds__(256) msm_len_hist_kernel(const unsigned int* offsets, const unsigned int* toff, size_t nbuckets,
-                                                           unsigned maxq, unsigned int* len_hist) {
-    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = b < nbuckets;
-    const unsigned cnt = valid ? offsets[b + 1] - offsets[b] : 0u;
-    const unsigned q = valid ? toff[b + 1] - toff[b] : 0u;
-    const int bin = task_len_bin(cnt, maxq);
-    unsigned pre, tot;
-    int first;
-    warp_bin_group(bin, q, pre, tot, first);
-    if (q && first == (int)(threadIdx.x & 31)) atomicAdd(&len_hist[bin], tot);
+                                                           unsigned maxq, unsigned int* len_hist, unsigned shift) {
+    __shared__ unsigned int cnt_s[MSM_LEN_BINS];
+    cnt_s[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t per = (nbuckets + gridDim.x - 1) / gridDim.x;
+    const size_t b0 = (size_t)blockIdx.x * per, b1 = b0 + per < nbuckets ? b0 + per : nbuckets;
+    for (size_t b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
+        const unsigned q = toff[b + 1] - toff[b];
+        if (q) atomicAdd(&cnt_s[task_len_bin((offsets[b + 1] - offsets[b]) >> shift, maxq)], q);
+    }
+    __syncthreads();
+    if (cnt_s[threadIdx.x]) atomicAdd(&len_hist[threadIdx.x], cnt_s[threadIdx.x]);
 }
 // len_hist: [0, 256) task counts per bin (read), [256, 512) cursors (zero on entry)
 __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* offsets, const unsigned int* toff, size_t nbuckets,
                                                         unsigned maxq, unsigned int* len_hist, uint32_t* task_bucket,
-                                                        uint32_t* order) {
-    __shared__ unsigned int bin_start[MSM_LEN_BINS];
+                                                        uint32_t* order, unsigned shift) {
+    __shared__ unsigned int bin_base[MSM_LEN_BINS], cnt_s[MSM_LEN_BINS], tmp[MSM_LEN_BINS];
+    const int k = threadIdx.x;
     {   // exclusive scan of the 256 bin counts (Hillis-Steele in shared memory)
-        __shared__ unsigned int tmp[MSM_LEN_BINS];
-        const int k = threadIdx.x;
-        unsigned v = len_hist[k];
+        const unsigned v = len_hist[k];
         tmp[k] = v;
+        cnt_s[k] = 0;
         __syncthreads();
         for (int off = 1; off < MSM_LEN_BINS; off <<= 1) {
             const unsigned add = k >= off ? tmp[k - off] : 0u;
@@ -349,26 +345,28 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* offs
             tmp[k] += add;
             __syncthreads();
         }
-        bin_start[k] = tmp[k] - v;
-        __syncthreads();
+        bin_base[k] = tmp[k] - v;  // start of bin k in `order`
     }
-    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = b < nbuckets;
-    const unsigned cnt = valid ? offsets[b + 1] - offsets[b] : 0u;
-    const unsigned t0 = valid ? toff[b] : 0u;
-    const unsigned q = valid ? toff[b + 1] - t0 : 0u;
-    const int bin = task_len_bin(cnt, maxq);
-    unsigned pre, tot;
-    int first;
-    warp_bin_group(bin, q, pre, tot, first);
-    unsigned base = 0;
-    if (q && first == (int)(threadIdx.x & 31)) base = atomicAdd(&len_hist[MSM_LEN_BINS + bin], tot);
-    base = __shfl_sync(0xffffffffu, base, first < 0 ? 0 : first);
-    if (!q) return;
-    const unsigned pos = bin_start[bin] + base + pre;
-    for (unsigned j = 0; j < q; ++j) {
-        task_bucket[t0 + j] = (uint32_t)b;
-        order[pos + j] = t0 + j;
+    __syncthreads();
+    const size_t per = (nbuckets + gridDim.x - 1) / gridDim.x;
+    const size_t b0 = (size_t)blockIdx.x * per, b1 = b0 + per < nbuckets ? b0 + per : nbuckets;
+    for (size_t b = b0 + k; b < b1; b += blockDim.x) {  // this block's tasks per bin
+        const unsigned q = toff[b + 1] - toff[b];
+        if (q) atomicAdd(&cnt_s[task_len_bin((offsets[b + 1] - offsets[b]) >> shift, maxq)], q);
+    }
+    __syncthreads();
+    if (cnt_s[k]) bin_base[k] += atomicAdd(&len_hist[MSM_LEN_BINS + k], cnt_s[k]);  // this block's share of bin k
+    cnt_s[k] = 0;
+    __syncthreads();
+    for (size_t b = b0 + k; b < b1; b += blockDim.x) {
+        const unsigned t0 = toff[b], q = toff[b + 1] - t0;
+        if (!q) continue;
+        const int bin = task_len_bin((offsets[b + 1] - offsets[b]) >> shift, maxq);
+        const unsigned pos = bin_base[bin] + atomicAdd(&cnt_s[bin], q);
+        for (unsigned j = 0; j < q; ++j) {
+            task_bucket[t0 + j] = (uint32_t)b;
+            order[pos + j] = t0 + j;
+        }
     }
 }
 
@@ -393,7 +391,7 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
     const size_t col = row_w ? i % row_w : i;  // index into the bases / a table row
     const int w_lo = mode == 1 ? (int)blockIdx.y : 0, w_hi = mode == 1 ? (int)blockIdx.y + 1 : W;
     for (int w = w_lo; w < w_hi; ++w) {
-        uint32_t enc = valid ? digits[(size_t)w * n + i] : 0u;
+        uint32_t enc = valid ? __ldcs(&digits[(size_t)w * n + i]) : 0u;  // streaming: leave the L2 to the destination
         const size_t slot = (shared ? row_slot : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
         if (mode == 2 && enc && (unsigned)(slot >> range_shift) != blockIdx.y) enc = 0;
         unsigned int pos;
@@ -418,16 +416,19 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
 // ---- 4. bucket accumulation: the hot kernel. One thread per task (a chunk of one bucket's list). A
 //         single-chunk bucket is written straight to `buckets`; chunks of a split bucket go to `partial`
 //         and are folded by msm_combine_kernel. --------------------------------------------------------
+// DIRECT (after the batched-affine levels): `bases` is the level-L point array, bucket b owns its entries
+// [offsets[b] >> shift, offsets[b + 1] >> shift) - affine points or the identity (0, 0) - and there is no index list.
+template <bool DIRECT>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bases, const uint32_t* sorted,
                                                              const unsigned int* offsets, const unsigned int* toff,
                                                              const uint32_t* task_bucket, const uint32_t* order,
                                                              size_t nbuckets, uint64_t* buckets, uint64_t* partial,
-                                                             unsigned maxq) {
+                                                             unsigned maxq, unsigned shift) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= toff[nbuckets]) return;
     const size_t t = order[k];  // tasks in length order (msm_tasks_kernel)
     const uint32_t b = task_bucket[t];
-    const unsigned int base = offsets[b], cnt = offsets[b + 1] - base;
+    const unsigned int base = offsets[b] >> shift, cnt = (offsets[b + 1] >> shift) - base;
     const unsigned int len = chunk_len(cnt, maxq), j = (unsigned int)t - toff[b];
     unsigned int lo = base + j * len;
     unsigned int hi = lo + len < base + cnt ? lo + len : base + cnt;
@@ -436,20 +437,23 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint64_t* bas
     // (the addresses come from the index list, not from the running sum).
     uint32_t e_next = 0;
     Fq nx = Fq::zero(), ny = Fq::zero();
-    if (lo < hi) {
-        e_next = sorted[lo];
-        nx = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu));
-        ny = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu) + 1);
-    }
-    for (unsigned int k = lo; k < hi; ++k) {
-        const uint32_t e = e_next;
-        const Fq px = nx, py = ny;
-        if (k + 1 < hi) {
-            e_next = sorted[k + 1];
+    auto fetch = [&](unsigned int at) {
+        if (DIRECT) {
+            nx = ld_elem_rw<Fq>(bases, 2 * (size_t)at);
+            ny = ld_elem_rw<Fq>(bases, 2 * (size_t)at + 1);
+        } else {
+            e_next = sorted[at];
             nx = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu));
             ny = ld_elem<Fq>(bases, 2 * (size_t)(e_next & 0x7fffffffu) + 1);
         }
-        xyzz_add_affine(acc, px, py, (e >> 31) != 0);
+    };
+    if (lo < hi) fetch(lo);
+    for (unsigned int i = lo; i < hi; ++i) {
+        const uint32_t e = e_next;
+        const Fq px = nx, py = ny;
+        if (i + 1 < hi) fetch(i + 1);
+        if (DIRECT && px.is_zero() && py.is_zero()) continue;  // a hole, or a pair that cancelled
+        xyzz_add_affine(acc, px, py, !DIRECT && (e >> 31) != 0);
     }
     if (toff[b + 1] - toff[b] == 1) st_xyzz(buckets, b, acc);
     else st_xyzz(partial, t, acc);
@@ -807,7 +811,12 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
     // Small MSMs (the tail of HyperKZG's intermediate commitments, verifier-sized MSMs) use a second, tiny
     // table with 8-bit windows over the first bases: 128 buckets, no doubling chain - latency, not work.
-    const bool use_small = by_rows || (srs.pre_small != nullptr && n <= 4096 && offset + n <= srs.pre_small_len);
+    static const size_t small_max = [] {  // JB_MSM_SMALL_MAX: largest MSM served by the 8-bit-window table (A/B)
+        const char* e = getenv("JB_MSM_SMALL_MAX");
+        const long v = e ? atol(e) : 4096;
+        return (size_t)(v > 0 ? v : 4096);
+    }();
+    const bool use_small = by_rows || (srs.pre_small != nullptr && n <= small_max && offset + n <= srs.pre_small_len);
     const bool use_big = !use_small && srs.pre != nullptr && n >= ((size_t)1 << (srs.pre_c - 4));
     const bool shared = use_small || use_big;
     const MsmPlan p = use_small ? plan_with(8, bits) : use_big ? plan_with(srs.pre_c, bits) : plan_for(n, bits);
@@ -822,6 +831,30 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
         return c->fail(JB_ERR_UNSUPPORTED, "msm: windows x terms must be < 2^32 (split the call)");
     // upper bound on tasks: every bucket at most cnt/MSM_CHUNK + 1 chunks
     const size_t max_tasks = nb + ((size_t)p.W * n) / MSM_CHUNK + 1;
+    // Batched-affine levels (msm_affine.cuh): field scalars only (uniform digits: a bucket holds ~entries / nb points)
+    // and only while a bucket still has several points per level. OFF by default: built, exact (tests force it at 2^13
+    // terms, exceptional pairs included) and measured SLOWER than the XYZZ accumulation it replaces - 2^24 terms,
+    // precomputed SRS: 30.6 ms of XYZZ accumulation (0.99 of the 10-products-per-addition ceiling once the tasks are
+    // walked in length order) against 35.2 / 36.2 / 38.2 ms with 2 / 3 / 4 affine levels in front of it; the level
+    // kernel reaches ~5.4 G additions/s = half of ITS ceiling (one thread's inversion idles its block, and the
+    // load - multiply - store chains of a thread expose the memory latency that the XYZZ walk hides behind 10 products).
+    // JB_MSM_BA = levels switches it on, JB_MSM_BA_MIN_LOG = log2 of the smallest windows x terms product that takes
+    // the path (tests lower it).
+    const size_t entries = (size_t)p.W * n;
+    unsigned ba_levels = 0;
+    if (kind == SK_FR && !by_rows && !use_small) {
+        const char* e_lv = getenv("JB_MSM_BA");
+        const char* e_min = getenv("JB_MSM_BA_MIN_LOG");
+        const int want = e_lv ? atoi(e_lv) : 0;
+        const int min_log = e_min ? atoi(e_min) : 26;
+        if (want > 0 && want <= 8 && entries >= ((size_t)1 << min_log)) {
+            ba_levels = (unsigned)want;
+            while (ba_levels > 0 && (entries / nb) >> ba_levels < 2) --ba_levels;  // keep >= 2 points per bucket and level
+        }
+    }
+    const size_t e_pad = entries + (ba_levels ? nb * (((size_t)1 << ba_levels) - 1) : 0);  // padded list length (bound)
+    if (e_pad >= ((size_t)1 << 32)) return c->fail(JB_ERR_UNSUPPORTED, "msm: windows x terms must be < 2^32 (split the call)");
+    uint64_t *lvl_a = nullptr, *lvl_b = nullptr, *ba_prefix = nullptr;
     uint32_t *digits = nullptr, *sorted = nullptr, *task_bucket = nullptr, *order = nullptr;
     unsigned int* len_hist = nullptr;
     unsigned int *hist = nullptr, *offsets = nullptr, *toff = nullptr, *block_sums = nullptr;
@@ -830,7 +863,13 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     uint64_t *tree_a = nullptr, *tree_b = nullptr;
     const size_t tree_pts = (size_t)Weff * ((p.T + 2047) / 2048) + 1;
     int st = c->dev_alloc((void**)&digits, (size_t)p.W * n * 4);
-    if (st == JB_OK) st = c->dev_alloc((void**)&sorted, (size_t)p.W * n * 4);
+    if (st == JB_OK) st = c->dev_alloc((void**)&sorted, e_pad * 4);
+    if (ba_levels) {
+        if (st == JB_OK) st = c->dev_alloc((void**)&lvl_a, (e_pad / 2 + 1) * 64);
+        if (st == JB_OK && ba_levels > 1) st = c->dev_alloc((void**)&lvl_b, (e_pad / 4 + 1) * 64);
+        if (st == JB_OK) st = c->dev_alloc((void**)&ba_prefix, (e_pad / 2 + 1) * 32);
+        if (st == JB_OK) st = c->check(cudaMemsetAsync(sorted, 0xFF, e_pad * 4, c->stream), "msm memset");  // holes
+    }
     if (st == JB_OK) st = c->dev_alloc((void**)&hist, nb * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&offsets, (nb + 1) * 4);
     if (st == JB_OK) st = c->dev_alloc((void**)&toff, (nb + 1) * 4);
@@ -854,11 +893,10 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
             msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
         else
             msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
-        msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq);
+        msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq, ba_levels);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
         {   // scatter, ordered in time by destination region once the destination outgrows the L2 (see the kernel)
-            const size_t entries = (size_t)p.W * n;
             int mode = 0, regions = 1;
             unsigned range_shift = 0;
             if (!by_rows && entries >= ((size_t)1 << 25)) {
@@ -867,8 +905,12 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
                     regions = p.W;
                 } else if (p.c - 1 >= 6) {
                     mode = 2;
-                    regions = entries >= ((size_t)1 << 27) ? 8 : 4;
-                    range_shift = (unsigned)(p.c - 1) - (regions == 8 ? 3u : 2u);  // nb = 2^(c-1) buckets
+                    int rl = entries >= ((size_t)1 << 27) ? 3 : 2;  // log2(regions)
+                    if (const char* e = getenv("JB_MSM_SCATTER_REGIONS_LOG")) rl = atoi(e);
+                    if (rl < 0) rl = 0;
+                    if (rl > 6) rl = 6;
+                    regions = 1 << rl;
+                    range_shift = (unsigned)(p.c - 1) - (unsigned)rl;  // nb = 2^(c-1) buckets
                 }
             }
             const dim3 sg(g, (unsigned)regions);
@@ -877,12 +919,33 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
             else
                 msm_scatter_kernel<false><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, mode, range_shift);
         }
-        msm_len_hist_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist);
-        msm_tasks_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist, task_bucket, order);
+        int tix = c->timing_begin(4, n, p.c + 100 * (int)ba_levels);  // (window bits, affine levels) for the bench's roofline
+        const uint64_t* acc_src = d_gather;
+        for (unsigned lvl = 0; lvl < ba_levels; ++lvl) {
+            // level lvl: (e_pad >> (lvl + 1)) pairs at most (the kernel reads the exact count from offsets[nb]);
+            // pairs per thread so that ~2 blocks per SM cover the level, 8..64, even (two chains per thread)
+            const size_t pairs = e_pad >> (lvl + 1);
+            size_t kp = (pairs + (size_t)BAL_BLOCK * 296 - 1) / ((size_t)BAL_BLOCK * 296);
+            kp = kp < 8 ? 8 : kp > 64 ? 64 : kp;
+            kp += kp & 1;
+            const unsigned lg = (unsigned)((pairs + BAL_BLOCK * kp - 1) / (BAL_BLOCK * kp));
+            uint64_t* dst = (lvl & 1) ? lvl_b : lvl_a;
+            if (lvl == 0)
+                msm_affine_level_kernel<true><<<lg, BAL_BLOCK, 0, c->stream>>>(d_gather, sorted, dst, ba_prefix, offsets + nb, lvl, (unsigned)kp);
+            else
+                msm_affine_level_kernel<false><<<lg, BAL_BLOCK, 0, c->stream>>>(acc_src, nullptr, dst, ba_prefix, offsets + nb, lvl, (unsigned)kp);
+            c->launches++;
+            acc_src = dst;
+        }
+        msm_len_hist_kernel<<<MSM_TASK_BLOCKS, 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist, ba_levels);
+        msm_tasks_kernel<<<MSM_TASK_BLOCKS, 256, 0, c->stream>>>(offsets, toff, nb, maxq, len_hist, task_bucket, order, ba_levels);
         c->launches++;
-        int tix = c->timing_begin(4, n, p.c);
-        msm_accumulate_kernel<<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff,
-                                                                                      task_bucket, order, nb, buckets, partial, maxq);
+        if (ba_levels)
+            msm_accumulate_kernel<true><<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(acc_src, sorted, offsets, toff, task_bucket,
+                                                                                                order, nb, buckets, partial, maxq, ba_levels);
+        else
+            msm_accumulate_kernel<false><<<(unsigned)((max_tasks + 127) / 128), 128, 0, c->stream>>>(d_gather, sorted, offsets, toff, task_bucket,
+                                                                                                 order, nb, buckets, partial, maxq, 0u);
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
         if (maxq > MSM_MAX_CHUNKS) {
@@ -924,6 +987,9 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     c->dev_free(digits);
     c->dev_free(sorted);
     c->dev_free(task_bucket);
+    if (lvl_a) c->dev_free(lvl_a);
+    if (lvl_b) c->dev_free(lvl_b);
+    if (ba_prefix) c->dev_free(ba_prefix);
     c->dev_free(order);
     c->dev_free(len_hist);
     c->dev_free(hist);

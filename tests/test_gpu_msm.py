@@ -219,3 +219,78 @@ def test_small_msm_over_precomputed_srs(sess, srs_bases, n):
     off = 100
     want2 = oracle_affine(*C.g1_msm_pippenger(srs_bases[off:off + n], sc, 0, C.max_threads()))
     assert g1_jacobian_to_affine(bases.msm(sc, offset=off)) == want2
+
+
+@pytest.fixture
+def force_affine_levels():
+    """The batched-affine levels (msm_affine.cuh) normally serve only windows x terms >= 2^26; JB_MSM_BA_MIN_LOG = 0
+    sends every field-scalar MSM that does not fit the small table through them (the library reads it per call)."""
+    import os
+    old = {k: os.environ.get(k) for k in ("JB_MSM_BA", "JB_MSM_BA_MIN_LOG")}
+    os.environ["JB_MSM_BA_MIN_LOG"] = "0"
+
+    def set_levels(levels: int):
+        os.environ["JB_MSM_BA"] = str(levels)
+    yield set_levels
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 5])
+def test_msm_batched_affine_levels_match_oracle(sess, srs_bases, force_affine_levels, levels):
+    """Same group value with the first `levels` halvings of every bucket done by batched affine additions
+    (the device form of crates/jolt-crypto/src/ec/bn254/batch_addition.rs:53-150, made complete)."""
+    force_affine_levels(levels)
+    for n in (1 << 13, (1 << 13) - 37):
+        sc = rand_limbs(0xBA + levels, n)
+        want = oracle_affine(*C.g1_msm_pippenger(srs_bases[:n], sc, 0, C.max_threads()))
+        plain = G1Bases.from_affine(sess, srs_bases[:n])
+        assert g1_jacobian_to_affine(plain.msm(sc)) == want
+        plain.free()
+        pre = G1Bases.from_affine(sess, srs_bases[:n]).precompute(10)
+        assert g1_jacobian_to_affine(pre.msm(sc)) == want
+        pre.free()
+
+
+def test_msm_batched_affine_exceptional_pairs(sess, force_affine_levels):
+    """What the reference's batch addition excludes by precondition and an MSM cannot: equal points in a pair (tangent),
+    opposite points (identity result, then an identity operand one level up), identity bases, all terms in one bucket."""
+    force_affine_levels(4)
+    n = 1 << 13
+    # every base the same point, every scalar the same: each bucket is a list of n copies of one point
+    one = [O.g1_scalar_mul(O.G1_GEN, 9)] * n
+    got = g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs(one), C.ints_to_mont([5] * n)))
+    assert got == O.g1_scalar_mul(O.G1_GEN, 9 * 5 * n)
+    # P, -P alternating with one scalar: every pair cancels
+    P = O.g1_scalar_mul(O.G1_GEN, 31)
+    alt = [P if i % 2 == 0 else O.g1_neg(P) for i in range(n)]
+    assert g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs(alt), C.ints_to_mont([77] * n))) is None
+    # a few distinct multiples repeated, identity bases mixed in, a handful of distinct scalars (crowded buckets,
+    # sums of pairs that coincide with other sums: (1 + 4) G == (2 + 3) G)
+    ks = [1, 2, 3, 4, 5, 6, 7, 8]
+    pts = [O.g1_scalar_mul(O.G1_GEN, k) for k in ks]
+    bases, mult = [], []
+    for i in range(n):
+        if i % 11 == 0:
+            bases.append(None)
+            mult.append(0)
+        else:
+            bases.append(pts[i % 8])
+            mult.append(ks[i % 8])
+    svals = [O.random_fr(5, 4)[i % 4] for i in range(n)]
+    total = sum(m * s for m, s in zip(mult, svals)) % O.R_MOD
+    got = g1_jacobian_to_affine(jolt_b200.msm(sess, g1_affine_limbs(bases), C.ints_to_mont(svals)))
+    assert got == O.g1_scalar_mul(O.G1_GEN, total)
+    # closed form over (i + 1) G with uniform scalars at 2^16, plain and precomputed
+    force_affine_levels(3)
+    n = 1 << 16
+    gen = G1Bases.generate_multiples(sess, G, n)
+    sc = rand_limbs(0x5CA1A2, n)
+    want = O.g1_scalar_mul(O.G1_GEN, _weighted_sum(sc))
+    assert g1_jacobian_to_affine(gen.msm(sc)) == want
+    gen.precompute()
+    assert g1_jacobian_to_affine(gen.msm(sc)) == want
+    gen.free()
