@@ -208,3 +208,8 @@ struct CtxGuard {
         if (!keep_resident && !ctx->runs.empty()) ctx->quiesce_resident(false);
     }
 };
+
+namespace jb {
+// msm.cu: commitments of HyperKZG's packed folded polynomials (lengths 2^(h-1) .. 2) in one pipeline pass
+int msm_halving_rows_device(jb_ctx* c, uint64_t srs, const uint64_t* d_scalars, int h, uint64_t* out_xyz);
+}  // namespace jb

@@ -326,11 +326,28 @@ int jb_hyperkzg_open(jb_ctx* c, jb_srs srs, jb_table evals, const uint64_t* poin
     }
     // ---- phase 1b: commit the intermediate polynomials (scheme.rs:141-145) ------------------------------
     {
+        // The polynomials of <= 2^15 entries (the last min(ell - 1, 15) of them) are packed back to back with halving
+        // lengths: one row-batched pass of the MSM pipeline commits them all (msm_halving_rows_device); 15 separate
+        // MSMs of that size are ~0.8 ms of launch latency each. The longer ones go one by one.
+        const int h = ell >= 3 ? (int)(ell < 16 ? ell : 16) : 0;  // tail = the polynomials of lengths 2^(h-1) .. 2
         size_t off = 0, len = n / 2;
-        for (size_t i = 1; i < ell && st == JB_OK; ++i) {
+        size_t i = 1;
+        for (; i < ell && st == JB_OK && (h == 0 || len > ((size_t)1 << (h - 1))); ++i) {
             st = jb_msm_g1_device(c, srs, 0, d_folded + 4 * off, len, out_com + 12 * (i - 1));
             off += len;
             len /= 2;
+        }
+        if (st == JB_OK && i < ell) {
+            int rs = jb::msm_halving_rows_device(c, srs, d_folded + 4 * off, h, out_com + 12 * (i - 1));
+            if (rs == JB_ERR_UNSUPPORTED) {  // no small table on this SRS handle: one by one
+                for (; i < ell && st == JB_OK; ++i) {
+                    st = jb_msm_g1_device(c, srs, 0, d_folded + 4 * off, len, out_com + 12 * (i - 1));
+                    off += len;
+                    len /= 2;
+                }
+            } else {
+                st = rs;
+            }
         }
     }
     uint64_t r_limbs[4], q_limbs[4];

@@ -36,13 +36,14 @@ namespace {
 // segment's plain sum by its first bucket number (double-and-add, ~330 products): the multiplication is per SEGMENT, so
 // short segments cost work (measured at 2^20 / 2^24 terms, precomputed SRS: 8 buckets 0.88 / 3.76 ms, 16 buckets
 // 0.55 / 2.38 ms). JB_MSM_SEG overrides (A/B).
-int msm_seg_size() {
-    static const int v = [] {
+int msm_seg_size(int buckets) {
+    static const int env = [] {
         const char* e = getenv("JB_MSM_SEG");
-        const int x = e ? atoi(e) : 16;
-        return x >= 2 && x <= 256 ? x : 16;
+        const int x = e ? atoi(e) : 0;
+        return x >= 2 && x <= 256 ? x : 0;
     }();
-    return v;
+    if (env) return env;
+    return buckets >= (1 << 21) ? 64 : 16;  // 2^24 terms (2^21 buckets): 16 / 32 / 64 = 40.6 / 40.0 / 39.7 ms per MSM; 2^20 terms: 3.17 / 3.26 / 3.61
 }
 
 struct MsmPlan {
@@ -59,7 +60,7 @@ MsmPlan plan_with(int c, int bits = 254) {
     p.W = (bits + c - 1) / c;
     if (bits - (p.W - 1) * c > c - 1) p.W += 1;  // top window: data < 2^(c-1), so data + carry <= 2^(c-1) = B
     p.B = 1 << (c - 1);
-    p.T = (p.B + msm_seg_size() - 1) / msm_seg_size();
+    p.T = (p.B + msm_seg_size(p.B) - 1) / msm_seg_size(p.B);
     return p;
 }
 
@@ -115,12 +116,18 @@ MsmPlan plan_for(size_t n, int bits = 254) {
 // as called from crates/jolt-prover-legacy/src/msm/mod.rs:27-150).
 // AGG: equal slots within a warp are counted by ONE atomic (match.any) - witness columns are skewed
 // (binary, one-hot, constants: millions of points in one bucket), and same-address atomics serialise.
+// Halving rows (HyperKZG's folded polynomials, packed back to back: lengths 2^(h-1), 2^(h-2), .., 2): term g of the
+// packed buffer belongs to row r = the number of leading ones of g as an h-bit number, at column g minus the row's
+// offset 2^h - 2^(h-r) - i.e. the low h - r - 1 bits of g.
+__device__ __forceinline__ int halving_row(unsigned g, int h) { return __clz(~(g << (32 - h))); }
+__device__ __forceinline__ unsigned halving_col(unsigned g, int h) { return g & ((1u << (h - halving_row(g, h) - 1)) - 1u); }
+
 // row_w: 0 for one MSM over n terms; otherwise the n terms are n / row_w ROWS of row_w scalars, every row against the
 // same bases[0 .. row_w) and with its own (shared-window) bucket set: slot = row * B + bucket (jb_msm_g1_rows).
 template <bool AGG>
 __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, int kind, const uint64_t* bases, size_t n, int c,
                                                          int W, int B, int shared, uint32_t* digits, unsigned int* hist,
-                                                         size_t row_w) {
+                                                         size_t row_w, int halving) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n;
     if (!AGG && !valid) return;
@@ -134,10 +141,11 @@ __global__ void __launch_bounds__(256) msm_digits_kernel(const void* scalars, in
             if (ld_small(scalars, i, kind, k.v)) flip = 0x80000000u;
         }
         // identity bases contribute nothing
-        const size_t bi = row_w ? i % row_w : i;
+        const size_t bi = halving ? halving_col((unsigned)i, halving) : row_w ? i % row_w : i;
         skip = ld_elem<Fq>(bases, 2 * bi).is_zero() && ld_elem<Fq>(bases, 2 * bi + 1).is_zero();
     }
-    const size_t row_slot = row_w && valid ? (i / row_w) * (size_t)B : 0;
+    const size_t row_slot = !valid ? 0 : halving ? (size_t)halving_row((unsigned)i, halving) * (size_t)B
+                                        : row_w ? (i / row_w) * (size_t)B : 0;
     uint32_t carry = 0;
     const uint32_t mask = (1u << c) - 1u;
     const int lane = threadIdx.x & 31;
@@ -376,7 +384,8 @@ __global__ void __launch_bounds__(256) msm_tasks_kernel(const unsigned int* offs
 template <bool AGG>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits, size_t n, int W, int B, int shared,
                                                           size_t stride, const unsigned int* offsets, unsigned int* cursor,
-                                                          uint32_t* sorted, size_t row_w, int mode, unsigned range_shift) {
+                                                          uint32_t* sorted, size_t row_w, int halving, int mode,
+                                                          unsigned range_shift) {
     // mode 0: every window in this thread. The positions are random within the destination, and a random 4-byte
     // store dirties a 32-byte sector: once the destination (4 B x windows x terms) outgrows the L2, the scatter runs at
     // the DRAM's sector rate (6.6 ms for 2^24 terms). So big MSMs order the work in TIME by destination region, one
@@ -387,8 +396,9 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
     const bool valid = i < n;
     if (!AGG && !valid) return;
     const int lane = threadIdx.x & 31;
-    const size_t row_slot = row_w && valid ? (i / row_w) * (size_t)B : 0;
-    const size_t col = row_w ? i % row_w : i;  // index into the bases / a table row
+    const size_t row_slot = !valid ? 0 : halving ? (size_t)halving_row((unsigned)i, halving) * (size_t)B
+                                        : row_w ? (i / row_w) * (size_t)B : 0;
+    const size_t col = !valid ? 0 : halving ? halving_col((unsigned)i, halving) : row_w ? i % row_w : i;  // index into the bases / a table row
     const int w_lo = mode == 1 ? (int)blockIdx.y : 0, w_hi = mode == 1 ? (int)blockIdx.y + 1 : W;
     for (int w = w_lo; w < w_hi; ++w) {
         uint32_t enc = valid ? __ldcs(&digits[(size_t)w * n + i]) : 0u;  // streaming: leave the L2 to the destination
@@ -800,11 +810,12 @@ using Guard = CtxGuard;
 // `srs`: the resident bases; terms are bases[offset .. offset + n).
 // rows > 1 (jb_msm_g1_rows): n = rows * row_w terms, row r = scalars[r * row_w ..) against bases[0 .. row_w); the
 // small table (8-bit shared windows) must cover row_w; out_xyz receives rows x 12 limbs.
+// halving = h > 0: the rows are the h - 1 packed polynomials of lengths 2^(h-1) .. 2 (n = 2^h - 2, rows = h - 1).
 int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, size_t n, uint64_t* out_xyz,
-               int kind = SK_FR, size_t rows = 1) {
+               int kind = SK_FR, size_t rows = 1, int halving = 0) {
     const int bits = small_kind_bits(kind);
     const bool by_rows = rows > 1;
-    const size_t row_w = by_rows ? n / rows : 0;
+    const size_t row_w = by_rows && !halving ? n / rows : 0;
     // (a row's bucket holds at most row_w * W points: 64 chunks bound the walk without the block-per-bucket pass)
     const unsigned maxq = (kind == SK_FR || by_rows) ? MSM_MAX_CHUNKS : MSM_MAX_CHUNKS_SMALL;
     // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
@@ -890,9 +901,9 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
         unsigned g = (unsigned)((n + 255) / 256);
         const bool agg = kind != SK_FR;
         if (agg)
-            msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
+            msm_digits_kernel<true><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w, halving);
         else
-            msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w);
+            msm_digits_kernel<false><<<g, 256, 0, c->stream>>>(d_scalars, kind, d_bases, n, p.c, p.W, p.B, shared ? 1 : 0, digits, hist, row_w, halving);
         msm_scan_local_kernel<<<scan_blocks, 1024, 0, c->stream>>>(hist, offsets, toff, nb, block_sums, maxq, ba_levels);
         msm_scan_blocks_kernel<<<1, 1024, 0, c->stream>>>(block_sums, (int)scan_blocks, offsets, toff, nb);
         msm_scan_apply_kernel<<<scan_blocks, 1024, 0, c->stream>>>(offsets, toff, nb, block_sums);
@@ -905,7 +916,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
                     regions = p.W;
                 } else if (p.c - 1 >= 6) {
                     mode = 2;
-                    int rl = entries >= ((size_t)1 << 27) ? 3 : 2;  // log2(regions)
+                    int rl = 2;  // log2(regions); measured at 2^24 terms, 12 windows: 1 / 2 / 4 / 8 / 16 regions = 41.7 / 40.5 / 39.2 / 40.6 / 44.8 ms per MSM
                     if (const char* e = getenv("JB_MSM_SCATTER_REGIONS_LOG")) rl = atoi(e);
                     if (rl < 0) rl = 0;
                     if (rl > 6) rl = 6;
@@ -915,9 +926,9 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
             }
             const dim3 sg(g, (unsigned)regions);
             if (agg)
-                msm_scatter_kernel<true><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, mode, range_shift);
+                msm_scatter_kernel<true><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, halving, mode, range_shift);
             else
-                msm_scatter_kernel<false><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, mode, range_shift);
+                msm_scatter_kernel<false><<<sg, 256, 0, c->stream>>>(digits, n, p.W, p.B, shared ? 1 : 0, pre_stride, offsets, hist, sorted, row_w, halving, mode, range_shift);
         }
         int tix = c->timing_begin(4, n, p.c + 100 * (int)ba_levels);  // (window bits, affine levels) for the bench's roofline
         const uint64_t* acc_src = d_gather;
@@ -952,7 +963,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
             msm_combine_wide_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(toff, partial, buckets);
             c->launches++;
         }
-        msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, msm_seg_size(), seg);
+        msm_segment_kernel<<<(unsigned)(((size_t)Weff * p.T + 127) / 128), 128, 0, c->stream>>>(buckets, Weff, p.B, p.T, msm_seg_size(p.B), seg);
         {   // tree-sum the T segment points of every bucket set, ping-ponging between two scratch buffers
             const uint64_t* src = seg;
             int count = p.T;
@@ -1076,6 +1087,20 @@ void identity_xyz(uint64_t out[12]) {
 }  // namespace
 
 void jb_ctx::msm_release() {}
+
+// HyperKZG open (hyperkzg.cu): the commitments of the h - 1 folded polynomials of lengths 2^(h-1) .. 2, packed back to
+// back on the device, in ONE pass of the pipeline over (polynomial, bucket) sets of the 8-bit-window table (the tail of an
+// open is 15 MSMs of <= 2^15 terms: launch latency, not work). Returns JB_ERR_UNSUPPORTED when the SRS has no small table
+// covering 2^(h-1) bases (the caller then commits them one by one). out_xyz: (h - 1) x 12 limbs.
+int jb::msm_halving_rows_device(jb_ctx* c, jb_srs h_srs, const uint64_t* d_scalars, int h, uint64_t* out_xyz) {
+    if (!c || !d_scalars || !out_xyz || h < 3 || h > 20) return JB_ERR_UNSUPPORTED;
+    Guard g(c);
+    auto it = c->srs.find(h_srs);
+    if (it == c->srs.end()) return c->fail(JB_ERR_INVALID, "unknown srs handle");
+    const Srs& srs = it->second;
+    if (!srs.pre_small || srs.pre_small_len < ((size_t)1 << (h - 1))) return JB_ERR_UNSUPPORTED;
+    return msm_device(c, srs, 0, d_scalars, ((size_t)1 << h) - 2, out_xyz, SK_FR, (size_t)(h - 1), h);
+}
 
 extern "C" {
 

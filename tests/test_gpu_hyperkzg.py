@@ -52,7 +52,7 @@ def oracle_open(srs_xy, evals_limbs, point_limbs, r_int, q_int):
 
 
 @pytest.mark.parametrize("ell,precompute", [(1, False), (2, False), (3, True), (5, False), (8, True), (11, False),
-                                            (14, False), (14, True)])
+                                            (14, False), (14, True), (4, True), (16, True), (17, True)])
 def test_open_matches_oracle(sess, ell, precompute):
     n = 1 << ell
     beta = C.ints_to_mont([O.random_fr(0x4D534D, 1)[0]])[0]

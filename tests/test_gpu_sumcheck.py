@@ -193,30 +193,32 @@ def test_sumcheck_2pow16_vs_c_oracle(sess, order):
     assert gpu.final_evals() == [C.mont_to_ints(t)[0] for t in cur]
 
 
-def test_sumcheck_2pow22_first_rounds_vs_c_oracle(sess):
-    """BASELINE config 2 size: rounds 0-2 at 2^22 (m = 2) vs the threaded C oracle, then the
-    size-independent property: all 22 rounds keep s(0)+s(1)==claim and end at prod f_j(point)."""
+@pytest.mark.parametrize("order", [LOW_TO_HIGH, HIGH_TO_LOW])
+def test_sumcheck_2pow22_every_round_vs_c_oracle(sess, order):
+    """BASELINE config 2 size: ALL 22 rounds at 2^22 (m = 2) against the threaded C oracle - every round polynomial
+    limb for limb and the final evaluations (the oracle's rounds halve, so the whole run costs two first rounds) - plus
+    the size-independent property: s(0) + s(1) == claim in every round and the run ends at prod f_j(point)."""
     n, m = 22, 2
     thr = C.max_threads()
     tabs = [rand_limbs(0xB200 + j, 1 << n) for j in range(m)]
-    gpu = ProductMember(sess, [Polynomial.new(sess, t) for t in tabs], LOW_TO_HIGH)
+    gpu = ProductMember(sess, [Polynomial.new(sess, t) for t in tabs], order)
     cur = tabs
     bind, claim = None, None
     for rnd in range(n):
-        if rnd <= 2:
-            if bind is not None:
-                cur = [C.bind(t, bind, LOW_TO_HIGH, thr) for t in cur]
-            want = C.mont_to_ints(C.product_round_evals(cur, m, LOW_TO_HIGH, thr))
-            claim = (want[0] + want[1]) % O.R_MOD if claim is None else claim
-            got = gpu.prove_round_evals(bind, rnd, claim)
-            assert got == want
-        else:
-            got = gpu.prove_round_evals(bind, rnd, claim)   # round check enforced inside the ABI
+        if bind is not None:
+            cur = [C.bind(t, bind, order, thr) for t in cur]
+        want = C.mont_to_ints(C.product_round_evals(cur, m, order, thr))
+        claim = (want[0] + want[1]) % O.R_MOD if claim is None else claim
+        assert (want[0] + want[1]) % O.R_MOD == claim, f"round {rnd}: the oracle's own round check"
+        got = gpu.prove_round_evals(bind, rnd, claim)
+        assert got == want, f"round {rnd}"
         poly = UnivariatePoly.from_evals(got)
-        bind = rand_challenge(2000 + rnd)
+        bind = rand_challenge(2000 + rnd) if rnd % 3 else rand_full(2000 + rnd)   # 125-bit challenges and full scalars mixed
         claim = poly.evaluate(F.from_limbs(bind))
+    cur = [C.bind(t, bind, order, thr) for t in cur]
     gpu.finish_rounds(bind)
     fe = gpu.final_evals()
+    assert fe == [C.mont_to_ints(t)[0] for t in cur]
     assert fe[0] * fe[1] % O.R_MOD == claim
 
 
