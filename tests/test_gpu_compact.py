@@ -243,3 +243,24 @@ def test_msm_rows_matches_row_msms(sess, srs_bases, rows, width):
     with pytest.raises(jolt_b200.JoltB200Error, match="length mismatch"):
         bases.msm_rows(np.zeros(2 * (width + 1), dtype=np.uint8), 2)
     bases.free()
+
+
+def test_msm_binary_fast_path(sess, srs_bases):
+    # from 2^14 terms a u8 / bool column is scanned once (the reference's par_iter().all(), msm/mod.rs:35-47, 96-106):
+    # all zero -> identity, all <= 1 -> msm_binary (the select-sum kernel), otherwise msm_u8
+    n = (1 << 14) + 37
+    reps = -(-n // len(srs_bases))
+    xy = np.concatenate([srs_bases] * reps)[:n].copy()     # repeated bases: P + P inside one thread's running sum
+    xy[5] = 0                                              # an identity base that is selected
+    xy[n - 1] = 0
+    bases = G1Bases.from_affine(sess, xy)
+    rng = np.random.default_rng(77)
+    for name, col in (("random", rng.integers(0, 2, size=n).astype(np.uint8)), ("bool", rng.integers(0, 2, size=n).astype(np.bool_)),
+                      ("all_ones", np.ones(n, dtype=np.uint8)), ("one_hot", np.eye(1, n, n - 3, dtype=np.uint8).reshape(-1)),
+                      ("zero", np.zeros(n, dtype=np.uint8)), ("not_binary", (rng.integers(0, 2, size=n) * 2).astype(np.uint8))):
+        vals = [int(v) for v in col]
+        vals[5] = int(col[5])
+        sc = C.ints_to_mont(vals)
+        want = oracle_affine(*C.g1_msm_pippenger(xy, sc, 0, C.max_threads()))
+        assert g1_jacobian_to_affine(bases.msm_small(col)) == want, name
+    bases.free()

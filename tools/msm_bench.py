@@ -24,7 +24,8 @@ for lg in sizes:
     pre_s = 0.0
     if "--pre" in sys.argv:
         t0 = time.perf_counter()
-        bases.precompute()
+        cw = [int(a[4:]) for a in sys.argv if a.startswith("--c=")]
+        bases.precompute(cw[0] if cw else 0)
         pre_s = time.perf_counter() - t0
     sc = C.rand_limbs(0x5CA1A2, n)
     tab = Polynomial.new(sess, sc)
