@@ -196,10 +196,16 @@ constexpr unsigned MSM_MAX_CHUNKS = 64;
 // maxq = MSM_MAX_CHUNKS for field scalars; the small-scalar kinds (a one-hot or binary column puts every
 // point into ONE bucket) raise it to MSM_MAX_CHUNKS_SMALL and fold wide buckets with a block per bucket.
 constexpr unsigned MSM_MAX_CHUNKS_SMALL = 16384;
+// `maxq` carries the task plan: the chunk cap in its low 16 bits, log2 of the smallest chunk above them (0 = MSM_CHUNK).
+// Field-scalar MSMs use 128-point chunks: at 2^24 terms with a 22-bit window a bucket holds ~96 points, and 64-point chunks
+// made two tasks, a 256-byte partial and a combine pass out of almost every bucket.
+__host__ __device__ __forceinline__ unsigned plan_cap(unsigned maxq) { return maxq & 0xffffu; }
+__host__ __device__ __forceinline__ unsigned plan_chunk(unsigned maxq) { return (maxq >> 16) ? 1u << (maxq >> 16) : MSM_CHUNK; }
 __device__ __forceinline__ unsigned chunk_count(unsigned cnt, unsigned maxq) {
     if (!cnt) return 0;
-    unsigned q = (cnt + MSM_CHUNK - 1) / MSM_CHUNK;
-    return q > maxq ? maxq : q;
+    const unsigned ch = plan_chunk(maxq), cap = plan_cap(maxq);
+    unsigned q = (cnt + ch - 1) / ch;
+    return q > cap ? cap : q;
 }
 __device__ __forceinline__ unsigned chunk_len(unsigned cnt, unsigned maxq) {
     unsigned q = chunk_count(cnt, maxq);
@@ -400,25 +406,48 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint32_t* digits
                                         : row_w ? (i / row_w) * (size_t)B : 0;
     const size_t col = !valid ? 0 : halving ? halving_col((unsigned)i, halving) : row_w ? i % row_w : i;  // index into the bases / a table row
     const int w_lo = mode == 1 ? (int)blockIdx.y : 0, w_hi = mode == 1 ? (int)blockIdx.y + 1 : W;
+    if (!AGG) {
+        // digit -> atomic on the bucket's cursor -> store is a dependent chain of L2 round trips (ncu: long_scoreboard 86 %
+        // with one window at a time); the windows of a term are independent, so eight of them are put in flight together:
+        // all the digit loads, then all the atomics and offset loads, then the stores.
+        constexpr int SW = 8;
+        for (int w0 = w_lo; w0 < w_hi; w0 += SW) {
+            uint32_t enc[SW];
+            size_t slot[SW];
+#pragma unroll
+            for (int j = 0; j < SW; ++j) enc[j] = (w0 + j < w_hi) ? __ldcs(&digits[(size_t)(w0 + j) * n + i]) : 0u;  // streaming: leave the L2 to the destination
+#pragma unroll
+            for (int j = 0; j < SW; ++j) {
+                slot[j] = (shared ? row_slot : (size_t)(w0 + j) * B) + ((enc[j] & 0x7fffffffu) - 1);
+                if (mode == 2 && enc[j] && (unsigned)(slot[j] >> range_shift) != blockIdx.y) enc[j] = 0;
+            }
+            unsigned int pos[SW], off[SW];
+#pragma unroll
+            for (int j = 0; j < SW; ++j) {
+                pos[j] = off[j] = 0;
+                if (enc[j]) {
+                    pos[j] = atomicAdd(&cursor[slot[j]], 1u);
+                    off[j] = offsets[slot[j]];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SW; ++j)
+                if (enc[j]) sorted[off[j] + pos[j]] = (uint32_t)(shared ? (size_t)(w0 + j) * stride + col : col) | (enc[j] & 0x80000000u);
+        }
+    } else
     for (int w = w_lo; w < w_hi; ++w) {
-        uint32_t enc = valid ? __ldcs(&digits[(size_t)w * n + i]) : 0u;  // streaming: leave the L2 to the destination
+        uint32_t enc = valid ? __ldcs(&digits[(size_t)w * n + i]) : 0u;
         const size_t slot = (shared ? row_slot : (size_t)w * B) + ((enc & 0x7fffffffu) - 1);
         if (mode == 2 && enc && (unsigned)(slot >> range_shift) != blockIdx.y) enc = 0;
-        unsigned int pos;
-        if (AGG) {
-            // one atomic per distinct slot in the warp; lanes take consecutive positions in lane order
-            const unsigned m = __ballot_sync(0xffffffffu, enc != 0);
-            if (!enc) continue;
-            const unsigned peers = __match_any_sync(m, (unsigned)slot);
-            const int leader = __ffs(peers) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(&cursor[slot], (unsigned)__popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            pos = offsets[slot] + base + (unsigned)__popc(peers & ((1u << lane) - 1u));
-        } else {
-            if (!enc) continue;
-            pos = offsets[slot] + atomicAdd(&cursor[slot], 1u);
-        }
+        // one atomic per distinct slot in the warp; lanes take consecutive positions in lane order
+        const unsigned m = __ballot_sync(0xffffffffu, enc != 0);
+        if (!enc) continue;
+        const unsigned peers = __match_any_sync(m, (unsigned)slot);
+        const int leader = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&cursor[slot], (unsigned)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const unsigned int pos = offsets[slot] + base + (unsigned)__popc(peers & ((1u << lane) - 1u));
         sorted[pos] = (uint32_t)(shared ? (size_t)w * stride + col : col) | (enc & 0x80000000u);
     }
 }
@@ -817,7 +846,10 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
     const bool by_rows = rows > 1;
     const size_t row_w = by_rows && !halving ? n / rows : 0;
     // (a row's bucket holds at most row_w * W points: 64 chunks bound the walk without the block-per-bucket pass)
-    const unsigned maxq = (kind == SK_FR || by_rows) ? MSM_MAX_CHUNKS : MSM_MAX_CHUNKS_SMALL;
+    // (128-point chunks only where there is parallelism to spare: a 4096-term MSM over the 128-bucket table wants
+    // its 2048 short tasks, not 1024 long ones)
+    const unsigned maxq = (kind == SK_FR || by_rows) ? (MSM_MAX_CHUNKS | (kind == SK_FR && !by_rows && n >= ((size_t)1 << 18) ? 7u << 16 : 0u))
+                                                     : MSM_MAX_CHUNKS_SMALL;
     // shared-bucket path when the SRS carries precomputed windows and the MSM is large enough for the
     // wide window's bucket reduction (2^(c-1) buckets) to be in the noise
     // Small MSMs (the tail of HyperKZG's intermediate commitments, verifier-sized MSMs) use a second, tiny
@@ -959,7 +991,7 @@ int msm_device(jb_ctx* c, const Srs& srs, size_t offset, const void* d_scalars, 
                                                                                                  order, nb, buckets, partial, maxq, 0u);
         c->timing_end(tix);
         msm_combine_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(toff, nb, partial, buckets);
-        if (maxq > MSM_MAX_CHUNKS) {
+        if (plan_cap(maxq) > MSM_MAX_CHUNKS) {
             msm_combine_wide_kernel<<<(unsigned)nb, 256, 0, c->stream>>>(toff, partial, buckets);
             c->launches++;
         }

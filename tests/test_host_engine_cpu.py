@@ -130,3 +130,25 @@ def test_host_round_cost_is_small(harness):
     res = subprocess.run([str(harness), "bench", "22"], capture_output=True, text=True, timeout=120, check=True)
     ns = json.loads(res.stdout)["host_ns_per_round"]
     assert ns < 50_000, ns          # generous: shared CI cores; typically ~1 us
+
+
+def test_sign_magnitude_records_layout():
+    """jb_s64 / jb_s128 (include/jolt_b200.h): N u64 magnitude limbs, then the sign byte (is_positive), padded to 8 -
+    the #[repr(C)] mirror of jolt_field::signed::SignedBigInt<N> (crates/jolt-field/src/signed.rs:25-32)."""
+    import numpy as np
+    from jolt_b200.api import SCALAR_KINDS, small_scalars
+    a, k, n = small_scalars([5, -7, (0, False), ((1 << 64) - 1, False)], "s64")
+    assert (k, n) == (SCALAR_KINDS["s64"], 4) and a.dtype == np.uint64 and a.shape == (4, 2) and a.nbytes == 4 * 16
+    raw = a.tobytes()
+    assert raw[0:8] == (5).to_bytes(8, "little") and raw[8] == 1 and raw[9:16] == bytes(7)
+    assert raw[16:24] == (7).to_bytes(8, "little") and raw[24] == 0          # -7: magnitude 7, is_positive = false
+    assert raw[32:40] == bytes(8) and raw[40] == 0                           # the reference's -0
+    assert raw[48:56] == b"\xff" * 8 and raw[56] == 0
+    b, k, n = small_scalars([-(1 << 100) - 3, ((1 << 128) - 1, True)], "s128")
+    assert (k, n) == (SCALAR_KINDS["s128"], 2) and b.shape == (2, 3) and b.nbytes == 2 * 24
+    raw = b.tobytes()
+    assert int.from_bytes(raw[0:16], "little") == (1 << 100) + 3 and raw[16] == 0 and raw[17:24] == bytes(7)
+    assert raw[24:40] == b"\xff" * 16 and raw[40] == 1
+    import pytest
+    with pytest.raises(ValueError):
+        small_scalars([1 << 64], "s64")
