@@ -264,3 +264,20 @@ def test_msm_binary_fast_path(sess, srs_bases):
         want = oracle_affine(*C.g1_msm_pippenger(xy, sc, 0, C.max_threads()))
         assert g1_jacobian_to_affine(bases.msm_small(col)) == want, name
     bases.free()
+
+
+@pytest.mark.parametrize("kind", ["u64", "i64", "u128", "i128", "s64", "s128"])
+def test_scalar_mul_fast_paths_match(sess, kind):
+    # crates/jolt-field/tests/bn254_differential.rs:126-152 (scalar_mul_fast_paths_match): t.mul_u64(s), mul_i64, mul_u128,
+    # mul_i128 == t * s mod r. The reference's Barrett fast paths exist to skip a Montgomery pass on the CPU; on the device
+    # the product of a field element by a primitive integer is the promotion (jb_table_upload_small) followed by the
+    # ordinary product - same VALUE, which is what the differential test pins (edges 0, 1, 2 and the type's extremes included)
+    n = 1 << 9
+    t = O.random_fr(0x7157 + len(kind), n)
+    s = column(kind, n, 17)
+    a, k = as_input(kind, s)
+    t_limbs = Polynomial.from_ints(sess, t).evals()
+    s_limbs = Polynomial.from_small(sess, a, k).evals()
+    from jolt_b200 import field as F
+    got = F.limbs_to_ints(sess.vec_op(0, 2, t_limbs, s_limbs))
+    assert got == [(x * y) % O.R_MOD for x, y in zip(t, s)]
