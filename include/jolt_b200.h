@@ -302,7 +302,9 @@ int jb_msm_g1(jb_ctx* ctx, jb_srs bases, size_t offset, const uint64_t* scalars,
  * values 0/1). `scalars`: host array of n primitive integers of `kind` (not JB_SCALAR_FR). Only
  * ceil(bits / c) windows are formed and the window is sized for the width (one 9-bit window for u8, five
  * 13-bit windows for u64); a negative scalar flips the sign of its digits. Skewed columns (one-hot, binary:
- * every point in one bucket) are cut into up to 16384 chunks per bucket. Same result conventions as jb_msm_g1. */
+ * every point in one bucket) are cut into up to 16384 chunks per bucket. A JB_SCALAR_U8 column of >= 2^14 entries is
+ * dispatched like the reference's U8Scalars arm (mod.rs:35-47, 96-106): all zero -> identity, all <= 1 -> msm_binary
+ * (the plain sum of the selected bases, no digits and no sort), else msm_u8. Same result conventions as jb_msm_g1. */
 int jb_msm_g1_small(jb_ctx* ctx, jb_srs bases, size_t offset, const void* scalars, size_t n, int kind,
                     uint64_t out_xyz[12]);
 /* VariableBaseMSM::batch_msm and batch_msm_univariate (crates/jolt-prover-legacy/src/msm/mod.rs:160-181): `count` MSMs,
