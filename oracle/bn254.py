@@ -481,6 +481,49 @@ def g1_msm_pippenger(bases, scalars, c: int | None = None):
     return total
 
 
+def signed_to_fr(magnitude: int, is_positive: bool, p: int = R_MOD) -> int:
+    """jolt_field::signed::SignedBigInt { magnitude, is_positive } (crates/jolt-field/src/signed.rs:25-32) as a field
+    value: +-magnitude mod r; "zero is not canonicalized" (:16-17), a zero magnitude with either sign is 0."""
+    return magnitude % p if is_positive else (-magnitude) % p
+
+
+def msm_small(bases, values, kind: str):
+    """The legacy small-scalar facade (crates/jolt-prover-legacy/src/msm/mod.rs:27-158): msm_u8 .. msm_i128 and
+    msm_s64 / msm_s128 take primitive (or sign-magnitude) scalars; the VALUE is the field-scalar MSM of their promotions
+    (from_u64 / from_i64 / from_u128 / from_i128, crates/jolt-field/src/bn254/mod.rs:265-298). The U8Scalars arm
+    (:35-47) and msm_u8 (:96-106) dispatch all-zero -> zero(), all <= 1 -> msm_binary, else msm_u8 - three schedules of
+    the same sum, restated here to pin that they agree. `values`: ints, or (magnitude, is_positive) pairs for s64 / s128."""
+    assert len(bases) == len(values), "msm: bases/scalars length mismatch"  # KeyLengthError, :48-50
+    if kind in ("s64", "s128"):
+        sc = [signed_to_fr(*v) if isinstance(v, tuple) else v % R_MOD for v in values]
+    else:
+        sc = [v % R_MOD for v in values]
+    if kind == "u8":
+        if all(v == 0 for v in values):
+            return None                                  # Self::zero()
+        if all(v <= 1 for v in values):                  # msm_binary: the plain sum of the selected bases
+            acc = None
+            for P, v in zip(bases, values):
+                if v:
+                    acc = g1_add(acc, P)
+            return acc
+    return g1_msm_naive(bases, sc)
+
+
+def batch_msm(bases, columns):
+    """VariableBaseMSM::batch_msm (msm/mod.rs:160-168): column k against the PREFIX bases[..len(column k)].
+    columns: (values, kind) pairs."""
+    return [msm_small(bases[: len(vals)], vals, kind) for vals, kind in columns]
+
+
+def msm_rows(bases, matrix, rows: int, kind: str):
+    """Dory tier-1 row commitments (crates/jolt-dory/src/streaming.rs:113-201): one MSM per matrix row against the same
+    bases[..row_width]."""
+    w = len(matrix) // rows
+    assert w * rows == len(matrix)
+    return [msm_small(bases[:w], matrix[r * w:(r + 1) * w], kind) for r in range(rows)]
+
+
 def batch_g1_additions_multi_affine(bases, indices_sets, q: int = Q_MOD):
     """crates/jolt-crypto/src/ec/bn254/batch_addition.rs:53-150: one affine sum per index set. Every level pairs
     neighbours (2j, 2j + 1) of each working set, all pairs of a level share one batch inversion (ark_ff's
