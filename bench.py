@@ -402,20 +402,23 @@ def kernels_section(sess, peak_hbm: float, with_cpu: bool):
                      "accumulate_kernel_ms": "batched-affine levels (if any) + the XYZZ accumulation kernel", "runs": msms}
 
     # ---- row-batched small-scalar MSM (Dory tier-1 rows) and a binary column ---------------------
-    rows_n, row_w = 1024, 4096
-    bases = G1Bases.generate_multiples(sess, G, 1 << 22)
-    rngm = np.random.Generator(np.random.PCG64(0xD0))
-    mat = rngm.integers(0, 1 << 64, size=rows_n * row_w, dtype=np.uint64)
-    bases.msm_rows(mat, rows_n)  # builds the 8-bit window table of the first row_w bases once
-    t_rows = timed(lambda a: bases.msm_rows(mat, rows_n), reps=3)
-    t_loop = timed(lambda a: [bases.msm_small(mat[r * row_w:(r + 1) * row_w]) for r in range(16)], reps=2) / 16 * rows_n
-    bits = rngm.integers(0, 2, size=1 << 22, dtype=np.uint8)
-    bases.msm_small(bits)
-    t_bin = timed(lambda a: bases.msm_small(bits), reps=3)
-    out["msm_rows_u64_1024x4096"] = {"ms": t_rows, "terms_per_s": rows_n * row_w / (t_rows * 1e-3), "row_by_row_ms_extrapolated_from_16_rows": t_loop,
-                                     "note": "jb_msm_g1_rows: host scalars (H2D of 8 B/term inside), one pipeline pass over (row, bucket) sets"}
-    out["msm_binary_2^22"] = {"ms": t_bin, "terms_per_s": (1 << 22) / (t_bin * 1e-3), "note": "msm_binary arm: host flags (1 B/term H2D inside), select-sum kernel"}
-    bases.free()
+    try:
+        rows_n, row_w = 1024, 4096
+        bases = G1Bases.generate_multiples(sess, G, 1 << 22)
+        rngm = np.random.Generator(np.random.PCG64(0xD0))
+        mat = rngm.integers(0, 1 << 64, size=rows_n * row_w, dtype=np.uint64)
+        bases.msm_rows(mat, rows_n)  # builds the 8-bit window table of the first row_w bases once
+        t_rows = timed(lambda a: bases.msm_rows(mat, rows_n), reps=3)
+        t_loop = timed(lambda a: [bases.msm_small(mat[r * row_w:(r + 1) * row_w]) for r in range(16)], reps=2) / 16 * rows_n
+        bits = rngm.integers(0, 2, size=1 << 22, dtype=np.uint8)
+        bases.msm_small(bits)
+        t_bin = timed(lambda a: bases.msm_small(bits), reps=3)
+        out["msm_rows_u64_1024x4096"] = {"ms": t_rows, "terms_per_s": rows_n * row_w / (t_rows * 1e-3), "row_by_row_ms_extrapolated_from_16_rows": t_loop,
+                                         "note": "jb_msm_g1_rows: host scalars (H2D of 8 B/term inside), one pipeline pass over (row, bucket) sets"}
+        out["msm_binary_2^22"] = {"ms": t_bin, "terms_per_s": (1 << 22) / (t_bin * 1e-3), "note": "msm_binary arm: host flags (1 B/term H2D inside), select-sum kernel"}
+        bases.free()
+    except Exception as e:  # secondary lines: report, do not fail the bench
+        out["msm_rows_u64_1024x4096"] = {"skipped": str(e)}
 
     # ---- HyperKZG open, ell = 22 (precomputed SRS) ----------------------------------------------
     ell = 22
